@@ -1,0 +1,193 @@
+// C-ABI entry points: error plumbing, the sequence encoder (news / user encoder)
+// forward + backward composed from the kernels of this directory, and test exports.
+#include <stdarg.h>
+
+#include "ebk_common.cuh"
+
+namespace ebk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int gemm_dispatch(int math, const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc,
+                  int M, int N, int K, float beta, cudaStream_t st) {
+  if (math == EBK_MATH_TF32) return gemm_tf32(A, B, ldb, transB, C, ldc, M, N, K, beta, st);
+  if (math == EBK_MATH_FP32) return gemm_f32(A, B, ldb, transB, C, ldc, M, N, K, beta, st);
+  set_error("unknown math mode %d", math);
+  return EBK_ERR_INVALID;
+}
+
+namespace {
+
+// Workspace of one sequence-encoder call.  Saved activations first, backward scratch after.
+struct SeqWs {
+  float *qkv, *y0, *hbuf, *w;          // saved by forward
+  float *dy, *dpre, *da, *dqkv, *dx;   // backward scratch
+  float* colsum;                       // column-sum partials
+  size_t bytes;
+};
+
+SeqWs seq_layout(const ebk_seqenc_desc& d, void* base) {
+  const size_t R = (size_t)d.n_seq * d.L, D = (size_t)d.nh * d.dh;
+  size_t off = 0;
+  auto take = [&](size_t nfloat) {
+    float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+    off += align_up(nfloat * sizeof(float), 256);
+    return p;
+  };
+  SeqWs w;
+  w.qkv = take(R * 3 * D);
+  w.y0 = take(R * D);
+  w.hbuf = take(R * d.att);
+  w.w = take(R);
+  w.dy = take(R * D);
+  w.dpre = take(R * d.att);
+  w.da = take(R);
+  w.dqkv = take(R * 3 * D);
+  w.dx = take(R * (size_t)d.Din);
+  w.colsum = take(colsum_partial_floats((int)R, d.att));
+  w.bytes = off;
+  return w;
+}
+
+int check_desc(const ebk_seqenc_desc* d) {
+  EBK_CHECK_ARG(d != nullptr, "seqenc: null descriptor");
+  EBK_CHECK_ARG(d->n_seq >= 0 && d->L >= 1 && d->L <= 64, "seqenc: need n_seq>=0, 1<=L<=64 (n_seq=%d L=%d)", d->n_seq, d->L);
+  EBK_CHECK_ARG(d->Din >= 4 && d->Din % 4 == 0, "seqenc: Din=%d must be a positive multiple of 4", d->Din);
+  EBK_CHECK_ARG(d->nh >= 1 && d->dh >= 1 && d->dh <= 32, "seqenc: need nh>=1, 1<=dh<=32 (nh=%d dh=%d)", d->nh, d->dh);
+  EBK_CHECK_ARG((d->nh * d->dh) % 4 == 0, "seqenc: D=nh*dh=%d must be a multiple of 4", d->nh * d->dh);
+  EBK_CHECK_ARG(d->att >= 1, "seqenc: att=%d", d->att);
+  EBK_CHECK_ARG(d->dropout >= 0.0f && d->dropout < 1.0f, "seqenc: dropout=%f outside [0,1)", d->dropout);
+  EBK_CHECK_ARG((long)d->n_seq * d->L < (1L << 31), "seqenc: n_seq*L overflows int32");
+  return EBK_OK;
+}
+
+}  // namespace
+}  // namespace ebk
+
+using namespace ebk;
+
+extern "C" const char* ebk_last_error(void) { return g_err; }
+extern "C" int ebk_version(void) { return 100; }
+
+extern "C" int ebk_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+  return p.major == 10 ? 1 : 0;
+}
+
+extern "C" size_t ebk_seqenc_workspace_bytes(const ebk_seqenc_desc* d) {
+  if (check_desc(d) != EBK_OK) return 0;
+  return seq_layout(*d, nullptr).bytes;
+}
+
+extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, const float* table_or_x,
+                              const float* Wqkv, const float* attW, const float* attb, const float* attq,
+                              int training, uint64_t seed1, uint64_t seed2, void* workspace,
+                              size_t workspace_bytes, float* out, void* stream) {
+  EBK_TRY(check_desc(d));
+  if (d->n_seq == 0) return EBK_OK;
+  EBK_CHECK_ARG(table_or_x && Wqkv && attW && attb && attq && out && workspace, "seqenc_fwd: null pointer");
+  EBK_CHECK_ARG(tok == nullptr || d->V >= 1, "seqenc_fwd: V=%d with a token gather", d->V);
+  EBK_CHECK_ARG(tok != nullptr || !(training && d->dropout > 0.0f), "seqenc_fwd: dropout on a dense input is not supported");
+  SeqWs ws = seq_layout(*d, workspace);
+  if (workspace_bytes < ws.bytes) {
+    set_error("seqenc_fwd: workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
+    return EBK_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = d->n_seq * d->L, D = d->nh * d->dh;
+  const Dropout drop1 = make_dropout(training != 0, d->dropout, seed1);
+  const Dropout drop2 = make_dropout(training != 0, d->dropout, seed2);
+  const Dropout none = make_dropout(false, 0.0f, 0);
+
+  // (1) Q|K|V = dropout1(gather(table, tok)) . Wqkv        nrms.py:134-139, layers.py:214-230
+  GemmOperandA ax{table_or_x, d->Din, false, tok, d->V, tok ? drop1 : none, d->Din};
+  EBK_TRY(gemm_dispatch(d->math, ax, Wqkv, 3 * D, false, ws.qkv, 3 * D, R, 3 * D, d->Din, 0.0f, st));
+  // (2) per-head softmax(QK^T/sqrt(dh)) and the adjoint product    layers.py:231-252
+  EBK_TRY(attention_core_fwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st));
+  // (3) pre-activation of AttLayer2: dropout2(Y0) . W              nrms.py:153-156, layers.py:65
+  GemmOperandA ay{ws.y0, D, false, nullptr, 0, drop2, D};
+  EBK_TRY(gemm_dispatch(d->math, ay, attW, d->att, false, ws.hbuf, d->att, R, d->att, D, 0.0f, st));
+  // (4) tanh, .q, exp, normalise (+1e-7), pool                     layers.py:65-81
+  EBK_TRY(attpool_fwd(d->n_seq, d->L, D, d->att, ws.y0, drop2, ws.hbuf, attb, attq, ws.w, out, st));
+  return EBK_OK;
+}
+
+extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, const float* table_or_x,
+                              const float* Wqkv, const float* attW, const float* attb, const float* attq,
+                              int training, uint64_t seed1, uint64_t seed2, void* workspace,
+                              size_t workspace_bytes, const float* d_out, float* dWqkv, float* dattW,
+                              float* dattb, float* dattq, float* d_table, float* d_x, void* stream) {
+  EBK_TRY(check_desc(d));
+  if (d->n_seq == 0) return EBK_OK;
+  (void)attb;
+  EBK_CHECK_ARG(table_or_x && Wqkv && attW && attq && d_out && workspace, "seqenc_bwd: null pointer");
+  EBK_CHECK_ARG(dWqkv && dattW && dattb && dattq, "seqenc_bwd: null parameter-gradient pointer");
+  EBK_CHECK_ARG(tok == nullptr || d_x == nullptr, "seqenc_bwd: d_x must be NULL when tokens are gathered");
+  EBK_CHECK_ARG(tok != nullptr || d_table == nullptr, "seqenc_bwd: d_table needs token ids");
+  EBK_CHECK_ARG(tok != nullptr || !(training && d->dropout > 0.0f), "seqenc_bwd: dropout on a dense input is not supported");
+  SeqWs ws = seq_layout(*d, workspace);
+  if (workspace_bytes < ws.bytes) {
+    set_error("seqenc_bwd: workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
+    return EBK_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = d->n_seq * d->L, D = d->nh * d->dh;
+  const Dropout drop1 = make_dropout(training != 0, d->dropout, seed1);
+  const Dropout drop2 = make_dropout(training != 0, d->dropout, seed2);
+  const Dropout none = make_dropout(false, 0.0f, 0);
+
+  // AttLayer2 backward (layers.py:55-81)
+  EBK_TRY(attpool_bwd(d->n_seq, d->L, D, d->att, ws.y0, drop2, ws.hbuf, attq, ws.w, d_out, ws.da, ws.dpre,
+                      ws.dy, st));
+  EBK_TRY(colsum_accum_ws(R, d->att, ws.hbuf, d->att, ws.da, dattq, ws.colsum, st));   // dq = sum_r h_r da_r
+  EBK_TRY(colsum_accum_ws(R, d->att, ws.dpre, d->att, nullptr, dattb, ws.colsum, st)); // db = sum_r dpre_r
+  GemmOperandA ayT{ws.y0, D, true, nullptr, 0, drop2, D};                              // dW += X^T dpre
+  EBK_TRY(gemm_dispatch(d->math, ayT, ws.dpre, d->att, false, dattW, d->att, D, d->att, R, 1.0f, st));
+  GemmOperandA adp{ws.dpre, d->att, false, nullptr, 0, none, 0};                       // dX += dpre W^T
+  EBK_TRY(gemm_dispatch(d->math, adp, attW, d->att, true, ws.dy, D, R, D, d->att, 1.0f, st));
+  // SelfAttention core backward (dropout2 mask applied while reading dy)
+  EBK_TRY(attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, st));
+  // dWqkv += X^T dQKV  (X = dropout1(gather))
+  GemmOperandA axT{table_or_x, d->Din, true, tok, d->V, tok ? drop1 : none, d->Din};
+  EBK_TRY(gemm_dispatch(d->math, axT, ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din, 3 * D, R, 1.0f, st));
+  // dX = dQKV Wqkv^T
+  if (tok != nullptr ? (d_table != nullptr) : (d_x != nullptr)) {
+    float* dx = tok ? ws.dx : d_x;
+    GemmOperandA adq{ws.dqkv, 3 * D, false, nullptr, 0, none, 0};
+    EBK_TRY(gemm_dispatch(d->math, adq, Wqkv, 3 * D, true, dx, d->Din, R, d->Din, 3 * D, 0.0f, st));
+    if (tok) EBK_TRY(scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
+  }
+  return EBK_OK;
+}
+
+extern "C" int ebk_gemm(int32_t math, int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K,
+                        const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
+                        float beta, void* stream) {
+  EBK_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && A && B && C, "gemm: bad argument");
+  GemmOperandA a{A, lda, transA != 0, nullptr, 0, make_dropout(false, 0.0f, 0), 0};
+  return gemm_dispatch(math, a, B, ldb, transB != 0, C, ldc, M, N, K, beta, (cudaStream_t)stream);
+}
+
+extern "C" int ebk_attention_core_fwd(int32_t n_seq, int32_t L, int32_t nh, int32_t dh, const float* qkv,
+                                      float* y, void* stream) {
+  EBK_CHECK_ARG(qkv && y, "attention_core_fwd: null pointer");
+  return attention_core_fwd(n_seq, L, nh, dh, qkv, y, (cudaStream_t)stream);
+}
+
+extern "C" int ebk_attention_core_bwd(int32_t n_seq, int32_t L, int32_t nh, int32_t dh, const float* qkv,
+                                      const float* dy, float drop_p, uint64_t drop_seed, float* dqkv,
+                                      void* stream) {
+  EBK_CHECK_ARG(qkv && dy && dqkv, "attention_core_bwd: null pointer");
+  return attention_core_bwd(n_seq, L, nh, dh, qkv, dy, make_dropout(drop_p > 0.0f, drop_p, drop_seed), dqkv,
+                            (cudaStream_t)stream);
+}

@@ -1,0 +1,204 @@
+// AttLayer2 (reference layers.py:55-81) around the GEMM X.W:
+//   h = tanh(X W + b); a = h q; e = exp(a) (NO max subtraction); w = e/(sum e + 1e-7); y = sum_t w_t X_t
+// X = dropout2(Y0) is recomputed from the saved attention output and the counter-based mask.
+// One CTA per sequence; also the column-sum and embedding-row scatter helpers.
+#include "ebk_common.cuh"
+
+namespace ebk {
+namespace {
+
+constexpr int PT = 128;  // threads per CTA
+constexpr float K_EPS = 1e-7f;  // keras.backend.epsilon()
+
+// hbuf [R, att]: in = X W (pre-activation without bias), out = tanh(. + b)
+__global__ void __launch_bounds__(PT) attpool_fwd_kernel(int L, int D, int att, const float* __restrict__ y0,
+                                                          Dropout drop, float* __restrict__ hbuf,
+                                                          const float* __restrict__ attb,
+                                                          const float* __restrict__ attq,
+                                                          float* __restrict__ w, float* __restrict__ out) {
+  __shared__ float a_s[64];
+  __shared__ float w_s[64];
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = PT / 32;
+  for (int t = warp; t < L; t += nwarp) {
+    float* hrow = hbuf + ((long)n * L + t) * att;
+    float acc = 0.0f;
+    for (int j = lane; j < att; j += 32) {
+      float h = tanhf(hrow[j] + attb[j]);
+      hrow[j] = h;
+      acc = fmaf(h, attq[j], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) a_s[t] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float s = 0.0f;
+    for (int t = lane; t < L; t += 32) {
+      float e = expf(a_s[t]);  // layers.py:70-71: plain exp
+      w_s[t] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    float r = 1.0f / (s + K_EPS);  // layers.py:75-77
+    for (int t = lane; t < L; t += 32) {
+      float ww = w_s[t] * r;
+      w_s[t] = ww;
+      w[(long)n * L + t] = ww;
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += PT) {
+    float acc = 0.0f;
+    for (int t = 0; t < L; ++t) {
+      long r = (long)n * L + t;
+      float x = y0[r * D + d];
+      if (drop.on()) x *= drop.factor((uint64_t)r * (uint64_t)D + (uint64_t)d);
+      acc = fmaf(w_s[t], x, acc);
+    }
+    out[(long)n * D + d] = acc;
+  }
+}
+
+// dy[r,:] = w_r * d_out[n,:]   (the dpre.W^T term is added afterwards by a beta=1 GEMM)
+// da[r]   = w_r (dw_r - sum_j w_j dw_j),  dw_r = X_r . d_out[n]
+// dpre[r,j] = da_r q_j (1 - h_rj^2)
+__global__ void __launch_bounds__(PT) attpool_bwd_kernel(int L, int D, int att, const float* __restrict__ y0,
+                                                          Dropout drop, const float* __restrict__ hbuf,
+                                                          const float* __restrict__ attq,
+                                                          const float* __restrict__ w,
+                                                          const float* __restrict__ d_out,
+                                                          float* __restrict__ da, float* __restrict__ dpre,
+                                                          float* __restrict__ dy) {
+  __shared__ float dw_s[64];
+  __shared__ float da_s[64];
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = PT / 32;
+  const float* g = d_out + (long)n * D;
+  for (int t = warp; t < L; t += nwarp) {
+    long r = (long)n * L + t;
+    float wt = w[r];
+    float acc = 0.0f;
+    for (int d = lane; d < D; d += 32) {
+      float x = y0[r * D + d];
+      if (drop.on()) x *= drop.factor((uint64_t)r * (uint64_t)D + (uint64_t)d);
+      float gd = g[d];
+      acc = fmaf(x, gd, acc);
+      dy[r * D + d] = wt * gd;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) dw_s[t] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float s = 0.0f;
+    for (int t = lane; t < L; t += 32) s = fmaf(w[(long)n * L + t], dw_s[t], s);
+    s = warp_sum(s);
+    for (int t = lane; t < L; t += 32) {
+      float v = w[(long)n * L + t] * (dw_s[t] - s);
+      da_s[t] = v;
+      da[(long)n * L + t] = v;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L * att; i += PT) {
+    int t = i / att, j = i % att;
+    long r = (long)n * L + t;
+    float h = hbuf[r * att + j];
+    dpre[r * att + j] = da_s[t] * attq[j] * (1.0f - h * h);
+  }
+}
+
+// Two-stage deterministic column reduction: partial[blk, j] then out[j] += sum_blk.
+constexpr int CS_ROWS = 256;
+__global__ void colsum_partial_kernel(int R, int Ncols, const float* __restrict__ X, int ldx,
+                                      const float* __restrict__ coef, float* __restrict__ partial) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Ncols) return;
+  int r0 = blockIdx.y * CS_ROWS, r1 = min(R, r0 + CS_ROWS);
+  float acc = 0.0f;
+  for (int r = r0; r < r1; ++r) {
+    float x = X[(long)r * ldx + j];
+    acc = coef ? fmaf(coef[r], x, acc) : acc + x;
+  }
+  partial[(long)blockIdx.y * Ncols + j] = acc;
+}
+__global__ void colsum_final_kernel(int nblk, int Ncols, const float* __restrict__ partial,
+                                    float* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Ncols) return;
+  float acc = 0.0f;
+  for (int b = 0; b < nblk; ++b) acc += partial[(long)b * Ncols + j];
+  out[j] += acc;
+}
+
+__global__ void scatter_rows_add_kernel(int R, int E4, int V, const int32_t* __restrict__ tok,
+                                        const float4* __restrict__ dX, Dropout drop,
+                                        float* __restrict__ d_table) {
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)R * E4) return;
+  int r = (int)(i / E4), c4 = (int)(i % E4);
+  int t = tok[r];
+  if (t < 0 || t >= V) return;
+  float4 g = dX[i];
+  if (drop.on()) {
+    float4 f = drop.factor4((uint64_t)i * 4ull);
+    g.x *= f.x; g.y *= f.y; g.z *= f.z; g.w *= f.w;
+  }
+  float* dst = d_table + ((long)t * E4 + c4) * 4;
+  // 128-bit vector reduction (sm_90+): one L2 atomic transaction for 4 floats
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g.x), "f"(g.y), "f"(g.z),
+               "f"(g.w)
+               : "memory");
+}
+
+}  // namespace
+
+int attpool_fwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, float* hbuf, const float* attb,
+                const float* attq, float* w, float* out, cudaStream_t st) {
+  if (n_seq <= 0) return EBK_OK;
+  EBK_CHECK_ARG(L <= 64, "attpool: L=%d > 64", L);
+  attpool_fwd_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, drop, hbuf, attb, attq, w, out);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+int attpool_bwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, const float* hbuf,
+                const float* attq, const float* w, const float* d_out, float* da, float* dpre, float* dy,
+                cudaStream_t st) {
+  if (n_seq <= 0) return EBK_OK;
+  EBK_CHECK_ARG(L <= 64, "attpool: L=%d > 64", L);
+  attpool_bwd_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, drop, hbuf, attq, w, d_out, da, dpre, dy);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+// scratch for colsum partials: a small static device buffer per process would break
+// re-entrancy, so the caller passes it through the workspace (see api.cu); this variant
+// takes it explicitly.
+int colsum_accum_ws(int R, int Ncols, const float* X, int ldx, const float* coef, float* out, float* partial,
+                    cudaStream_t st) {
+  if (R <= 0 || Ncols <= 0) return EBK_OK;
+  int nblk = ceil_div(R, CS_ROWS);
+  dim3 grid(ceil_div(Ncols, 128), nblk);
+  colsum_partial_kernel<<<grid, 128, 0, st>>>(R, Ncols, X, ldx, coef, partial);
+  EBK_LAUNCH_CHECK();
+  colsum_final_kernel<<<ceil_div(Ncols, 128), 128, 0, st>>>(nblk, Ncols, partial, out);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+size_t colsum_partial_floats(int R, int Ncols) { return (size_t)ceil_div(R, CS_ROWS) * (size_t)Ncols; }
+
+int scatter_rows_add(int R, int E, int V, const int32_t* tok, const float* dX, Dropout drop, float* d_table,
+                     cudaStream_t st) {
+  if (R <= 0) return EBK_OK;
+  EBK_CHECK_ARG(E % 4 == 0, "scatter: E=%d must be a multiple of 4", E);
+  long n = (long)R * (E / 4);
+  scatter_rows_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R, E / 4, V, tok,
+                                                                       reinterpret_cast<const float4*>(dX), drop,
+                                                                       d_table);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+}  // namespace ebk

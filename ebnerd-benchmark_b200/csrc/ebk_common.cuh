@@ -1,0 +1,146 @@
+// Shared helpers for the ebk kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ebk.h"
+
+namespace ebk {
+
+// ---- error plumbing -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define EBK_CHECK_ARG(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      ::ebk::set_error(__VA_ARGS__);        \
+      return EBK_ERR_INVALID;               \
+    }                                       \
+  } while (0)
+
+#define EBK_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      ::ebk::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return EBK_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+#define EBK_LAUNCH_CHECK() EBK_CUDA(cudaGetLastError())
+
+#define EBK_TRY(call)              \
+  do {                             \
+    int s__ = (call);              \
+    if (s__ != EBK_OK) return s__; \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- counter-based dropout (mirrors oracle/nrms_oracle.py::dropout_keep_mask) ----------
+// group g = idx >> 2 draws r = mix64(seed + (g+1)*GOLDEN); lane j = idx & 3 uses bits
+// [16j,16j+16); element kept iff bits >= thr, thr = floor(p*65536 + 0.5).
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t dropout_group_bits(uint64_t seed, uint64_t group) {
+  return mix64(seed + (group + 1ull) * 0x9E3779B97F4A7C15ull);
+}
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
+  return (uint32_t)floorf(p * 65536.0f + 0.5f);
+}
+// keep flag for a single element
+__host__ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t thr) {
+  uint64_t r = dropout_group_bits(seed, idx >> 2);
+  return (uint32_t)((r >> ((idx & 3ull) * 16ull)) & 0xFFFFull) >= thr;
+}
+
+struct Dropout {
+  uint64_t seed;
+  uint32_t thr;   // 0 => disabled
+  float scale;    // 1/(1-p)
+  __host__ __device__ bool on() const { return thr != 0; }
+  // scale factor (0 or 1/(1-p)) of element idx
+  __device__ __forceinline__ float factor(uint64_t idx) const {
+    return dropout_keep(seed, idx, thr) ? scale : 0.0f;
+  }
+  // factors of the 4 elements of an aligned group starting at idx (idx % 4 == 0)
+  __device__ __forceinline__ float4 factor4(uint64_t idx) const {
+    uint64_t r = dropout_group_bits(seed, idx >> 2);
+    float4 f;
+    f.x = ((uint32_t)(r & 0xFFFF) >= thr) ? scale : 0.0f;
+    f.y = ((uint32_t)((r >> 16) & 0xFFFF) >= thr) ? scale : 0.0f;
+    f.z = ((uint32_t)((r >> 32) & 0xFFFF) >= thr) ? scale : 0.0f;
+    f.w = ((uint32_t)((r >> 48) & 0xFFFF) >= thr) ? scale : 0.0f;
+    return f;
+  }
+};
+static inline Dropout make_dropout(bool training, float p, uint64_t seed) {
+  Dropout d;
+  d.seed = seed;
+  if (training && p > 0.0f) {
+    d.thr = dropout_threshold(p);
+    d.scale = 1.0f / (1.0f - p);
+  } else {
+    d.thr = 0;
+    d.scale = 1.0f;
+  }
+  return d;
+}
+
+// ---- warp helpers ---------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- internal launchers shared between translation units ---------------------------------
+struct GemmOperandA {
+  const float* ptr;       // storage [rows, lda]
+  int lda;
+  bool trans;             // false: A(m,k)=S(m,k); true: A(m,k)=S(k,m)  (S = storage)
+  const int32_t* gather;  // optional: storage row s is read from row gather[s]
+  int gather_limit;       // rows outside [0, limit) read as zero
+  Dropout drop;           // optional dropout on S(s,c) with element index s*drop_ld + c
+  int drop_ld;
+};
+
+int gemm_f32(const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc,
+             int M, int N, int K, float beta, cudaStream_t st);
+int gemm_tf32(const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc,
+              int M, int N, int K, float beta, cudaStream_t st);
+int gemm_dispatch(int math, const GemmOperandA& A, const float* B, int ldb, bool transB, float* C,
+                  int ldc, int M, int N, int K, float beta, cudaStream_t st);
+
+int attention_core_fwd(int n_seq, int L, int nh, int dh, const float* qkv, float* y, cudaStream_t st);
+int attention_core_bwd(int n_seq, int L, int nh, int dh, const float* qkv, const float* dy,
+                       Dropout drop, float* dqkv, cudaStream_t st);
+
+// AttLayer2 pieces
+int attpool_fwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, float* hbuf /*[R,att] in: pre-act, out: tanh*/,
+                const float* attb, const float* attq, float* w /*[R]*/, float* out /*[n_seq,D]*/, cudaStream_t st);
+int attpool_bwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, const float* hbuf,
+                const float* attq, const float* w, const float* d_out, float* da /*[R]*/,
+                float* dpre /*[R,att]*/, float* dy /*[R,D] = w_t*d_out*/, cudaStream_t st);
+// column sums: out[j] += sum_r coef[r] * X[r,j]   (coef may be NULL => 1); deterministic
+// two-stage reduction through `partial` (colsum_partial_floats(R, Ncols) floats of scratch)
+int colsum_accum_ws(int R, int Ncols, const float* X, int ldx, const float* coef, float* out, float* partial,
+                    cudaStream_t st);
+size_t colsum_partial_floats(int R, int Ncols);
+
+// d_table[tok[r], :] += dX[r, :] * dropout(r*E + e)
+int scatter_rows_add(int R, int E, int V, const int32_t* tok, const float* dX, Dropout drop,
+                     float* d_table, cudaStream_t st);
+
+}  // namespace ebk

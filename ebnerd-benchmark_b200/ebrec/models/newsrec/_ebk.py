@@ -1,0 +1,102 @@
+"""ctypes binding of libebk.so (the C-ABI declared in include/ebk.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or the device is not
+a CC 10.x (sm_100a) part, every compute entry point raises.  Tensors cross the boundary
+as raw device pointers (``tensor.data_ptr()``) plus explicit shapes; the stream is
+torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_PKG_ROOT = Path(__file__).resolve().parents[3]  # .../ebnerd-benchmark_b200
+LIB_PATH = Path(os.environ.get("EBK_LIB", _PKG_ROOT / "csrc" / "libebk.so"))
+
+MATH_FP32 = 0
+MATH_TF32 = 1
+
+SYMBOLS = [
+    "ebk_last_error", "ebk_version", "ebk_device_ok",
+    "ebk_seqenc_workspace_bytes", "ebk_seqenc_fwd", "ebk_seqenc_bwd",
+    "ebk_score_softmax_ce", "ebk_score_sigmoid", "ebk_adam_keras_step",
+    "ebk_gemm", "ebk_attention_core_fwd", "ebk_attention_core_bwd", "ebk_dropout_mask",
+]
+
+
+class EbkError(RuntimeError):
+    pass
+
+
+class SeqEncDesc(C.Structure):
+    """Mirror of ebk_seqenc_desc (include/ebk.h)."""
+    _fields_ = [
+        ("n_seq", C.c_int32), ("L", C.c_int32), ("Din", C.c_int32), ("nh", C.c_int32),
+        ("dh", C.c_int32), ("att", C.c_int32), ("V", C.c_int32), ("dropout", C.c_float),
+        ("math", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libebk.so once; raise loudly if it is absent (no CPU/PyTorch fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise EbkError(
+            f"CUDA extension {LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"(or `make -C {LIB_PATH.parent}`); there is no CPU fallback.")
+    l = C.CDLL(str(LIB_PATH))
+    vp, i32, u64, f32, f64, sz = C.c_void_p, C.c_int32, C.c_uint64, C.c_float, C.c_double, C.c_size_t
+    dp = C.POINTER(SeqEncDesc)
+    l.ebk_last_error.restype = C.c_char_p
+    l.ebk_last_error.argtypes = []
+    l.ebk_version.restype = C.c_int
+    l.ebk_device_ok.restype = C.c_int
+    l.ebk_seqenc_workspace_bytes.restype = sz
+    l.ebk_seqenc_workspace_bytes.argtypes = [dp]
+    l.ebk_seqenc_fwd.argtypes = [dp, vp, vp, vp, vp, vp, vp, C.c_int, u64, u64, vp, sz, vp, vp]
+    l.ebk_seqenc_bwd.argtypes = [dp, vp, vp, vp, vp, vp, vp, C.c_int, u64, u64, vp, sz, vp,
+                                 vp, vp, vp, vp, vp, vp, vp]
+    l.ebk_score_softmax_ce.argtypes = [i32, i32, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp]
+    l.ebk_score_sigmoid.argtypes = [i32, i32, i32, vp, vp, vp, vp]
+    l.ebk_adam_keras_step.argtypes = [vp, vp, vp, vp, sz, f32, f64, f64, f32, C.c_int, vp]
+    l.ebk_gemm.argtypes = [i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, f32, vp]
+    l.ebk_attention_core_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp]
+    l.ebk_attention_core_bwd.argtypes = [i32, i32, i32, i32, vp, vp, f32, u64, vp, vp]
+    l.ebk_dropout_mask.argtypes = [u64, f32, sz, vp, vp]
+    for name in SYMBOLS:
+        fn = getattr(l, name)
+        if name not in ("ebk_last_error", "ebk_seqenc_workspace_bytes"):
+            fn.restype = C.c_int
+    _lib = l
+    return l
+
+
+def require_device() -> None:
+    if not torch.cuda.is_available():
+        raise EbkError("no CUDA device: the ebk hot path is sm_100a-only and has no CPU fallback")
+    if not lib().ebk_device_ok():
+        raise EbkError("current CUDA device is not compute capability 10.x (B200 / sm_100a)")
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise EbkError(f"ebk status {status}: {lib().ebk_last_error().decode()}")
+
+
+def ptr(t: torch.Tensor | None):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "ebk needs contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,261 @@
+"""Device engine of the NRMS model: parameter storage in HBM and the per-batch
+forward / backward / optimizer sequence issued through the ebk C-ABI.
+
+Layout in HBM (DESIGN.md "Data layout"): ONE flat fp32 parameter buffer
+``theta = [table | news_Wqkv | news_attW | news_attb | news_attq | user_Wqkv | ...]``
+(segments 256-byte aligned) with matching flat ``grad``, Adam ``m`` and ``v`` buffers, so
+the optimizer is a single streaming launch and data-parallel training needs exactly one
+all-reduce over ``grad`` per step.  WQ|WK|WV of a SelfAttention layer are stored fused as
+one ``[Din, 3D]`` matrix (one projection GEMM); get/set_weights split / fuse them so the
+Keras weight order of the reference is preserved.
+
+Reference: src/ebrec/models/newsrec/nrms.py:23-210 (graph wiring, loss, optimizer).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _ebk
+
+_ALIGN = 64  # floats (256 bytes)
+_U64 = (1 << 64) - 1
+
+
+def _mix(a: int, b: int) -> int:
+    z = (a * 0x9E3779B97F4A7C15 + b * 0xD1B54A32D192ED03 + 0x2545F4914F6CDD1D) & _U64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _U64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _U64
+    return z ^ (z >> 31)
+
+
+def keras_adam_alpha(lr: float, t: int, beta1: float, beta2: float) -> float:
+    """alpha = lr*sqrt(1-b2^t)/(1-b1^t) in fp32, as tf.keras.optimizers.Adam.update_step."""
+    f = np.float32
+    return float(f(lr) * np.sqrt(f(1.0) - np.power(f(beta2), f(t))) / (f(1.0) - np.power(f(beta1), f(t))))
+
+
+class FlatParams:
+    """Named views into one flat fp32 device buffer (plus grad / Adam moments)."""
+
+    def __init__(self, spec: list[tuple[str, tuple[int, ...]]], device):
+        self.spec = spec
+        self.offsets = {}
+        off = 0
+        for name, shape in spec:
+            self.offsets[name] = off
+            off += (int(np.prod(shape)) + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.n = off
+        self.theta = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros_like(self.theta)
+        self.m = torch.zeros_like(self.theta)
+        self.v = torch.zeros_like(self.theta)
+
+    def view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        shape = dict(self.spec)[name]
+        off = self.offsets[name]
+        return buf[off: off + int(np.prod(shape))].view(*shape)
+
+    def p(self, name):
+        return self.view(self.theta, name)
+
+    def g(self, name):
+        return self.view(self.grad, name)
+
+
+class NRMSEngine:
+    """NRMS on one GPU (one process per GPU under torch.distributed for data parallel)."""
+
+    def __init__(self, *, V, E, T, H, nh, dh, att, dropout, lr, seed=None, math=_ebk.MATH_TF32,
+                 device=None, beta1=0.9, beta2=0.999, eps=1e-7):
+        _ebk.require_device()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.V, self.E, self.T, self.H = int(V), int(E), int(T), int(H)
+        self.nh, self.dh, self.att = int(nh), int(dh), int(att)
+        self.D = self.nh * self.dh
+        self.dropout = float(dropout)
+        self.lr, self.beta1, self.beta2, self.eps = float(lr), beta1, beta2, eps
+        self.math = int(math)
+        self.seed = 0 if seed is None else int(seed)
+        self.step_count = 0  # optimizer iterations
+        D, A = self.D, self.att
+        self.params = FlatParams([
+            ("table", (self.V, self.E)),
+            ("news_Wqkv", (self.E, 3 * D)), ("news_attW", (D, A)), ("news_attb", (A,)), ("news_attq", (A,)),
+            ("user_Wqkv", (D, 3 * D)), ("user_attW", (D, A)), ("user_attb", (A,)), ("user_attq", (A,)),
+        ], self.device)
+        self._ws = {}
+        self._bufs = {}
+        self.world = 1
+        self.rank = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size()
+            self.rank = torch.distributed.get_rank()
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ weights
+    def set_weights(self, weights: list[np.ndarray]) -> None:
+        """Keras order: [table, WQ,WK,WV,W,b,q (news), WQ,WK,WV,W,b,q (user)]."""
+        if len(weights) != 13:
+            raise ValueError(f"NRMS expects 13 weight arrays, got {len(weights)}")
+        w = [torch.as_tensor(np.asarray(a, dtype=np.float32)) for a in weights]
+        P = self.params
+        with torch.no_grad():
+            P.p("table").copy_(w[0])
+            for pre, o in (("news", 1), ("user", 7)):
+                P.p(f"{pre}_Wqkv").copy_(torch.cat([w[o], w[o + 1], w[o + 2]], dim=1))
+                P.p(f"{pre}_attW").copy_(w[o + 3])
+                P.p(f"{pre}_attb").copy_(w[o + 4].reshape(-1))
+                P.p(f"{pre}_attq").copy_(w[o + 5].reshape(-1))
+
+    def get_weights(self) -> list[np.ndarray]:
+        P, D = self.params, self.D
+        out = [P.p("table").cpu().numpy()]
+        for pre in ("news", "user"):
+            Wqkv = P.p(f"{pre}_Wqkv").cpu().numpy()
+            out += [Wqkv[:, :D].copy(), Wqkv[:, D:2 * D].copy(), Wqkv[:, 2 * D:].copy()]
+            out += [P.p(f"{pre}_attW").cpu().numpy(), P.p(f"{pre}_attb").cpu().numpy(),
+                    P.p(f"{pre}_attq").cpu().numpy().reshape(-1, 1)]
+        return out
+
+    def count_params(self) -> int:
+        return int(sum(int(np.prod(s)) for _, s in self.params.spec))
+
+    # ------------------------------------------------------------------ scratch
+    def _desc(self, kind: str, n_seq: int) -> _ebk.SeqEncDesc:
+        if kind == "news":
+            return _ebk.SeqEncDesc(n_seq, self.T, self.E, self.nh, self.dh, self.att, self.V, self.dropout, self.math)
+        return _ebk.SeqEncDesc(n_seq, self.H, self.D, self.nh, self.dh, self.att, 0, 0.0, self.math)
+
+    def _workspace(self, kind: str, desc) -> torch.Tensor:
+        need = _ebk.lib().ebk_seqenc_workspace_bytes(C.byref(desc))
+        if need == 0 and desc.n_seq > 0:
+            raise _ebk.EbkError(f"bad descriptor: {_ebk.lib().ebk_last_error().decode()}")
+        cur = self._ws.get(kind)
+        if cur is None or cur.numel() < need:
+            cur = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+            self._ws[kind] = cur
+        return cur
+
+    def _buf(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        n = int(np.prod(shape))
+        cur = self._bufs.get(name)
+        if cur is None or cur.numel() < n or cur.dtype != dtype:
+            cur = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._bufs[name] = cur
+        return cur[:n].view(*shape)
+
+    # ------------------------------------------------------------------ forward pieces
+    def _encode(self, tok_all: torch.Tensor, B: int, Hh: int, training: bool, seeds=(0, 0)):
+        """tok_all [B*Hh + B*C, T] int32 -> (n_all [N, D], u [B, D]); keeps descs/workspaces for backward."""
+        lib, P = _ebk.lib(), self.params
+        N = tok_all.shape[0]
+        if Hh != self.H:
+            raise ValueError(f"history length {Hh} != hparams.history_size {self.H}")
+        dn = self._desc("news", N)
+        wn = self._workspace("news", dn)
+        n_all = self._buf("n_all", (N, self.D))
+        _ebk.check(lib.ebk_seqenc_fwd(C.byref(dn), _ebk.ptr(tok_all), _ebk.ptr(P.p("table")),
+                                      _ebk.ptr(P.p("news_Wqkv")), _ebk.ptr(P.p("news_attW")),
+                                      _ebk.ptr(P.p("news_attb")), _ebk.ptr(P.p("news_attq")),
+                                      int(training), seeds[0], seeds[1], _ebk.ptr(wn), wn.numel(),
+                                      _ebk.ptr(n_all), _ebk.stream()))
+        du = self._desc("user", B)
+        wu = self._workspace("user", du)
+        u = self._buf("u", (B, self.D))
+        _ebk.check(lib.ebk_seqenc_fwd(C.byref(du), None, _ebk.ptr(n_all), _ebk.ptr(P.p("user_Wqkv")),
+                                      _ebk.ptr(P.p("user_attW")), _ebk.ptr(P.p("user_attb")),
+                                      _ebk.ptr(P.p("user_attq")), 0, 0, 0, _ebk.ptr(wu), wu.numel(),
+                                      _ebk.ptr(u), _ebk.stream()))
+        return n_all, u, (dn, wn, du, wu)
+
+    @staticmethod
+    def pack_tokens(his: np.ndarray, pred: np.ndarray) -> np.ndarray:
+        """[B,H,T] + [B,C,T] -> [B*H + B*C, T] int32 (history rows first)."""
+        B, H, T = his.shape
+        C_ = pred.shape[1]
+        out = np.empty((B * H + B * C_, T), dtype=np.int32)
+        out[: B * H] = his.reshape(B * H, T)
+        out[B * H:] = pred.reshape(B * C_, T)
+        return out
+
+    # ------------------------------------------------------------------ public steps (device tensors)
+    def forward_logits_parts(self, tok_all, B, C_, training=False, seeds=(0, 0)):
+        n_all, u, ctx = self._encode(tok_all, B, self.H, training, seeds)
+        news_c = n_all[B * self.H:].view(B, C_, self.D)
+        return n_all, news_c, u, ctx
+
+    def predict_dev(self, tok_all: torch.Tensor, B: int, C_: int, head: str = "softmax") -> torch.Tensor:
+        lib = _ebk.lib()
+        _, news_c, u, _ = self.forward_logits_parts(tok_all, B, C_)
+        out = self._buf("probs", (B, C_))
+        if head == "sigmoid":
+            _ebk.check(lib.ebk_score_sigmoid(B, C_, self.D, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(out), _ebk.stream()))
+        else:
+            labels = self._buf("labels0", (B, C_))
+            labels.zero_()
+            loss = self._buf("loss", (1,))
+            loss.zero_()
+            _ebk.check(lib.ebk_score_softmax_ce(B, C_, self.D, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(labels),
+                                                0.0, _ebk.ptr(out), _ebk.ptr(loss), None, None, _ebk.stream()))
+        return out
+
+    def step_seeds(self) -> tuple[int, int]:
+        base = _mix(self.seed, self.step_count * self.world + self.rank)
+        return _mix(base, 1), _mix(base, 2)
+
+    def loss_and_grads_dev(self, tok_all, labels, B, C_, training=True, seeds=None):
+        """Forward + backward; gradients ACCUMULATE into params.grad.  Returns (loss_sum, probs)."""
+        lib, P = _ebk.lib(), self.params
+        seeds = self.step_seeds() if seeds is None else seeds
+        n_all, news_c, u, (dn, wn, du, wu) = self.forward_logits_parts(tok_all, B, C_, training, seeds)
+        N = n_all.shape[0]
+        probs = self._buf("probs", (B, C_))
+        loss = self._buf("loss", (1,))
+        loss.zero_()
+        dn_all = self._buf("dn_all", (N, self.D))
+        d_user = self._buf("d_user", (B, self.D))
+        d_news_c = dn_all[B * self.H:]
+        scale = 1.0 / (B * self.world)
+        _ebk.check(lib.ebk_score_softmax_ce(B, C_, self.D, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(labels), scale,
+                                            _ebk.ptr(probs), _ebk.ptr(loss), _ebk.ptr(d_news_c), _ebk.ptr(d_user),
+                                            _ebk.stream()))
+        _ebk.check(lib.ebk_seqenc_bwd(C.byref(du), None, _ebk.ptr(n_all), _ebk.ptr(P.p("user_Wqkv")),
+                                      _ebk.ptr(P.p("user_attW")), _ebk.ptr(P.p("user_attb")),
+                                      _ebk.ptr(P.p("user_attq")), 0, 0, 0, _ebk.ptr(wu), wu.numel(),
+                                      _ebk.ptr(d_user), _ebk.ptr(P.g("user_Wqkv")), _ebk.ptr(P.g("user_attW")),
+                                      _ebk.ptr(P.g("user_attb")), _ebk.ptr(P.g("user_attq")), None,
+                                      _ebk.ptr(dn_all), _ebk.stream()))
+        _ebk.check(lib.ebk_seqenc_bwd(C.byref(dn), _ebk.ptr(tok_all), _ebk.ptr(P.p("table")),
+                                      _ebk.ptr(P.p("news_Wqkv")), _ebk.ptr(P.p("news_attW")),
+                                      _ebk.ptr(P.p("news_attb")), _ebk.ptr(P.p("news_attq")), int(training),
+                                      seeds[0], seeds[1], _ebk.ptr(wn), wn.numel(), _ebk.ptr(dn_all),
+                                      _ebk.ptr(P.g("news_Wqkv")), _ebk.ptr(P.g("news_attW")),
+                                      _ebk.ptr(P.g("news_attb")), _ebk.ptr(P.g("news_attq")),
+                                      _ebk.ptr(P.g("table")), None, _ebk.stream()))
+        return loss, probs
+
+    def apply_adam(self) -> None:
+        """One Keras-form Adam iteration over the whole flat buffer (clears grad in the same pass)."""
+        P = self.params
+        if self.world > 1:
+            torch.distributed.all_reduce(P.grad)  # the one collective of the step (sum; loss pre-scaled by 1/world)
+        self.step_count += 1
+        alpha = keras_adam_alpha(self.lr, self.step_count, self.beta1, self.beta2)
+        _ebk.check(_ebk.lib().ebk_adam_keras_step(_ebk.ptr(P.theta), _ebk.ptr(P.grad), _ebk.ptr(P.m), _ebk.ptr(P.v),
+                                                  P.n, alpha, self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
+
+    def train_step_dev(self, tok_all, labels, B, C_):
+        loss, probs = self.loss_and_grads_dev(tok_all, labels, B, C_, training=True)
+        self.apply_adam()
+        return loss, probs
+
+    # ------------------------------------------------------------------ host-array convenience
+    def to_device_batch(self, his: np.ndarray, pred: np.ndarray, y: np.ndarray | None = None):
+        tok = torch.from_numpy(self.pack_tokens(np.asarray(his), np.asarray(pred))).to(self.device, non_blocking=True)
+        lab = None
+        if y is not None:
+            lab = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).to(self.device, non_blocking=True)
+        return tok, lab

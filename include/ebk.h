@@ -1,0 +1,145 @@
+/*
+ * ebk.h -- C-ABI of the B200-native NRMS-family hot path ("ebk" = EB-NeRD kernels).
+ *
+ * The reference (ebanalyse/ebnerd-benchmark) has NO FFI/plugin interface: its hot
+ * path is Keras graph code executed by TensorFlow.  Each entry point below
+ * therefore cites the reference *Python* lines whose arithmetic it replaces
+ * (paths relative to the reference repository root).  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds under src/ebrec/models/newsrec/.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative ebk_status otherwise, and never
+ *    throws; ebk_last_error() returns a thread-local message for the last failure;
+ *  - all tensor arguments are raw DEVICE pointers owned by the caller (row-major,
+ *    contiguous, 16-byte aligned), fp32 unless noted, indices int32;
+ *  - kernels never allocate: scratch and saved activations live in a caller-provided
+ *    workspace whose size comes from the matching *_workspace_bytes() query;
+ *    a forward and its backward must be given the SAME workspace;
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous, stateless
+ *    and ordered only by the stream.
+ */
+#ifndef EBK_H_
+#define EBK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  EBK_OK = 0,
+  EBK_ERR_INVALID = -1,   /* bad argument / shape / alignment */
+  EBK_ERR_WORKSPACE = -2, /* workspace too small */
+  EBK_ERR_CUDA = -3,      /* CUDA runtime error (message in ebk_last_error) */
+  EBK_ERR_UNSUPPORTED = -4
+} ebk_status;
+
+/* Arithmetic mode of the dense contractions. */
+typedef enum {
+  EBK_MATH_FP32 = 0, /* CUDA-core fp32 FMA (exact-ish; small shapes, debugging) */
+  EBK_MATH_TF32 = 1  /* tcgen05 kind::tf32 tensor cores, fp32 accumulate in TMEM */
+} ebk_math;
+
+const char* ebk_last_error(void);
+int ebk_version(void);
+/* 1 when the library was built for sm_100a and the current device is CC 10.x. */
+int ebk_device_ok(void);
+
+/* ------------------------------------------------------------------------------------
+ * Sequence encoder = [gather] -> Dropout -> SelfAttention -> Dropout -> AttLayer2.
+ * One description serves the news encoder (token ids gathered from the table,
+ * nrms.py:116-159) and the user encoder (dense [n_seq, L, Din] input, no dropout,
+ * nrms.py:92-114).
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_seq;   /* sequences: articles N = B*(H+C) (news) or impressions B (user)      */
+  int32_t L;       /* sequence length: title_size T (news) or history_size H (user), <=64 */
+  int32_t Din;     /* input width: table width E (news) or D (user); multiple of 4        */
+  int32_t nh, dh;  /* heads, head dim (layers.py:137-141); D = nh*dh, dh <= 32            */
+  int32_t att;     /* attention_hidden_dim of AttLayer2 (layers.py:14-22)                 */
+  int32_t V;       /* table rows when gathering; ids outside [0,V) -> zero row, no grad   */
+  float dropout;   /* Keras Dropout rate (nrms.py:136,153); used only when training != 0  */
+  int32_t math;    /* ebk_math                                                             */
+} ebk_seqenc_desc;
+
+size_t ebk_seqenc_workspace_bytes(const ebk_seqenc_desc* d);
+
+/* Forward.  Replaces Embedding+Dropout+SelfAttention+Dropout+AttLayer2
+ * (nrms.py:125-156; layers.py:200-254 with the adjoint_a=True product of layers.py:249;
+ * layers.py:55-81 incl. exp without max-subtraction and the +1e-7 of layers.py:75-77).
+ *   tok   [n_seq, L] int32 or NULL; table/x: [V, Din] when tok != NULL else [n_seq*L, Din]
+ *   Wqkv  [Din, 3*D]  columns = WQ | WK | WV (layers.py:155-172, no bias)
+ *   attW  [D, att], attb [att], attq [att]   (layers.py:35-52)
+ *   out   [n_seq, D]
+ *   training != 0: inverted dropout with the counter-based mask of DESIGN.md
+ *   (seed1: embedded tokens, element index r*Din+e; seed2: attention output, r*D+d). */
+int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, const float* table_or_x,
+                   const float* Wqkv, const float* attW, const float* attb, const float* attq,
+                   int training, uint64_t seed1, uint64_t seed2,
+                   void* workspace, size_t workspace_bytes, float* out, void* stream);
+
+/* Backward of ebk_seqenc_fwd (the reference gets it from TF autodiff).  Gradients are
+ * ACCUMULATED (+=) into dWqkv/dattW/dattb/dattq.  Input gradient:
+ *   tok != NULL: rows of dX are scatter-added into d_table [V, Din] (the Embedding's
+ *                IndexedSlices gradient, nrms.py:125-134), d_x must be NULL;
+ *   tok == NULL: d_x [n_seq*L, Din] is overwritten (may be NULL to skip). */
+int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, const float* table_or_x,
+                   const float* Wqkv, const float* attW, const float* attb, const float* attq,
+                   int training, uint64_t seed1, uint64_t seed2,
+                   void* workspace, size_t workspace_bytes, const float* d_out,
+                   float* dWqkv, float* dattW, float* dattb, float* dattq,
+                   float* d_table, float* d_x, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Click score + loss.  Replaces Dot(axes=-1) + Activation("softmax") +
+ * categorical_crossentropy (nrms.py:201-202, 61-62) and its gradient.
+ *   news [B, C, D], user [B, D], labels [B, C] fp32 (one-hot)
+ *   probs [B, C] out; loss_sum: 1 float, += sum_b CE_b * loss_scale  (caller zeroes)
+ *   d_news [B, C, D], d_user [B, D] out = gradient of (loss_scale * sum_b CE_b);
+ *   pass loss_scale = 1/B_global for Keras' batch-mean reduction.
+ *   d_news/d_user may be NULL (forward only).
+ * ---------------------------------------------------------------------------------- */
+int ebk_score_softmax_ce(int32_t B, int32_t C, int32_t D, const float* news, const float* user,
+                         const float* labels, float loss_scale, float* probs, float* loss_sum,
+                         float* d_news, float* d_user, void* stream);
+
+/* scorer head: sigmoid(news . user), nrms.py:204-205.  news [B, C, D] -> out [B, C]. */
+int ebk_score_sigmoid(int32_t B, int32_t C, int32_t D, const float* news, const float* user,
+                      float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * tf.keras.optimizers.Adam (nrms.py:76-77), dense (non-lazy) Keras form:
+ *   m += (g-m)(1-b1); v += (g*g-v)(1-b2); theta -= (m*alpha)/(sqrt(v)+eps)
+ *   with alpha = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller; (1-b1), (1-b2) are formed
+ *   in double and rounded to fp32 once, as Keras' Python-float constants are.
+ * If zero_grad != 0 the gradient buffer is cleared in the same pass.
+ * ---------------------------------------------------------------------------------- */
+int ebk_adam_keras_step(float* theta, float* g, float* m, float* v, size_t n, float alpha,
+                        double beta1, double beta2, float eps, int zero_grad, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Building blocks exported for the parity tests.
+ * ---------------------------------------------------------------------------------- */
+/* C[M,N] = (beta ? C : 0) + opA(A)[M,K] * opB(B)[K,N]; row-major; ld* in elements. */
+int ebk_gemm(int32_t math, int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K,
+             const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
+             float beta, void* stream);
+
+/* Multi-head attention core on packed projections (layers.py:231-252).
+ *   qkv [n_seq*L, 3*D] -> y [n_seq*L, D] */
+int ebk_attention_core_fwd(int32_t n_seq, int32_t L, int32_t nh, int32_t dh, const float* qkv,
+                           float* y, void* stream);
+/*  dy [n_seq*L, D] (optionally dropout-masked on read) -> dqkv [n_seq*L, 3*D] */
+int ebk_attention_core_bwd(int32_t n_seq, int32_t L, int32_t nh, int32_t dh, const float* qkv,
+                           const float* dy, float drop_p, uint64_t drop_seed, float* dqkv,
+                           void* stream);
+
+/* Keep-mask of the counter-based dropout, for tests: out[i] = 1.0f/0.0f, i in [0,n). */
+int ebk_dropout_mask(uint64_t seed, float p, size_t n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EBK_H_ */

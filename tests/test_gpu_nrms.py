@@ -1,0 +1,141 @@
+"""GPU parity of the NRMS hot path (through the C-ABI and the engine) against the oracle.
+
+Tolerances: EBK_MATH_FP32 -> 1e-4 relative (fp32 round-off vs the float64 oracle);
+EBK_MATH_TF32 -> 1e-3 relative on forward click scores (the north-star gate) and 2e-2 of
+the gradient's max-norm for backward quantities (tf32 inputs, fp32 accumulation).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nrms_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = {0: 1e-4, 1: 1e-3}
+BWD_TOL = {0: 2e-4, 1: 2e-2}
+
+
+def make_case(rng, V, E, nh, dh, att, B, H, C, T, table_scale=None):
+    P = O.init_nrms_params(rng, V, E, nh, dh, att, dtype=np.float64)
+    if table_scale is not None:
+        P["table"] = rng.random((V, E)) * table_scale
+    for k in ("news_b", "user_b"):
+        P[k] = rng.standard_normal(P[k].shape) * 0.05
+    his = rng.integers(0, V, (B, H, T)).astype(np.int32)
+    pred = rng.integers(0, V, (B, C, T)).astype(np.int32)
+    y = np.zeros((B, C), np.float32)
+    y[np.arange(B), rng.integers(0, C, B)] = 1
+    return P, his, pred, y
+
+
+def make_engine(P, V, E, T, H, nh, dh, att, dropout, lr, math, seed=3):
+    from ebrec.models.newsrec._engine import NRMSEngine
+
+    eng = NRMSEngine(V=V, E=E, T=T, H=H, nh=nh, dh=dh, att=att, dropout=dropout, lr=lr, seed=seed, math=math)
+    eng.set_weights([P[k] for k in O.NRMS_PARAM_ORDER])
+    return eng
+
+
+def rel(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return float(np.abs(got - want).max() / (np.abs(want).max() + 1e-30))
+
+
+CASES = [
+    # V, E, nh, dh, att, B, H, C, T
+    (1000, 100, 20, 20, 200, 8, 20, 5, 30),   # config 1 (nrms_dummy.py) at a small batch
+    (500, 64, 16, 16, 200, 4, 20, 5, 30),
+    (300, 32, 4, 8, 24, 3, 50, 7, 12),        # long history, odd sizes
+    (50, 16, 3, 4, 10, 1, 5, 1, 6),           # single impression, single candidate
+]
+
+
+@pytest.mark.parametrize("math", [0, 1])
+@pytest.mark.parametrize("case", CASES)
+def test_forward_scores(math, case):
+    V, E, nh, dh, att, B, H, C, T = case
+    rng = np.random.default_rng(sum(case))
+    P, his, pred, y = make_case(rng, V, E, nh, dh, att, B, H, C, T, table_scale=1.0 if V == 1000 else None)
+    eng = make_engine(P, V, E, T, H, nh, dh, att, 0.2, 1e-4, math)
+    tok, _ = eng.to_device_batch(his, pred)
+    # gather indices are passed through bit-exact
+    assert np.array_equal(tok.cpu().numpy(), np.concatenate([his.reshape(-1, T), pred.reshape(-1, T)]))
+    probs = eng.predict_dev(tok, B, C).cpu().numpy()
+    want = O.nrms_predict(his, pred, P, nh, dh)
+    assert rel(probs, want) < FWD_TOL[math], (rel(probs, want))
+    sig = eng.predict_dev(tok, B, C, head="sigmoid").cpu().numpy()
+    assert rel(sig, O.nrms_score(his, pred, P, nh, dh)) < FWD_TOL[math]
+
+
+def test_out_of_range_ids_read_zero_rows():
+    V, E, nh, dh, att, B, H, C, T = 50, 16, 3, 4, 10, 2, 5, 3, 6
+    rng = np.random.default_rng(1)
+    P, his, pred, y = make_case(rng, V, E, nh, dh, att, B, H, C, T)
+    his[0, 0, :3] = [V, V + 100, -1]
+    eng = make_engine(P, V, E, T, H, nh, dh, att, 0.0, 1e-4, 0)
+    tok, lab = eng.to_device_batch(his, pred, y)
+    probs = eng.predict_dev(tok, B, C).cpu().numpy()
+    assert rel(probs, O.nrms_predict(his, pred, P, nh, dh)) < 1e-4
+
+
+@pytest.mark.parametrize("math", [0, 1])
+@pytest.mark.parametrize("dropout", [0.0, 0.2])
+@pytest.mark.parametrize("case", CASES[:3])
+def test_loss_and_gradients(math, dropout, case):
+    V, E, nh, dh, att, B, H, C, T = case
+    rng = np.random.default_rng(sum(case) + 1)
+    P, his, pred, y = make_case(rng, V, E, nh, dh, att, B, H, C, T)
+    eng = make_engine(P, V, E, T, H, nh, dh, att, dropout, 1e-4, math)
+    tok, lab = eng.to_device_batch(his, pred, y)
+    s1, s2 = 1234567, 7654321
+    eng.params.grad.zero_()
+    loss, probs = eng.loss_and_grads_dev(tok, lab, B, C, training=True, seeds=(s1, s2))
+    wl, wp, G = O.nrms_loss_and_grads(his, pred, y, P, nh, dh, training=True, p_drop=dropout, seed1=s1, seed2=s2)
+    assert abs(float(loss) - wl) < FWD_TOL[math] * max(1.0, abs(wl))
+    assert rel(probs.cpu().numpy(), wp) < FWD_TOL[math] * 3
+    D = nh * dh
+    got = {
+        "table": eng.params.g("table").cpu().numpy(),
+        "news_W": eng.params.g("news_attW").cpu().numpy(),
+        "news_b": eng.params.g("news_attb").cpu().numpy(),
+        "news_q": eng.params.g("news_attq").cpu().numpy().reshape(-1, 1),
+        "user_W": eng.params.g("user_attW").cpu().numpy(),
+        "user_b": eng.params.g("user_attb").cpu().numpy(),
+        "user_q": eng.params.g("user_attq").cpu().numpy().reshape(-1, 1),
+    }
+    for pre in ("news", "user"):
+        W = eng.params.g(f"{pre}_Wqkv").cpu().numpy()
+        got[f"{pre}_WQ"], got[f"{pre}_WK"], got[f"{pre}_WV"] = W[:, :D], W[:, D:2 * D], W[:, 2 * D:]
+    for k in O.NRMS_PARAM_ORDER:
+        assert rel(got[k], G[k]) < BWD_TOL[math], (k, rel(got[k], G[k]))
+
+
+@pytest.mark.parametrize("math", [0, 1])
+def test_train_steps_follow_oracle(math):
+    """3 optimizer steps with dropout: weights track the float64 oracle run with the same masks."""
+    V, E, nh, dh, att, B, H, C, T = 200, 32, 4, 8, 24, 6, 10, 5, 12
+    rng = np.random.default_rng(11)
+    P, his, pred, y = make_case(rng, V, E, nh, dh, att, B, H, C, T)
+    lr = 1e-3
+    eng = make_engine(P, V, E, T, H, nh, dh, att, 0.2, lr, math, seed=5)
+    Pm = {k: np.zeros_like(v) for k, v in P.items()}
+    Pv = {k: np.zeros_like(v) for k, v in P.items()}
+    losses = []
+    for t in range(1, 4):
+        his = rng.integers(0, V, (B, H, T)).astype(np.int32)
+        pred = rng.integers(0, V, (B, C, T)).astype(np.int32)
+        tok, lab = eng.to_device_batch(his, pred, y)
+        s1, s2 = eng.step_seeds()
+        loss, _ = eng.train_step_dev(tok, lab, B, C)
+        wl, _, G = O.nrms_loss_and_grads(his, pred, y, P, nh, dh, training=True, p_drop=0.2, seed1=s1, seed2=s2)
+        for k in P:
+            O.keras_adam_step(P[k], G[k], Pm[k], Pv[k], t, lr)
+        losses.append((float(loss), wl))
+        assert abs(float(loss) - wl) < 5e-3 * max(1, abs(wl))
+    W = eng.get_weights()
+    for k, w in zip(O.NRMS_PARAM_ORDER, W):
+        # Adam's first steps move every touched weight by ~lr regardless of gradient scale, so
+        # compare the *update* against lr
+        assert np.abs(w - P[k]).max() < (2e-5 if math == 0 else 6e-4), (k, np.abs(w - P[k]).max())
+    assert float(eng.params.grad.abs().max()) == 0.0
