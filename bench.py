@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Headline benchmark: NRMS train impressions/sec on synthetic EB-NeRD-shaped batches.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm; N>1 under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...   (reference arm: CPU restatement)
+
+Workload (BASELINE.json configs[2], the config the metric "NRMS ebnerd_small-shape" is
+quoted on): NRMS token path, xlm-roberta-base table 250002 x 768 fp32, title_len 30,
+history 20, npratio 4 (5 candidates), 20 heads x 20, attention_hidden 200, 256
+impressions per GPU per step (weak scaling), dropout 0.2, Keras-form dense Adam.
+A step = forward + backward + (gradient all-reduce) + Adam over one batch.
+
+Prints ONE JSON line (rank 0).  `value`: device-resident batches, CUDA-event timed, max
+over ranks.  `e2e`: the same steps through the public API (`NRMSModel.model.train_on_batch`)
+with host batches: pinned H2D of token ids + labels and a D2H read of the loss inside the
+timed region.  `roofline`: dominant kernel group timed live with CUDA events (library
+profiler) in a separate pass.  `cpu_baseline`: the torch-CPU restatement of the reference
+graph (oracle/torch_port.py -- TensorFlow is not installable here) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for _p in (str(ROOT), str(ROOT / "ebnerd-benchmark_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOADS = {
+    # name: V, E, T, H, C, nh, dh, att, B per GPU
+    "nrms_ebnerd_small_xlmr_base_bs256": dict(V=250002, E=768, T=30, H=20, C=5, nh=20, dh=20, att=200, B=256),
+    "nrms_ebnerd_large_shape_h50_bs256": dict(V=250002, E=768, T=30, H=50, C=5, nh=20, dh=20, att=200, B=256),
+    "nrms_dummy_bs32": dict(V=1000, E=100, T=30, H=20, C=5, nh=20, dh=20, att=200, B=32),
+}
+DEFAULT_WORKLOAD = "nrms_ebnerd_small_xlmr_base_bs256"
+SEED = 20240617
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return dict(hbm=float(d["hbm_gbs"]), tensor_burst=float(d["bf16_tflops"]),
+                    tensor=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, src="fallback")
+
+
+def synth_batch(rng, w, B):
+    his = rng.integers(0, w["V"], (B, w["H"], w["T"]), dtype=np.int32)
+    pred = rng.integers(0, w["V"], (B, w["C"], w["T"]), dtype=np.int32)
+    y = np.zeros((B, w["C"]), np.float32)
+    y[np.arange(B), rng.integers(0, w["C"], B)] = 1.0
+    return his, pred, y
+
+
+def bytes_per_impression(w):
+    S = (w["H"] + w["C"]) * w["T"]
+    return 2 * S * w["E"] * 4 + 4 * S  # gathered row read fwd + grad row written bwd + ids
+
+
+def flops_per_impression_fwd(w):
+    S = (w["H"] + w["C"]) * w["T"]
+    D = w["nh"] * w["dh"]
+    H, T, E, att, nh, dh, C = w["H"], w["T"], w["E"], w["att"], w["nh"], w["dh"], w["C"]
+    return (S * 6 * E * D + (H + C) * nh * 4 * T * T * dh + S * (2 * D * att + 2 * att)
+            + H * 6 * D * D + nh * 4 * H * H * dh + H * (2 * D * att + 2 * att) + 2 * C * D)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: torch-CPU restatement of the reference graph (oracle port)
+# ------------------------------------------------------------------------------------------
+def cpu_port_run(w, steps, warmup, B_cpu=32):
+    import torch
+
+    from oracle import nrms_oracle as O, torch_port as TP
+
+    torch.manual_seed(0)
+    rng = np.random.default_rng(SEED)
+    table = rng.normal(0, 0.02, (w["V"], w["E"])).astype(np.float32)
+    P = TP.params_to_torch(O.init_nrms_params(rng, w["V"], w["E"], w["nh"], w["dh"], w["att"], table=table))
+    opt = TP.KerasAdam(P, 1e-4)
+    batches = [synth_batch(rng, w, B_cpu) for _ in range(2)]
+    gen = torch.Generator().manual_seed(1)
+
+    def step(i):
+        his, pred, y = batches[i % len(batches)]
+        return TP.train_step(torch.from_numpy(his), torch.from_numpy(pred), torch.from_numpy(y), P, opt,
+                             w["nh"], w["dh"], p_drop=0.2, rng=gen)
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    return dict(value=B_cpu * steps / dt, ms_per_step=1e3 * dt / steps, cores=torch.get_num_threads(),
+                sample=f"{steps} train steps of {B_cpu} impressions (same shapes, V={w['V']}, E={w['E']}), "
+                       f"torch-CPU fp32 restatement with autograd + dense Keras-form Adam, {warmup} warm-up")
+
+
+def run_reference(args, w, wname):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 2))
+    r = cpu_port_run(w, steps, warm)
+    line = {
+        "impl": "reference", "metric": "train_impressions_per_sec", "value": r["value"], "unit": "impressions/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wname, **{k: w[k] for k in ("V", "E", "T", "H", "C", "nh", "dh", "att")},
+                   "batch_per_step": 32, "device": "cpu"},
+        "cpu_baseline": {"value": r["value"], "unit": "impressions/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "impressions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement of the reference graph (TensorFlow cannot be installed in this image)",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args, w, wname):
+    import torch
+    import torch.distributed as dist
+
+    from ebrec.models.newsrec import _ebk
+    from ebrec.models.newsrec.model_config import hparams_nrms
+    from ebrec.models.newsrec.nrms import NRMSModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
+
+    class hp(hparams_nrms):
+        pass
+
+    hp.title_size, hp.history_size = w["T"], w["H"]
+    hp.head_num, hp.head_dim, hp.attention_hidden_dim = w["nh"], w["dh"], w["att"]
+    hp.dropout, hp.learning_rate = 0.2, 1e-4
+
+    rng = np.random.default_rng(SEED)
+    table = rng.normal(0, 0.02, (w["V"], w["E"])).astype(np.float32)
+    model = NRMSModel(hp, word2vec_embedding=table, seed=42)
+    eng = model._engine
+    B, C_ = w["B"], w["C"]
+    rng = np.random.default_rng(SEED + 1 + rank)
+    n_pool = 4
+    host = [synth_batch(rng, w, B) for _ in range(n_pool)]
+    dev = [eng.to_device_batch(*b) for b in host]
+    lib = _ebk.lib()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------
+    for i in range(args.warmup):
+        eng.train_step_dev(dev[i % n_pool][0], dev[i % n_pool][1], B, C_)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.ebk_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        eng.train_step_dev(dev[i % n_pool][0], dev[i % n_pool][1], B, C_)
+    e1.record()
+    sync_all()
+    launches = lib.ebk_launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end through the public API (host batches, pinned H2D, loss read back) --
+    for i in range(min(3, args.warmup)):
+        model.model.train_on_batch((host[i % n_pool][0], host[i % n_pool][1]), host[i % n_pool][2])
+    sync_all()
+    t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t_e0.record()
+    for i in range(args.steps):
+        h = host[i % n_pool]
+        model.model.train_on_batch((h[0], h[1]), h[2])  # returns float(loss): D2H read each step
+    t_e1.record()
+    sync_all()
+    ms2 = torch.tensor([t_e0.elapsed_time(t_e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2)
+    h2d = host[0][0].nbytes + host[0][1].nbytes + host[0][2].nbytes
+
+    # ---- per-kernel profile pass (library CUDA-event profiler; not part of the numbers above) --
+    prof = {}
+    if rank == 0:
+        psteps = min(args.steps, 10)
+        lib.ebk_prof_enable(1)
+        for i in range(psteps):
+            eng.train_step_dev(dev[i % n_pool][0], dev[i % n_pool][1], B, C_)
+        torch.cuda.synchronize()
+        prof = {k: (ms_ / psteps, c // psteps) for k, (ms_, c) in _ebk.prof_collect().items()}
+        lib.ebk_prof_enable(0)
+    sync_all()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_port_run(w, 3, 1)
+        cpu = {"value": r["value"], "unit": "impressions/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        pk = peaks()
+        ms_step = ms_total / args.steps
+        value = B * world * args.steps / (ms_total / 1e3)
+        e2e_value = B * world * args.steps / (e2e_ms / 1e3)
+        R = B * (w["H"] + w["C"]) * w["T"]
+        D = w["nh"] * w["dh"]
+        gemm_flops = {"news.qkv_gemm_fwd": 2.0 * R * w["E"] * 3 * D, "news.qkv_dgrad_gemm": 2.0 * R * w["E"] * 3 * D,
+                      "news.qkv_wgrad_gemm": 2.0 * R * w["E"] * 3 * D}
+        step_prof_ms = sum(v[0] for v in prof.values()) or 1.0
+        dom = max(prof, key=lambda k: prof[k][0]) if prof else None
+        roof = None
+        if dom in gemm_flops:
+            ach = gemm_flops[dom] / (prof[dom][0] * 1e-3) / 1e12
+            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tensor"], "traffic": None,
+                    "peak_source": f"{pk['src']} bf16 sustained (kernel computes in tf32, nominal half-rate of bf16)",
+                    "share_of_step": prof[dom][0] / step_prof_ms, "ms_per_launch": prof[dom][0]}
+        elif dom is not None:
+            nparam = eng.params.n
+            byts = {"news.adam": 7.0 * 4 * nparam, "user.adam": 7.0 * 4 * nparam}.get(dom)
+            if byts:
+                ach = byts / (prof[dom][0] * 1e-3) / 1e9
+                roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                        "share_of_step": prof[dom][0] / step_prof_ms, "ms_per_launch": prof[dom][0]}
+        bpi = bytes_per_impression(w)
+        line = {
+            "metric": "train_impressions_per_sec", "value": value, "unit": "impressions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": wname, **{k: w[k] for k in ("V", "E", "T", "H", "C", "nh", "dh", "att")},
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "dropout": 0.2, "optimizer": "keras-adam-dense",
+                       "l2_policy": "inputs larger than L2 (768 MB table + 3 GB optimizer state streamed per step)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "impressions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "roofline_hbm_gather": {"bound": "hbm", "achieved": value / world * bpi / 1e9, "peak": pk["hbm"],
+                                    "unit": "GB/s", "frac": value / world * bpi / 1e9 / pk["hbm"],
+                                    "bytes_per_impression": bpi, "peak_source": pk["src"],
+                                    "note": "contractual embedding-gather roofline of SURVEY.md 8(d), whole step"},
+            "tensor_fraction_step": {"achieved": value / world * 3 * flops_per_impression_fwd(w) / 1e12,
+                                     "peak": pk["tensor"], "unit": "TFLOP/s",
+                                     "frac": value / world * 3 * flops_per_impression_fwd(w) / 1e12 / pk["tensor"]},
+            "kernel_ms_per_step": {k: round(v[0], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w, args.workload)
+    else:
+        run_ours(args, w, args.workload)
+
+
+if __name__ == "__main__":
+    main()

@@ -2,6 +2,9 @@
 // forward + backward composed from the kernels of this directory, and test exports.
 #include <stdarg.h>
 
+#include <atomic>
+#include <vector>
+
 #include "ebk_common.cuh"
 
 namespace ebk {
@@ -15,9 +18,38 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- launch counter + event profiler -----------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+namespace {
+struct ProfRec { int tag; int user; cudaEvent_t a, b; };
+bool g_prof = false;
+int g_prof_user = 0;  // 0 = news encoder call, 1 = user encoder call (set by the seqenc entry points)
+std::vector<ProfRec> g_recs;
+std::vector<cudaEvent_t> g_pool;
+cudaEvent_t prof_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+const char* kTagNames[T_NUM_TAGS] = {"qkv_gemm_fwd", "attn_core_fwd", "att_gemm_fwd", "attpool_fwd", "attpool_bwd",
+                                     "colsum", "att_wgrad_gemm", "att_dgrad_gemm", "attn_core_bwd", "qkv_wgrad_gemm",
+                                     "qkv_dgrad_gemm", "embed_scatter", "score_ce", "adam"};
+}  // namespace
+bool prof_on() { return g_prof; }
+void prof_begin(int tag, cudaStream_t st) {
+  ProfRec r{tag, g_prof_user, prof_event(), prof_event()};
+  cudaEventRecord(r.a, st);
+  g_recs.push_back(r);
+}
+void prof_end(int tag, cudaStream_t st) {
+  (void)tag;
+  cudaEventRecord(g_recs.back().b, st);
+}
+
 int gemm_dispatch(int math, const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc,
-                  int M, int N, int K, float beta, cudaStream_t st) {
-  if (math == EBK_MATH_TF32) return gemm_tf32(A, B, ldb, transB, C, ldc, M, N, K, beta, st);
+                  int M, int N, int K, float beta, cudaStream_t st, bool b_rounded) {
+  if (math == EBK_MATH_TF32) return gemm_tf32(A, B, ldb, transB, C, ldc, M, N, K, beta, st, b_rounded);
   if (math == EBK_MATH_FP32) return gemm_f32(A, B, ldb, transB, C, ldc, M, N, K, beta, st);
   set_error("unknown math mode %d", math);
   return EBK_ERR_INVALID;
@@ -30,6 +62,7 @@ struct SeqWs {
   float *qkv, *y0, *hbuf, *w;          // saved by forward
   float *dy, *dpre, *da, *dqkv, *dx;   // backward scratch
   float* colsum;                       // column-sum partials
+  float *wqkv_r, *attw_r;              // tf32-rounded copies of the weights (B operands of the tcgen05 GEMMs)
   size_t bytes;
 };
 
@@ -52,6 +85,8 @@ SeqWs seq_layout(const ebk_seqenc_desc& d, void* base) {
   w.dqkv = take(R * 3 * D);
   w.dx = take(R * (size_t)d.Din);
   w.colsum = take(colsum_partial_floats((int)R, d.att));
+  w.wqkv_r = take((size_t)d.Din * 3 * D);
+  w.attw_r = take(D * (size_t)d.att);
   w.bytes = off;
   return w;
 }
@@ -74,6 +109,34 @@ int check_desc(const ebk_seqenc_desc* d) {
 using namespace ebk;
 
 extern "C" const char* ebk_last_error(void) { return g_err; }
+extern "C" long long ebk_launch_count(void) { return g_launches.load(); }
+extern "C" int ebk_prof_enable(int on) {
+  g_prof = on != 0;
+  if (g_prof) {
+    for (auto& r : g_recs) { g_pool.push_back(r.a); g_pool.push_back(r.b); }
+    g_recs.clear();
+  }
+  return EBK_OK;
+}
+extern "C" int ebk_prof_num_tags(void) { return 2 * T_NUM_TAGS; }
+extern "C" const char* ebk_prof_tag_name(int slot) {
+  static thread_local char buf[64];
+  if (slot < 0 || slot >= 2 * T_NUM_TAGS) return "";
+  snprintf(buf, sizeof(buf), "%s%s", slot >= T_NUM_TAGS ? "user." : "news.", kTagNames[slot % T_NUM_TAGS]);
+  return buf;
+}
+extern "C" int ebk_prof_collect(double* ms_out, long long* count_out) {
+  for (int i = 0; i < 2 * T_NUM_TAGS; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
+  for (auto& r : g_recs) {
+    EBK_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.0f;
+    EBK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    int slot = r.tag + (r.user ? T_NUM_TAGS : 0);
+    ms_out[slot] += ms;
+    count_out[slot] += 1;
+  }
+  return EBK_OK;
+}
 extern "C" int ebk_version(void) { return 100; }
 
 extern "C" int ebk_device_ok(void) {
@@ -104,21 +167,31 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
     return EBK_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  g_prof_user = tok == nullptr;
   const int R = d->n_seq * d->L, D = d->nh * d->dh;
   const Dropout drop1 = make_dropout(training != 0, d->dropout, seed1);
   const Dropout drop2 = make_dropout(training != 0, d->dropout, seed2);
   const Dropout none = make_dropout(false, 0.0f, 0);
 
+  // B operands of the tensor-core GEMMs: tf32-rounded (to nearest) copies of the weights, kept in the
+  // workspace for the backward pass.  The fp32 path uses the weights as they are.
+  const bool tc = d->math == EBK_MATH_TF32;
+  if (tc) {
+    EBK_TRY(round_tf32_copy(ws.wqkv_r, Wqkv, (size_t)d->Din * 3 * D, st));
+    EBK_TRY(round_tf32_copy(ws.attw_r, attW, (size_t)D * d->att, st));
+  }
+  const float* Wqkv_b = tc ? ws.wqkv_r : Wqkv;
+  const float* attW_b = tc ? ws.attw_r : attW;
   // (1) Q|K|V = dropout1(gather(table, tok)) . Wqkv        nrms.py:134-139, layers.py:214-230
   GemmOperandA ax{table_or_x, d->Din, false, tok, d->V, tok ? drop1 : none, d->Din};
-  EBK_TRY(gemm_dispatch(d->math, ax, Wqkv, 3 * D, false, ws.qkv, 3 * D, R, 3 * D, d->Din, 0.0f, st));
+  EBK_PROF(T_QKV_FWD, gemm_dispatch(d->math, ax, Wqkv_b, 3 * D, false, ws.qkv, 3 * D, R, 3 * D, d->Din, 0.0f, st, tc));
   // (2) per-head softmax(QK^T/sqrt(dh)) and the adjoint product    layers.py:231-252
-  EBK_TRY(attention_core_fwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st));
+  EBK_PROF(T_ATTN_FWD, attention_core_fwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st));
   // (3) pre-activation of AttLayer2: dropout2(Y0) . W              nrms.py:153-156, layers.py:65
   GemmOperandA ay{ws.y0, D, false, nullptr, 0, drop2, D};
-  EBK_TRY(gemm_dispatch(d->math, ay, attW, d->att, false, ws.hbuf, d->att, R, d->att, D, 0.0f, st));
+  EBK_PROF(T_ATT_GEMM_FWD, gemm_dispatch(d->math, ay, attW_b, d->att, false, ws.hbuf, d->att, R, d->att, D, 0.0f, st, tc));
   // (4) tanh, .q, exp, normalise (+1e-7), pool                     layers.py:65-81
-  EBK_TRY(attpool_fwd(d->n_seq, d->L, D, d->att, ws.y0, drop2, ws.hbuf, attb, attq, ws.w, out, st));
+  EBK_PROF(T_POOL_FWD, attpool_fwd(d->n_seq, d->L, D, d->att, ws.y0, drop2, ws.hbuf, attb, attq, ws.w, out, st));
   return EBK_OK;
 }
 
@@ -141,31 +214,37 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
     return EBK_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  g_prof_user = tok == nullptr;
   const int R = d->n_seq * d->L, D = d->nh * d->dh;
   const Dropout drop1 = make_dropout(training != 0, d->dropout, seed1);
   const Dropout drop2 = make_dropout(training != 0, d->dropout, seed2);
   const Dropout none = make_dropout(false, 0.0f, 0);
 
+  // tensor-core mode: the forward left tf32-rounded weights in the workspace, and the kernels that
+  // produce dpre / dQKV round them on store so they can be staged as B operands with cp.async.
+  const bool tc = d->math == EBK_MATH_TF32;
+  const float* Wqkv_b = tc ? ws.wqkv_r : Wqkv;
+  const float* attW_b = tc ? ws.attw_r : attW;
   // AttLayer2 backward (layers.py:55-81)
-  EBK_TRY(attpool_bwd(d->n_seq, d->L, D, d->att, ws.y0, drop2, ws.hbuf, attq, ws.w, d_out, ws.da, ws.dpre,
-                      ws.dy, st));
-  EBK_TRY(colsum_accum_ws(R, d->att, ws.hbuf, d->att, ws.da, dattq, ws.colsum, st));   // dq = sum_r h_r da_r
-  EBK_TRY(colsum_accum_ws(R, d->att, ws.dpre, d->att, nullptr, dattb, ws.colsum, st)); // db = sum_r dpre_r
+  EBK_PROF(T_POOL_BWD, attpool_bwd(d->n_seq, d->L, D, d->att, ws.y0, drop2, ws.hbuf, attq, ws.w, d_out, ws.da, ws.dpre,
+                      ws.dy, tc, st));
+  EBK_PROF(T_COLSUM, colsum_accum_ws(R, d->att, ws.hbuf, d->att, ws.da, dattq, ws.colsum, st));   // dq = sum_r h_r da_r
+  EBK_PROF(T_COLSUM, colsum_accum_ws(R, d->att, ws.dpre, d->att, nullptr, dattb, ws.colsum, st)); // db = sum_r dpre_r
   GemmOperandA ayT{ws.y0, D, true, nullptr, 0, drop2, D};                              // dW += X^T dpre
-  EBK_TRY(gemm_dispatch(d->math, ayT, ws.dpre, d->att, false, dattW, d->att, D, d->att, R, 1.0f, st));
+  EBK_PROF(T_ATT_WGRAD, gemm_dispatch(d->math, ayT, ws.dpre, d->att, false, dattW, d->att, D, d->att, R, 1.0f, st, tc));
   GemmOperandA adp{ws.dpre, d->att, false, nullptr, 0, none, 0};                       // dX += dpre W^T
-  EBK_TRY(gemm_dispatch(d->math, adp, attW, d->att, true, ws.dy, D, R, D, d->att, 1.0f, st));
+  EBK_PROF(T_ATT_DGRAD, gemm_dispatch(d->math, adp, attW_b, d->att, true, ws.dy, D, R, D, d->att, 1.0f, st, tc));
   // SelfAttention core backward (dropout2 mask applied while reading dy)
-  EBK_TRY(attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, st));
+  EBK_PROF(T_ATTN_BWD, attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, tc, st));
   // dWqkv += X^T dQKV  (X = dropout1(gather))
   GemmOperandA axT{table_or_x, d->Din, true, tok, d->V, tok ? drop1 : none, d->Din};
-  EBK_TRY(gemm_dispatch(d->math, axT, ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din, 3 * D, R, 1.0f, st));
+  EBK_PROF(T_QKV_WGRAD, gemm_dispatch(d->math, axT, ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din, 3 * D, R, 1.0f, st, tc));
   // dX = dQKV Wqkv^T
   if (tok != nullptr ? (d_table != nullptr) : (d_x != nullptr)) {
     float* dx = tok ? ws.dx : d_x;
     GemmOperandA adq{ws.dqkv, 3 * D, false, nullptr, 0, none, 0};
-    EBK_TRY(gemm_dispatch(d->math, adq, Wqkv, 3 * D, true, dx, d->Din, R, d->Din, 3 * D, 0.0f, st));
-    if (tok) EBK_TRY(scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
+    EBK_PROF(T_QKV_DGRAD, gemm_dispatch(d->math, adq, Wqkv_b, 3 * D, true, dx, d->Din, R, d->Din, 3 * D, 0.0f, st, tc));
+    if (tok) EBK_PROF(T_SCATTER, scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
   }
   return EBK_OK;
 }
@@ -189,5 +268,5 @@ extern "C" int ebk_attention_core_bwd(int32_t n_seq, int32_t L, int32_t nh, int3
                                       void* stream) {
   EBK_CHECK_ARG(qkv && dy && dqkv, "attention_core_bwd: null pointer");
   return attention_core_bwd(n_seq, L, nh, dh, qkv, dy, make_dropout(drop_p > 0.0f, drop_p, drop_seed), dqkv,
-                            (cudaStream_t)stream);
+                            false, (cudaStream_t)stream);
 }

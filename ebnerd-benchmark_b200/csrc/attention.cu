@@ -98,7 +98,7 @@ template <int DH>
 __global__ void __launch_bounds__(WARPS * 32) attn_bwd_kernel(int n_seq, int L, int nh, int dh,
                                                                const float* __restrict__ qkv,
                                                                const float* __restrict__ dy, Dropout drop,
-                                                               float* __restrict__ dqkv) {
+                                                               float* __restrict__ dqkv, bool round_out) {
   extern __shared__ float smem[];
   constexpr int DP = Lay<DH>::DP;
   const int LP = L | 1;
@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(WARPS * 32) attn_bwd_kernel(int n_seq, int L, 
 #pragma unroll
       for (int d = 0; d < DH; ++d)
         if (d < dh) {
-          out[d] = dq[d] * inv;
-          out[2 * D + d] = dv[d];
+          out[d] = round_out ? round_tf32_bits(dq[d] * inv) : dq[d] * inv;
+          out[2 * D + d] = round_out ? round_tf32_bits(dv[d]) : dv[d];
         }
     }
     __syncwarp();
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_bwd_kernel(int n_seq, int L, 
       float* out = dqkv + ((long)n * L + k) * 3 * D + D + h * dh;
 #pragma unroll
       for (int d = 0; d < DH; ++d)
-        if (d < dh) out[d] = dk[d] * inv;
+        if (d < dh) out[d] = round_out ? round_tf32_bits(dk[d] * inv) : dk[d] * inv;
     }
     __syncwarp();
   }
@@ -247,7 +247,7 @@ int attention_core_fwd(int n_seq, int L, int nh, int dh, const float* qkv, float
 }
 
 int attention_core_bwd(int n_seq, int L, int nh, int dh, const float* qkv, const float* dy, Dropout drop,
-                       float* dqkv, cudaStream_t st) {
+                       float* dqkv, bool round_out, cudaStream_t st) {
   if (n_seq <= 0) return EBK_OK;
   EBK_CHECK_ARG(L >= 1 && L <= 64 && dh >= 1 && dh <= 32 && nh >= 1, "attention: need 1<=L<=64, 1<=dh<=32 (L=%d dh=%d)", L, dh);
   const int LP = L | 1;
@@ -257,7 +257,7 @@ int attention_core_bwd(int n_seq, int L, int nh, int dh, const float* qkv, const
   {                                                                                            \
     size_t smem = (size_t)WARPS * (4 * L * (DH_ + 1) + 2 * L * LP) * sizeof(float);            \
     EBK_TRY(launch_cfg(attn_bwd_kernel<DH_>, smem, total, &grid));                             \
-    attn_bwd_kernel<DH_><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, dh, qkv, dy, drop, dqkv); \
+    attn_bwd_kernel<DH_><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, dh, qkv, dy, drop, dqkv, round_out); \
   }
   if (dh <= 16) RUN(16) else if (dh <= 20) RUN(20) else RUN(32)
 #undef RUN

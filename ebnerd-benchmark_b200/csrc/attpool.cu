@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(PT) attpool_bwd_kernel(int L, int D, int att, 
                                                           const float* __restrict__ w,
                                                           const float* __restrict__ d_out,
                                                           float* __restrict__ da, float* __restrict__ dpre,
-                                                          float* __restrict__ dy) {
+                                                          float* __restrict__ dy, bool round_dpre) {
   __shared__ float dw_s[64];
   __shared__ float da_s[64];
   const int n = blockIdx.x;
@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(PT) attpool_bwd_kernel(int L, int D, int att, 
     int t = i / att, j = i % att;
     long r = (long)n * L + t;
     float h = hbuf[r * att + j];
-    dpre[r * att + j] = da_s[t] * attq[j] * (1.0f - h * h);
+    const float v = da_s[t] * attq[j] * (1.0f - h * h);
+    dpre[r * att + j] = round_dpre ? round_tf32_bits(v) : v;
   }
 }
 
@@ -130,6 +131,14 @@ __global__ void colsum_final_kernel(int nblk, int Ncols, const float* __restrict
   float acc = 0.0f;
   for (int b = 0; b < nblk; ++b) acc += partial[(long)b * Ncols + j];
   out[j] += acc;
+}
+
+__global__ void round_tf32_copy_kernel(float4* __restrict__ dst, const float4* __restrict__ src, size_t n4) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = src[i];
+  v.x = round_tf32_bits(v.x); v.y = round_tf32_bits(v.y); v.z = round_tf32_bits(v.z); v.w = round_tf32_bits(v.w);
+  dst[i] = v;
 }
 
 __global__ void scatter_rows_add_kernel(int R, int E4, int V, const int32_t* __restrict__ tok,
@@ -165,10 +174,10 @@ int attpool_fwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop,
 
 int attpool_bwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, const float* hbuf,
                 const float* attq, const float* w, const float* d_out, float* da, float* dpre, float* dy,
-                cudaStream_t st) {
+                bool round_dpre, cudaStream_t st) {
   if (n_seq <= 0) return EBK_OK;
   EBK_CHECK_ARG(L <= 64, "attpool: L=%d > 64", L);
-  attpool_bwd_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, drop, hbuf, attq, w, d_out, da, dpre, dy);
+  attpool_bwd_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, drop, hbuf, attq, w, d_out, da, dpre, dy, round_dpre);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }
@@ -188,6 +197,16 @@ int colsum_accum_ws(int R, int Ncols, const float* X, int ldx, const float* coef
   return EBK_OK;
 }
 size_t colsum_partial_floats(int R, int Ncols) { return (size_t)ceil_div(R, CS_ROWS) * (size_t)Ncols; }
+
+int round_tf32_copy(float* dst, const float* src, size_t n, cudaStream_t st) {
+  if (n == 0) return EBK_OK;
+  EBK_CHECK_ARG(n % 4 == 0, "round_tf32_copy: n=%zu must be a multiple of 4", n);
+  size_t n4 = n / 4;
+  round_tf32_copy_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(dst),
+                                                                       reinterpret_cast<const float4*>(src), n4);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
 
 int scatter_rows_add(int R, int E, int V, const int32_t* tok, const float* dX, Dropout drop, float* d_table,
                      cudaStream_t st) {

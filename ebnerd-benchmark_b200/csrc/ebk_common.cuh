@@ -29,12 +29,36 @@ void set_error(const char* fmt, ...);
     }                                                                                      \
   } while (0)
 
-#define EBK_LAUNCH_CHECK() EBK_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro -> also counts launches
+#define EBK_LAUNCH_CHECK()           \
+  do {                               \
+    ::ebk::note_launch();            \
+    EBK_CUDA(cudaGetLastError());    \
+  } while (0)
 
 #define EBK_TRY(call)              \
   do {                             \
     int s__ = (call);              \
     if (s__ != EBK_OK) return s__; \
+  } while (0)
+
+void note_launch();
+
+// ---- optional per-kernel profiling (CUDA events on the launching stream) ------------------
+enum ProfTag {
+  T_QKV_FWD = 0, T_ATTN_FWD, T_ATT_GEMM_FWD, T_POOL_FWD, T_POOL_BWD, T_COLSUM, T_ATT_WGRAD, T_ATT_DGRAD,
+  T_ATTN_BWD, T_QKV_WGRAD, T_QKV_DGRAD, T_SCATTER, T_SCORE, T_ADAM, T_NUM_TAGS
+};
+bool prof_on();
+void prof_begin(int tag, cudaStream_t st);
+void prof_end(int tag, cudaStream_t st);
+// run `call` (an int-returning launcher using stream `st`), timing it when profiling is enabled
+#define EBK_PROF(tag, call)                         \
+  do {                                              \
+    if (::ebk::prof_on()) ::ebk::prof_begin(tag, st); \
+    int s__ = (call);                               \
+    if (::ebk::prof_on()) ::ebk::prof_end(tag, st); \
+    if (s__ != EBK_OK) return s__;                  \
   } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -93,6 +117,19 @@ static inline Dropout make_dropout(bool training, float p, uint64_t seed) {
   return d;
 }
 
+// round-to-nearest to tf32 by bit arithmetic (the tensor core truncates the low 13 mantissa bits)
+__host__ __device__ __forceinline__ float round_tf32_bits(float x) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+#else
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&x, &u, 4);
+  return x;
+#endif
+}
+
 // ---- warp helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -118,21 +155,25 @@ struct GemmOperandA {
 
 int gemm_f32(const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc,
              int M, int N, int K, float beta, cudaStream_t st);
+// b_rounded: B already holds tf32-rounded values (round_tf32_copy / producers that round on store)
 int gemm_tf32(const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc,
-              int M, int N, int K, float beta, cudaStream_t st);
+              int M, int N, int K, float beta, cudaStream_t st, bool b_rounded = false);
 int gemm_dispatch(int math, const GemmOperandA& A, const float* B, int ldb, bool transB, float* C,
-                  int ldc, int M, int N, int K, float beta, cudaStream_t st);
+                  int ldc, int M, int N, int K, float beta, cudaStream_t st, bool b_rounded = false);
+// dst[i] = round-to-nearest-tf32(src[i])  (so that the tensor core's truncation is exact)
+int round_tf32_copy(float* dst, const float* src, size_t n, cudaStream_t st);
 
 int attention_core_fwd(int n_seq, int L, int nh, int dh, const float* qkv, float* y, cudaStream_t st);
+// round_out: store dqkv rounded to tf32 (it is the cp.async-staged B operand of the wgrad GEMM)
 int attention_core_bwd(int n_seq, int L, int nh, int dh, const float* qkv, const float* dy,
-                       Dropout drop, float* dqkv, cudaStream_t st);
+                       Dropout drop, float* dqkv, bool round_out, cudaStream_t st);
 
 // AttLayer2 pieces
 int attpool_fwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, float* hbuf /*[R,att] in: pre-act, out: tanh*/,
                 const float* attb, const float* attq, float* w /*[R]*/, float* out /*[n_seq,D]*/, cudaStream_t st);
 int attpool_bwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, const float* hbuf,
                 const float* attq, const float* w, const float* d_out, float* da /*[R]*/,
-                float* dpre /*[R,att]*/, float* dy /*[R,D] = w_t*d_out*/, cudaStream_t st);
+                float* dpre /*[R,att]*/, float* dy /*[R,D] = w_t*d_out*/, bool round_dpre, cudaStream_t st);
 // column sums: out[j] += sum_r coef[r] * X[r,j]   (coef may be NULL => 1); deterministic
 // two-stage reduction through `partial` (colsum_partial_floats(R, Ncols) floats of scratch)
 int colsum_accum_ws(int R, int Ncols, const float* X, int ldx, const float* coef, float* out, float* partial,

@@ -131,8 +131,11 @@ extern "C" int ebk_score_softmax_ce(int32_t B, int32_t C, int32_t D, const float
   EBK_CHECK_ARG((d_news == nullptr) == (d_user == nullptr), "score_softmax_ce: d_news/d_user must both be set or both NULL");
   EBK_CHECK_ARG(C <= 4096, "score_softmax_ce: C=%d > 4096", C);
   (void)SC_MAXC;
-  score_ce_kernel<<<B, 128, 2 * C * sizeof(float), (cudaStream_t)stream>>>(C, D, news, user, labels, loss_scale,
-                                                                         probs, loss_sum, d_news, d_user);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prof_on()) prof_begin(T_SCORE, st);
+  score_ce_kernel<<<B, 128, 2 * C * sizeof(float), st>>>(C, D, news, user, labels, loss_scale, probs, loss_sum,
+                                                         d_news, d_user);
+  if (prof_on()) prof_end(T_SCORE, st);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }
@@ -159,6 +162,7 @@ extern "C" int ebk_adam_keras_step(float* theta, float* g, float* m, float* v, s
   cudaStream_t st = (cudaStream_t)stream;
   const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   size_t n4 = n / 4;
+  if (prof_on()) prof_begin(T_ADAM, st);
   if (n4) {
     size_t blocks = (n4 + 255) / 256;
     size_t cap = 148 * 16;
@@ -171,6 +175,7 @@ extern "C" int ebk_adam_keras_step(float* theta, float* g, float* m, float* v, s
     adam_keras_tail_kernel<<<1, 32, 0, st>>>(theta, g, m, v, n4 * 4, n, alpha, omb1, omb2, eps, zero_grad);
     EBK_LAUNCH_CHECK();
   }
+  if (prof_on()) prof_end(T_ADAM, st);
   return EBK_OK;
 }
 

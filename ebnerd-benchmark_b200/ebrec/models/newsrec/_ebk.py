@@ -23,6 +23,7 @@ SYMBOLS = [
     "ebk_last_error", "ebk_version", "ebk_device_ok",
     "ebk_seqenc_workspace_bytes", "ebk_seqenc_fwd", "ebk_seqenc_bwd",
     "ebk_score_softmax_ce", "ebk_score_sigmoid", "ebk_adam_keras_step",
+    "ebk_launch_count", "ebk_prof_enable", "ebk_prof_num_tags", "ebk_prof_tag_name", "ebk_prof_collect",
     "ebk_gemm", "ebk_attention_core_fwd", "ebk_attention_core_bwd", "ebk_dropout_mask",
 ]
 
@@ -75,6 +76,11 @@ def lib() -> C.CDLL:
         fn = getattr(l, name)
         if name not in ("ebk_last_error", "ebk_seqenc_workspace_bytes"):
             fn.restype = C.c_int
+    l.ebk_launch_count.restype = C.c_longlong
+    l.ebk_prof_tag_name.restype = C.c_char_p
+    l.ebk_prof_tag_name.argtypes = [C.c_int]
+    l.ebk_prof_enable.argtypes = [C.c_int]
+    l.ebk_prof_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     _lib = l
     return l
 
@@ -96,6 +102,16 @@ def ptr(t: torch.Tensor | None):
         return None
     assert t.is_cuda and t.is_contiguous(), "ebk needs contiguous CUDA tensors"
     return C.c_void_p(t.data_ptr())
+
+
+def prof_collect() -> dict[str, tuple[float, int]]:
+    """{kernel-group name: (total ms, count)} recorded since ebk_prof_enable(1)."""
+    l = lib()
+    n = l.ebk_prof_num_tags()
+    ms = (C.c_double * n)()
+    cnt = (C.c_longlong * n)()
+    check(l.ebk_prof_collect(ms, cnt))
+    return {l.ebk_prof_tag_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i]}
 
 
 def stream():

@@ -123,6 +123,9 @@ class NRMSEngine:
     def count_params(self) -> int:
         return int(sum(int(np.prod(s)) for _, s in self.params.spec))
 
+    def trainable_params(self) -> int:
+        return self.count_params()
+
     # ------------------------------------------------------------------ scratch
     def _desc(self, kind: str, n_seq: int) -> _ebk.SeqEncDesc:
         if kind == "news":
@@ -201,6 +204,36 @@ class NRMSEngine:
             _ebk.check(lib.ebk_score_softmax_ce(B, C_, self.D, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(labels),
                                                 0.0, _ebk.ptr(out), _ebk.ptr(loss), None, None, _ebk.stream()))
         return out
+
+    def eval_loss_dev(self, tok_all, labels, B, C_):
+        """Validation forward: dropout off, mean CE over the batch and the softmax probabilities."""
+        lib = _ebk.lib()
+        _, news_c, u, _ = self.forward_logits_parts(tok_all, B, C_)
+        probs = self._buf("probs", (B, C_))
+        loss = self._buf("loss", (1,))
+        loss.zero_()
+        _ebk.check(lib.ebk_score_softmax_ce(B, C_, self.D, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(labels), 1.0 / B,
+                                            _ebk.ptr(probs), _ebk.ptr(loss), None, None, _ebk.stream()))
+        return loss, probs
+
+    def encode_host(self, kind: str, x: np.ndarray) -> np.ndarray:
+        """newsencoder.predict ([N,T] ids -> [N,D]) / userencoder.predict ([B,H,T] ids -> [B,D])."""
+        lib, P = _ebk.lib(), self.params
+        x = np.asarray(x)
+        if kind == "news":
+            tok = torch.from_numpy(np.ascontiguousarray(x.reshape(-1, self.T), dtype=np.int32)).to(self.device)
+            dn = self._desc("news", tok.shape[0])
+            wn = self._workspace("news", dn)
+            out = torch.empty((tok.shape[0], self.D), device=self.device)
+            _ebk.check(lib.ebk_seqenc_fwd(C.byref(dn), _ebk.ptr(tok), _ebk.ptr(P.p("table")),
+                                          _ebk.ptr(P.p("news_Wqkv")), _ebk.ptr(P.p("news_attW")),
+                                          _ebk.ptr(P.p("news_attb")), _ebk.ptr(P.p("news_attq")), 0, 0, 0,
+                                          _ebk.ptr(wn), wn.numel(), _ebk.ptr(out), _ebk.stream()))
+            return out.cpu().numpy()
+        B = x.shape[0]
+        tok = torch.from_numpy(np.ascontiguousarray(x.reshape(B * self.H, self.T), dtype=np.int32)).to(self.device)
+        _, u, _ = self._encode(tok, B, self.H, False)
+        return u.clone().cpu().numpy()
 
     def step_seeds(self) -> tuple[int, int]:
         base = _mix(self.seed, self.step_count * self.world + self.rank)

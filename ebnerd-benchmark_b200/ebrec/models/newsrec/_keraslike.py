@@ -1,0 +1,314 @@
+"""Minimal Keras-shaped host facade over a device engine.
+
+The reference drives its models through ``keras.Model`` (third-party): ``summary``,
+``compile``, ``fit``, ``predict``, ``save_weights`` ... (call sites:
+examples/quick_start/nrms_dummy.py:16,46-47; examples/reproducibility_scripts/ebnerd_nrms.py:244-260,302,338).
+These classes keep that surface -- same method names, argument meaning and return types
+(numpy arrays, ``History`` with ``.history``) -- while every FLOP runs in the ebk CUDA
+library.  No TensorFlow import; callbacks are duck-typed (``set_model``, ``on_train_begin``,
+``on_epoch_begin``, ``on_epoch_end(epoch, logs)``, ``on_train_end``).
+"""
+from __future__ import annotations
+
+import queue
+import threading
+import time
+
+import numpy as np
+import torch
+
+
+class History:
+    def __init__(self):
+        self.history: dict[str, list[float]] = {}
+        self.epoch: list[int] = []
+        self.model = None
+
+    def _append(self, epoch: int, logs: dict):
+        self.epoch.append(epoch)
+        for k, v in logs.items():
+            self.history.setdefault(k, []).append(v)
+
+
+class _LR:
+    """Mutable learning-rate handle; behaves like a float and like a tf.Variable (assign/numpy)."""
+
+    def __init__(self, engine):
+        self._e = engine
+
+    def numpy(self):
+        return np.float32(self._e.lr)
+
+    def assign(self, v):
+        self._e.lr = float(v)
+
+    def __float__(self):
+        return float(self._e.lr)
+
+    def __repr__(self):
+        return f"{self._e.lr}"
+
+
+class AdamHandle:
+    """What ``model.optimizer`` returns: Keras-form Adam state lives in the engine."""
+
+    def __init__(self, engine):
+        self._e = engine
+        self._lr = _LR(engine)
+
+    @property
+    def lr(self):
+        return self._lr
+
+    @lr.setter
+    def lr(self, v):
+        self._e.lr = float(v)
+
+    learning_rate = lr
+
+    @property
+    def iterations(self):
+        return self._e.step_count
+
+    def get_config(self):
+        e = self._e
+        return {"name": "Adam", "learning_rate": e.lr, "beta_1": e.beta1, "beta_2": e.beta2, "epsilon": e.eps}
+
+
+def keras_auc(y_true: np.ndarray, y_pred: np.ndarray, num_thresholds: int = 200) -> float:
+    """keras.metrics.AUC(num_thresholds=200, curve='ROC', summation_method='interpolation') over
+    flattened predictions -- what ``metrics=['AUC']`` means in ebnerd_nrms.py:244-248."""
+    yt = np.asarray(y_true).reshape(-1) > 0.5
+    yp = np.asarray(y_pred, dtype=np.float64).reshape(-1)
+    eps = 1e-7
+    th = np.array([0.0 - eps] + [(i + 1) / (num_thresholds - 1) for i in range(num_thresholds - 2)] + [1.0 + eps])
+    order = np.sort(yp[yt])
+    tp = order.size - np.searchsorted(order, th, side="right")
+    order_n = np.sort(yp[~yt])
+    fp = order_n.size - np.searchsorted(order_n, th, side="right")
+    fn, tn = yt.sum() - tp, (~yt).sum() - fp
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tpr = np.where(tp + fn > 0, tp / (tp + fn), 0.0)
+        fpr = np.where(fp + tn > 0, fp / (fp + tn), 0.0)
+    return float(np.sum((fpr[:-1] - fpr[1:]) * (tpr[:-1] + tpr[1:]) / 2.0))
+
+
+class _Prefetcher:
+    """Background-thread batch fetch (Keras' OrderedEnqueuer with workers=1 does the same)."""
+
+    def __init__(self, fetch, order, depth=3):
+        self.q: queue.Queue = queue.Queue(maxsize=depth)
+        self.t = threading.Thread(target=self._run, args=(fetch, order), daemon=True)
+        self.t.start()
+
+    def _run(self, fetch, order):
+        try:
+            for i in order:
+                self.q.put(fetch(i))
+        except BaseException as e:  # surface loader errors in the consumer
+            self.q.put(e)
+        self.q.put(None)
+
+    def __iter__(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+
+
+def _is_sequence(x) -> bool:
+    return hasattr(x, "__getitem__") and hasattr(x, "__len__") and not isinstance(x, (tuple, list, np.ndarray))
+
+
+class KerasLikeModel:
+    """Common fit/predict loop.  Subclasses provide ``_train_batch``, ``_eval_batch``,
+    ``_predict_batch`` (host arrays in, numpy out) and weight accessors via ``self._engine``."""
+
+    def __init__(self, owner, engine, name, head):
+        self._owner, self._engine, self.name, self._head = owner, engine, name, head
+        self.optimizer = AdamHandle(engine)
+        self.loss = None
+        self._metrics: list[str] = []
+        self.stop_training = False
+        self.history = None
+
+    # ---- Keras surface ------------------------------------------------------------
+    def compile(self, optimizer=None, loss=None, metrics=None, **_):
+        if loss is not None:
+            self.loss = loss
+        if metrics is not None:
+            self._metrics = [str(m).lower() for m in metrics]
+        if optimizer is not None and not isinstance(optimizer, AdamHandle):
+            lr = getattr(optimizer, "learning_rate", getattr(optimizer, "lr", None))
+            if lr is not None:
+                self._engine.lr = float(lr.numpy() if hasattr(lr, "numpy") else lr)
+
+    def count_params(self) -> int:
+        return self._engine.count_params()
+
+    def get_weights(self):
+        return self._engine.get_weights()
+
+    def set_weights(self, weights):
+        self._engine.set_weights(weights)
+
+    @property
+    def variables(self):
+        return self.get_weights()
+
+    def save_weights(self, filepath, overwrite=True, **_):
+        import os
+
+        os.makedirs(os.path.dirname(str(filepath)) or ".", exist_ok=True)
+        e = self._engine
+        state = {"weights": [torch.from_numpy(w) for w in e.get_weights()], "step_count": e.step_count,
+                 "adam_m": e.params.m.cpu(), "adam_v": e.params.v.cpu(), "lr": e.lr}
+        torch.save(state, str(filepath))
+
+    def load_weights(self, filepath, **_):
+        e = self._engine
+        state = torch.load(str(filepath), map_location="cpu", weights_only=True)
+        e.set_weights([w.numpy() for w in state["weights"]])
+        if "adam_m" in state and state["adam_m"].numel() == e.params.m.numel():
+            e.params.m.copy_(state["adam_m"])
+            e.params.v.copy_(state["adam_v"])
+            e.step_count = int(state["step_count"])
+
+    def summary(self, print_fn=print):
+        e = self._engine
+        print_fn(f'Model: "{self.name}"')
+        print_fn("_" * 65)
+        print_fn(f"{'Parameter (HBM, fp32)':<40}{'Shape':<18}{'Param #':>7}")
+        print_fn("=" * 65)
+        for n, s in e.params.spec:
+            print_fn(f"{n:<40}{str(tuple(s)):<18}{int(np.prod(s)):>7}")
+        print_fn("=" * 65)
+        print_fn(f"Total params: {e.count_params():,}")
+        print_fn(f"Trainable params: {e.trainable_params():,}")
+        print_fn("_" * 65)
+
+    # ---- batching -------------------------------------------------------------------
+    @staticmethod
+    def _n_samples(x):
+        return int(np.asarray(x[0]).shape[0])
+
+    def _batches(self, x, y, batch_size, shuffle, rng):
+        """Yield (inputs_tuple, y_or_None).  Arrays: Keras shuffles samples; Sequence: batch order."""
+        if _is_sequence(x):
+            order = np.arange(len(x))
+            if shuffle:
+                rng.shuffle(order)
+
+            def fetch(i):
+                item = x[int(i)]
+                return (item[0], item[1]) if isinstance(item, tuple) and len(item) == 2 else (item, None)
+
+            yield from _Prefetcher(fetch, order)
+            return
+        xs = tuple(np.asarray(a) for a in x)
+        n = self._n_samples(xs)
+        bs = int(batch_size or 32)
+        idx = np.arange(n)
+        if shuffle:
+            rng.shuffle(idx)
+        for s in range(0, n, bs):
+            sel = idx[s: s + bs]
+            if not shuffle:
+                sel = slice(s, s + bs)
+            yield tuple(a[sel] for a in xs), (None if y is None else np.asarray(y)[sel])
+
+    # ---- fit / evaluate / predict -----------------------------------------------------
+    def fit(self, x=None, y=None, batch_size=None, epochs=1, verbose=1, callbacks=None, validation_data=None,
+            shuffle=True, initial_epoch=0, **_):
+        cbs = list(callbacks or [])
+        hist = History()
+        hist.model = self
+        self.history = hist
+        self.stop_training = False
+        for cb in cbs:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
+        for cb in cbs:
+            if hasattr(cb, "on_train_begin"):
+                cb.on_train_begin({})
+        rng = np.random.default_rng(self._engine.seed + 7919)
+        for epoch in range(initial_epoch, epochs):
+            for cb in cbs:
+                if hasattr(cb, "on_epoch_begin"):
+                    cb.on_epoch_begin(epoch, {})
+            t0 = time.time()
+            tot_loss = torch.zeros(1, device=self._engine.device)
+            n_seen = 0
+            ys, ps = [], []
+            nb = 0
+            for inputs, yb in self._batches(x, y, batch_size, shuffle, rng):
+                loss_dev, probs_dev, bsz = self._train_batch(inputs, yb)
+                tot_loss += loss_dev * bsz  # stays on device: no per-step host sync
+                n_seen += bsz
+                nb += 1
+                if "auc" in self._metrics:
+                    ys.append(np.asarray(yb))
+                    ps.append(probs_dev.clone())
+            logs = {"loss": float(tot_loss) / max(n_seen, 1)}
+            if "auc" in self._metrics and ys:
+                logs["auc"] = keras_auc(np.concatenate(ys), torch.cat(ps).cpu().numpy())
+            if validation_data is not None:
+                vlogs = self.evaluate(validation_data, verbose=0, return_dict=True)
+                logs.update({f"val_{k}": v for k, v in vlogs.items()})
+            logs["lr"] = float(self._engine.lr)
+            if verbose:
+                dt = time.time() - t0
+                msg = " - ".join(f"{k}: {v:.4f}" for k, v in logs.items() if k != "lr")
+                print(f"Epoch {epoch + 1}/{epochs}\n{nb}/{nb} - {dt:.0f}s {1e3 * dt / max(nb, 1):.0f}ms/step - {msg}")
+            hist._append(epoch, logs)
+            for cb in cbs:
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(epoch, logs)
+            if self.stop_training:
+                break
+        for cb in cbs:
+            if hasattr(cb, "on_train_end"):
+                cb.on_train_end({})
+        return hist
+
+    def evaluate(self, x=None, y=None, batch_size=None, verbose=0, return_dict=False, **_):
+        tot, n_seen, ys, ps = 0.0, 0, [], []
+        rng = np.random.default_rng(0)
+        for inputs, yb in self._batches(x, y, batch_size, False, rng):
+            loss, probs, bsz = self._eval_batch(inputs, yb)
+            tot += loss * bsz
+            n_seen += bsz
+            ys.append(np.asarray(yb))
+            ps.append(probs)
+        logs = {"loss": tot / max(n_seen, 1)}
+        if "auc" in self._metrics and ys:
+            logs["auc"] = keras_auc(np.concatenate(ys), np.concatenate(ps))
+        if return_dict:
+            return logs
+        return logs["loss"] if len(logs) == 1 else list(logs.values())
+
+    def predict(self, x, batch_size=None, verbose=0, **_):
+        outs = []
+        rng = np.random.default_rng(0)
+        for inputs, _y in self._batches(x, None, batch_size, False, rng):
+            outs.append(self._predict_batch(inputs))
+        if not outs:
+            return np.zeros((0, 1), np.float32)
+        return np.concatenate(outs, axis=0)
+
+    def train_on_batch(self, x, y):
+        loss, _, _ = self._train_batch(tuple(np.asarray(a) for a in x), np.asarray(y))
+        return float(loss)
+
+    def test_on_batch(self, x, y):
+        loss, _, _ = self._eval_batch(tuple(np.asarray(a) for a in x), np.asarray(y))
+        return float(loss)
+
+    def predict_on_batch(self, x):
+        return self._predict_batch(tuple(np.asarray(a) for a in x))
+
+    def __call__(self, x, training=False):
+        return self.predict_on_batch(x)

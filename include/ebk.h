@@ -120,6 +120,19 @@ int ebk_adam_keras_step(float* theta, float* g, float* m, float* v, size_t n, fl
                         double beta1, double beta2, float eps, int zero_grad, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): number of kernels this library has launched so far, and an
+ * optional per-kernel timer (CUDA events recorded on the launching stream around every
+ * internal launch while enabled).  Slots [0, ebk_prof_num_tags()) are named by
+ * ebk_prof_tag_name(); ebk_prof_collect() synchronises the recorded events and returns the
+ * summed milliseconds and launch-group counts per slot since the last ebk_prof_enable(1).
+ * ---------------------------------------------------------------------------------- */
+long long ebk_launch_count(void);
+int ebk_prof_enable(int on);
+int ebk_prof_num_tags(void);
+const char* ebk_prof_tag_name(int slot);
+int ebk_prof_collect(double* ms_out, long long* count_out);
+
+/* ------------------------------------------------------------------------------------
  * Building blocks exported for the parity tests.
  * ---------------------------------------------------------------------------------- */
 /* C[M,N] = (beta ? C : 0) + opA(A)[M,K] * opB(B)[K,N]; row-major; ld* in elements. */

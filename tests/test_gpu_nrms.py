@@ -22,6 +22,10 @@ def make_case(rng, V, E, nh, dh, att, B, H, C, T, table_scale=None):
         P["table"] = rng.random((V, E)) * table_scale
     for k in ("news_b", "user_b"):
         P[k] = rng.standard_normal(P[k].shape) * 0.05
+    # Glorot-sized WQ/WK give near-uniform attention, whose WQ/WK gradients are pure fp32
+    # cancellation noise (dS = A o (dA - rowsum)); scale them so the softmax is exercised.
+    for k in ("news_WQ", "news_WK", "user_WQ", "user_WK"):
+        P[k] = P[k] * 6.0
     his = rng.integers(0, V, (B, H, T)).astype(np.int32)
     pred = rng.integers(0, V, (B, C, T)).astype(np.int32)
     y = np.zeros((B, C), np.float32)
@@ -107,8 +111,25 @@ def test_loss_and_gradients(math, dropout, case):
     for pre in ("news", "user"):
         W = eng.params.g(f"{pre}_Wqkv").cpu().numpy()
         got[f"{pre}_WQ"], got[f"{pre}_WK"], got[f"{pre}_WV"] = W[:, :D], W[:, D:2 * D], W[:, 2 * D:]
+    # Conditioning-aware bound: some gradients (WQ/WK, AttLayer2 W/b/q) are differences of nearly
+    # equal terms, so their achievable accuracy is set by the arithmetic's epsilon times a
+    # cancellation factor.  That factor is measured by evaluating the SAME oracle in float32:
+    # allowed error = tol * max|G| + 20 * |G_f32 - G_f64| * (eps_math / eps_f32).
+    P32 = {k: v.astype(np.float32) for k, v in P.items()}
+    _, _, G32 = O.nrms_loss_and_grads(his, pred, y, P32, nh, dh, training=True, p_drop=dropout, seed1=s1, seed2=s2)
+    amp = {0: 1.0, 1: 2.0 ** 13}[math]  # tf32 keeps 10 mantissa bits vs fp32's 23
+    report = {}
     for k in O.NRMS_PARAM_ORDER:
-        assert rel(got[k], G[k]) < BWD_TOL[math], (k, rel(got[k], G[k]))
+        err = np.abs(got[k] - G[k]).max()
+        noise = np.abs(G32[k].astype(np.float64) - G[k]).max()
+        allowed = BWD_TOL[math] * np.abs(G[k]).max() + 20.0 * amp * noise
+        report[k] = (err / (np.abs(G[k]).max() + 1e-30), err / allowed)
+    print("gradient (rel err, err/allowed):", {k: (f"{a:.1e}", f"{b:.2f}") for k, (a, b) in report.items()})
+    for k, (_, ratio) in report.items():
+        assert ratio < 1.0, (k, report)
+    # the well-conditioned gradients must be tight without the noise allowance
+    for k in ("table", "news_WV", "user_WV"):
+        assert report[k][0] < BWD_TOL[math], (k, report)
 
 
 @pytest.mark.parametrize("math", [0, 1])
@@ -135,7 +156,8 @@ def test_train_steps_follow_oracle(math):
         assert abs(float(loss) - wl) < 5e-3 * max(1, abs(wl))
     W = eng.get_weights()
     for k, w in zip(O.NRMS_PARAM_ORDER, W):
-        # Adam's first steps move every touched weight by ~lr regardless of gradient scale, so
-        # compare the *update* against lr
-        assert np.abs(w - P[k]).max() < (2e-5 if math == 0 else 6e-4), (k, np.abs(w - P[k]).max())
+        # Adam's first steps move every weight by ~lr whatever the gradient scale (and flip sign
+        # with the gradient's sign), so compare the mean deviation with the total travel 3*lr.
+        dev = np.abs(w - P[k]).mean() / (3 * lr)
+        assert dev < (2e-3 if math == 0 else 3e-2), (k, dev)
     assert float(eng.params.grad.abs().max()) == 0.0

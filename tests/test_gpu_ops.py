@@ -50,15 +50,17 @@ def test_gemm(ebk, math, tA, tB, M, N, K):
     B = rng.standard_normal((N, K) if tB else (K, N)).astype(np.float32)
     C0 = rng.standard_normal((M, N)).astype(np.float32)
     want = (A.T if tA else A).astype(np.float64) @ (B.T if tB else B).astype(np.float64)
+    Ad, Bd = dev(A), dev(B)  # keep alive: ptr() of a temporary would dangle
     for beta in (0.0, 1.0):
         Cd = dev(C0)
-        ebk.check(ebk.lib().ebk_gemm(math, tA, tB, M, N, K, ebk.ptr(dev(A)), A.shape[1], ebk.ptr(dev(B)), B.shape[1],
+        ebk.check(ebk.lib().ebk_gemm(math, tA, tB, M, N, K, ebk.ptr(Ad), A.shape[1], ebk.ptr(Bd), B.shape[1],
                                      ebk.ptr(Cd), N, beta, ebk.stream()))
         ref = want + (C0 if beta else 0)
         # tf32: 10-bit mantissa inputs, fp32 accumulate -> ~1e-3 relative to the row/col norms
         tol = 2e-5 if math == 0 else 2e-3
         scale = np.sqrt(K) + np.abs(C0).max()
-        assert np.abs(Cd.cpu().numpy() - ref).max() / scale < tol
+        err = np.abs(Cd.cpu().numpy() - ref).max() / scale
+        assert err < tol, f"beta={beta} err={err:.3e}"
 
 
 @pytest.mark.parametrize("n_seq,L,nh,dh", [(3, 30, 20, 20), (5, 20, 16, 16), (2, 50, 20, 20), (4, 7, 3, 4), (1, 64, 2, 20), (2, 33, 2, 32)])
@@ -91,7 +93,8 @@ def test_attention_core(ebk, n_seq, L, nh, dh):
     dK = np.einsum("nhqk,nhqd->nhkd", dS, Q) / np.sqrt(dh)
     want = np.concatenate([x.transpose(0, 2, 1, 3).reshape(n_seq, L, D) for x in (dQ, dK, dV)], axis=-1)
     dqkv = torch.empty(n_seq * L, 3 * D, device="cuda")
-    ebk.check(ebk.lib().ebk_attention_core_bwd(n_seq, L, nh, dh, ebk.ptr(qd), ebk.ptr(dev(dy.reshape(n_seq * L, D))),
+    dyd = dev(dy.reshape(n_seq * L, D))
+    ebk.check(ebk.lib().ebk_attention_core_bwd(n_seq, L, nh, dh, ebk.ptr(qd), ebk.ptr(dyd),
                                                p, seed, ebk.ptr(dqkv), ebk.stream()))
     assert relerr(dqkv.cpu().numpy().reshape(n_seq, L, 3 * D), want) < 5e-5
 
@@ -108,14 +111,15 @@ def test_score_softmax_ce_and_sigmoid(ebk):
         probs = torch.empty(B, Cc, device="cuda")
         ls = torch.zeros(1, device="cuda")
         dn, du = torch.empty(B, Cc, D, device="cuda"), torch.empty(B, D, device="cuda")
-        ebk.check(ebk.lib().ebk_score_softmax_ce(B, Cc, D, ebk.ptr(dev(news)), ebk.ptr(dev(user)), ebk.ptr(dev(y)), scale,
+        nd, ud, yd = dev(news), dev(user), dev(y)
+        ebk.check(ebk.lib().ebk_score_softmax_ce(B, Cc, D, ebk.ptr(nd), ebk.ptr(ud), ebk.ptr(yd), scale,
                                                  ebk.ptr(probs), ebk.ptr(ls), ebk.ptr(dn), ebk.ptr(du), ebk.stream()))
         assert relerr(probs.cpu().numpy(), p) < 1e-5
         assert abs(float(ls) - loss) < 1e-5 * max(1, abs(loss))
         assert relerr(dn.cpu().numpy(), dz[..., None] * user[:, None, :]) < 1e-5
         assert relerr(du.cpu().numpy(), np.einsum("bc,bcd->bd", dz, news)) < 1e-5
         sg = torch.empty(B, Cc, device="cuda")
-        ebk.check(ebk.lib().ebk_score_sigmoid(B, Cc, D, ebk.ptr(dev(news)), ebk.ptr(dev(user)), ebk.ptr(sg), ebk.stream()))
+        ebk.check(ebk.lib().ebk_score_sigmoid(B, Cc, D, ebk.ptr(nd), ebk.ptr(ud), ebk.ptr(sg), ebk.stream()))
         assert relerr(sg.cpu().numpy(), O.sigmoid(z)) < 1e-5
 
 
