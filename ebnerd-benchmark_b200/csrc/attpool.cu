@@ -141,6 +141,16 @@ __global__ void round_tf32_copy_kernel(float4* __restrict__ dst, const float4* _
   dst[i] = v;
 }
 
+__global__ void split_tf32_copy_kernel(float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ src,
+                                       size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = src[i];
+  const float h = round_tf32_bits(x);
+  hi[i] = h;
+  lo[i] = round_tf32_bits(x - h);
+}
+
 __global__ void scatter_rows_add_kernel(int R, int E4, int V, const int32_t* __restrict__ tok,
                                         const float4* __restrict__ dX, Dropout drop,
                                         float* __restrict__ d_table) {
@@ -204,6 +214,13 @@ int round_tf32_copy(float* dst, const float* src, size_t n, cudaStream_t st) {
   size_t n4 = n / 4;
   round_tf32_copy_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(dst),
                                                                        reinterpret_cast<const float4*>(src), n4);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+int split_tf32_copy(float* hi, float* lo, const float* src, size_t n, cudaStream_t st) {
+  if (n == 0) return EBK_OK;
+  split_tf32_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hi, lo, src, n);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

@@ -156,10 +156,15 @@ struct GemmOperandA {
 int gemm_f32(const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc,
              int M, int N, int K, float beta, cudaStream_t st);
 // b_rounded: B already holds tf32-rounded values (round_tf32_copy / producers that round on store)
+// x3: error-compensated 3xTF32 (needs B_lo when b_rounded: the low parts from split_tf32_copy)
 int gemm_tf32(const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc,
-              int M, int N, int K, float beta, cudaStream_t st, bool b_rounded = false);
+              int M, int N, int K, float beta, cudaStream_t st, bool b_rounded = false, bool x3 = false,
+              const float* B_lo = nullptr);
 int gemm_dispatch(int math, const GemmOperandA& A, const float* B, int ldb, bool transB, float* C,
-                  int ldc, int M, int N, int K, float beta, cudaStream_t st, bool b_rounded = false);
+                  int ldc, int M, int N, int K, float beta, cudaStream_t st, bool b_rounded = false,
+                  const float* B_lo = nullptr);
+// hi[i] = tf32(src[i]) (round to nearest), lo[i] = src[i] - hi[i]
+int split_tf32_copy(float* hi, float* lo, const float* src, size_t n, cudaStream_t st);
 // dst[i] = round-to-nearest-tf32(src[i])  (so that the tensor core's truncation is exact)
 int round_tf32_copy(float* dst, const float* src, size_t n, cudaStream_t st);
 

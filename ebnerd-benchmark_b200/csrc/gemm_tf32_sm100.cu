@@ -36,6 +36,7 @@ constexpr uint32_t SPIN_LIMIT = 1u << 26;  // bounded mbarrier spins: a protocol
 struct Params {
   const float* A; int lda; const int32_t* a_gather; int a_gather_limit; Dropout a_drop; int a_drop_ld;
   const float* B; int ldb;
+  const float* B_lo;  // X3 + pre-split B: the low parts (same layout as B)
   float* C; int ldc;
   int M, N, K;
   int BN;             // tile width, multiple of 16, <= 256
@@ -198,6 +199,15 @@ __device__ __forceinline__ float4 ldg_chunk(const float* src, int nvalid) {
 // round-to-nearest to tf32: the tensor core TRUNCATES the low 13 mantissa bits of an fp32 word,
 // so adding half a tf32 ulp to the bit pattern beforehand makes that truncation a rounding.
 __device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+// 3xTF32 split: x = hi + lo with hi exactly a tf32 value (round to nearest) and lo = x - hi exact
+// in fp32 (|lo| <= 2^-11 |x|); the products hi*hi + lo*hi + hi*lo recover ~fp32 accuracy.
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = rn_tf32(x - hi);
+}
+__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
+  split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+}
 
 // cp.async path (operand already tf32-rounded in memory, no mask)
 template <bool MN>
@@ -228,8 +238,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 // B_REG: B is staged through registers with in-flight tf32 rounding (generic callers); otherwise B
 // must already be tf32-rounded in memory and is staged with cp.async.
-template <bool A_MN, bool B_MN, bool B_REG>
-__global__ void __launch_bounds__(THREADS, 2) gemm_tf32_kernel(const Params p) {
+// X3: error-compensated 3xTF32 (hi/lo split of both operands, three MMAs per k-chunk) for the
+// inference forward, whose click scores must match the fp32 reference to 1e-3.
+template <bool A_MN, bool B_MN, bool B_REG, bool X3>
+__global__ void __launch_bounds__(THREADS, X3 ? 1 : 2) gemm_tf32_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -241,9 +253,11 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tf32_kernel(const Params p) {
   const int BN = p.BN;
   const int bn_pad = (BN + 31) & ~31;  // MN-major B rows are staged in 32-wide groups
   const int b_ext = B_MN ? bn_pad : BN;
-  const uint32_t a_bytes = BM * BK * 4;                                   // 16 KB
-  const uint32_t b_bytes = (uint32_t)b_ext * BK * 4;                      // <= 32 KB
-  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
+  constexpr uint32_t NSPLIT = X3 ? 2u : 1u;                               // hi [+ lo] tiles per operand
+  const uint32_t a_tile = BM * BK * 4;                                    // 16 KB
+  const uint32_t b_tile = ((uint32_t)b_ext * BK * 4 + 1023u) & ~1023u;    // <= 32 KB
+  const uint32_t a_bytes = NSPLIT * a_tile;
+  const uint32_t stage_bytes = a_bytes + NSPLIT * b_tile;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_base = smem_u32(smem);
 
@@ -296,7 +310,10 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tf32_kernel(const Params p) {
         mbar_wait(smem_u32(&empty_bar[s]), (uint32_t)((round & 1) ^ 1));
         uint8_t* pa = smem + (size_t)s * stage_bytes;
         const uint32_t sb = smem_base + (uint32_t)s * stage_bytes + a_bytes;
-        if (!B_REG) stage_async<B_MN>(sb, p.B, p.ldb, n0, p.N, b_ext, k0, p.K, ptid);
+        if (!B_REG) {
+          stage_async<B_MN>(sb, p.B, p.ldb, n0, p.N, b_ext, k0, p.K, ptid);
+          if (X3) stage_async<B_MN>(sb + b_tile, p.B_lo, p.ldb, n0, p.N, b_ext, k0, p.K, ptid);
+        }
         // ---- A: dropout mask (zeroing only; 1/(1-p) is applied as alpha in the epilogue),
         //         round to tf32, store with the UMMA swizzle ----
 #pragma unroll
@@ -308,8 +325,16 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tf32_kernel(const Params p) {
             const float4 f = p.a_drop.factor4(srow * (uint64_t)p.a_drop_ld + scol);  // scale forced to 1
             v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
           }
-          v.x = rn_tf32(v.x); v.y = rn_tf32(v.y); v.z = rn_tf32(v.z); v.w = rn_tf32(v.w);
-          *reinterpret_cast<float4*>(pa + (A_MN ? mn_off(arow[q], ac[q], a_groups) : k_off(arow[q], ac[q]))) = v;
+          const uint32_t off = A_MN ? mn_off(arow[q], ac[q], a_groups) : k_off(arow[q], ac[q]);
+          if (X3) {
+            float4 hi, lo;
+            split4(v, hi, lo);
+            *reinterpret_cast<float4*>(pa + off) = hi;
+            *reinterpret_cast<float4*>(pa + a_tile + off) = lo;
+          } else {
+            v.x = rn_tf32(v.x); v.y = rn_tf32(v.y); v.z = rn_tf32(v.z); v.w = rn_tf32(v.w);
+            *reinterpret_cast<float4*>(pa + off) = v;
+          }
         }
         if (B_REG) {
           uint8_t* pb = pa + a_bytes;
@@ -332,8 +357,16 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tf32_kernel(const Params p) {
             for (int q = 0; q < 8; ++q) {
               if (!bok[q]) continue;
               float4 v = bv[q];
-              v.x = rn_tf32(v.x); v.y = rn_tf32(v.y); v.z = rn_tf32(v.z); v.w = rn_tf32(v.w);
-              *reinterpret_cast<float4*>(pb + (B_MN ? mn_off(brow[q], bc[q], b_groups) : k_off(brow[q], bc[q]))) = v;
+              const uint32_t off = B_MN ? mn_off(brow[q], bc[q], b_groups) : k_off(brow[q], bc[q]);
+              if (X3) {
+                float4 hi, lo;
+                split4(v, hi, lo);
+                *reinterpret_cast<float4*>(pb + off) = hi;
+                *reinterpret_cast<float4*>(pb + b_tile + off) = lo;
+              } else {
+                v.x = rn_tf32(v.x); v.y = rn_tf32(v.y); v.z = rn_tf32(v.z); v.w = rn_tf32(v.w);
+                *reinterpret_cast<float4*>(pb + off) = v;
+              }
             }
           }
         }
@@ -419,8 +452,14 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tf32_kernel(const Params p) {
           // K-major: +32 bytes inside the 128-byte swizzle row; MN-major: 8 k = two 4-row k-groups
           const uint32_t a_addr = sa + (A_MN ? (uint32_t)(2 * k) * a_sbo : (uint32_t)k * 32u);
           const uint32_t b_addr = sb + (B_MN ? (uint32_t)(2 * k) * b_sbo : (uint32_t)k * 32u);
-          umma_tf32(tmem, make_desc(a_addr, a_lbo, a_sbo, a_lt), make_desc(b_addr, b_lbo, b_sbo, b_lt), idesc,
-                    (uint32_t)((i | k) != 0));
+          const uint64_t da = make_desc(a_addr, a_lbo, a_sbo, a_lt), db = make_desc(b_addr, b_lbo, b_sbo, b_lt);
+          if (X3) {  // small terms first: lo*hi + hi*lo + hi*hi
+            umma_tf32(tmem, make_desc(a_addr + a_tile, a_lbo, a_sbo, a_lt), db, idesc, (uint32_t)((i | k) != 0));
+            umma_tf32(tmem, da, make_desc(b_addr + b_tile, b_lbo, b_sbo, b_lt), idesc, 1u);
+            umma_tf32(tmem, da, db, idesc, 1u);
+          } else {
+            umma_tf32(tmem, da, db, idesc, (uint32_t)((i | k) != 0));
+          }
         }
         umma_commit(smem_u32(&empty_bar[s]));  // frees the stage when these MMAs retire
       }
@@ -443,7 +482,7 @@ __global__ void zero_matrix_kernel(float* C, int ldc, int M, int N) {
 }  // namespace
 
 int gemm_tf32(const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc, int M, int N, int K,
-              float beta, cudaStream_t st, bool b_rounded) {
+              float beta, cudaStream_t st, bool b_rounded, bool x3, const float* B_lo) {
   if (M <= 0 || N <= 0) return EBK_OK;
   EBK_CHECK_ARG(K >= 0 && A.ptr && B && C, "gemm_tf32: null operand");
   // 16-byte cp.async needs 4-float aligned rows; tiny or unaligned problems take the fp32 FMA kernel.
@@ -456,7 +495,8 @@ int gemm_tf32(const GemmOperandA& A, const float* B, int ldb, bool transB, float
   p.a_drop_ld = A.drop_ld;
   p.alpha = A.drop.on() ? A.drop.scale : 1.0f;  // mask in the operand, scale on the accumulator
   p.a_drop.scale = 1.0f;
-  p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
+  EBK_CHECK_ARG(!(x3 && b_rounded && B_lo == nullptr), "gemm_tf32: 3xTF32 with a pre-split B needs B_lo");
+  p.B = B; p.B_lo = B_lo; p.ldb = ldb; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
   const bool a_mn = A.trans, b_mn = !transB;
   const int ntiles_n = ceil_div(N, 256);
   // MN-major B is staged in 32-column swizzle atoms -> keep the UMMA N a whole number of atoms
@@ -464,8 +504,8 @@ int gemm_tf32(const GemmOperandA& A, const float* B, int ldb, bool transB, float
   p.BN = ceil_div(ceil_div(N, ntiles_n), bn_quant) * bn_quant;
   const int bn_pad = (p.BN + 31) & ~31;
   const size_t b_bytes = align_up((size_t)(b_mn ? bn_pad : p.BN) * BK * 4, 1024);
-  const size_t stage_bytes = (size_t)BM * BK * 4 + b_bytes;
-  const size_t budget = 111 * 1024;  // two CTAs per SM
+  const size_t stage_bytes = ((size_t)BM * BK * 4 + b_bytes) * (x3 ? 2 : 1);
+  const size_t budget = x3 ? 220 * 1024 : 111 * 1024;  // two CTAs per SM (one for the 3-pass variant)
   int stages = (int)((budget - 1024) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) stages = 2;
@@ -490,23 +530,25 @@ int gemm_tf32(const GemmOperandA& A, const float* B, int ldb, bool transB, float
     EBK_LAUNCH_CHECK();
   }
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-#define LAUNCH3(AMN_, BMN_, BREG_)                                                                                  \
-  {                                                                                                                 \
-    EBK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<AMN_, BMN_, BREG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  (int)smem));                                                                      \
-    gemm_tf32_kernel<AMN_, BMN_, BREG_><<<grid, THREADS, smem, st>>>(p);                                            \
+#define LAUNCH4(AMN_, BMN_, BREG_, X3_)                                                                  \
+  {                                                                                                      \
+    EBK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<AMN_, BMN_, BREG_, X3_>,                               \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    gemm_tf32_kernel<AMN_, BMN_, BREG_, X3_><<<grid, THREADS, smem, st>>>(p);                             \
   }
-#define LAUNCH(AMN_, BMN_)            \
-  {                                   \
-    if (b_rounded) LAUNCH3(AMN_, BMN_, false) \
-    else LAUNCH3(AMN_, BMN_, true)    \
+#define LAUNCH(AMN_, BMN_)                                   \
+  {                                                          \
+    if (b_rounded && !x3) LAUNCH4(AMN_, BMN_, false, false)  \
+    else if (b_rounded && x3) LAUNCH4(AMN_, BMN_, false, true) \
+    else if (!x3) LAUNCH4(AMN_, BMN_, true, false)           \
+    else LAUNCH4(AMN_, BMN_, true, true)                     \
   }
   if (!a_mn && !b_mn) LAUNCH(false, false)
   else if (!a_mn && b_mn) LAUNCH(false, true)
   else if (a_mn && !b_mn) LAUNCH(true, false)
   else LAUNCH(true, true)
 #undef LAUNCH
-#undef LAUNCH3
+#undef LAUNCH4
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

@@ -18,6 +18,7 @@ LIB_PATH = Path(os.environ.get("EBK_LIB", _PKG_ROOT / "csrc" / "libebk.so"))
 
 MATH_FP32 = 0
 MATH_TF32 = 1
+MATH_TF32X3 = 2
 
 SYMBOLS = [
     "ebk_last_error", "ebk_version", "ebk_device_ok",

@@ -78,6 +78,9 @@ class NRMSEngine:
         self.dropout = float(dropout)
         self.lr, self.beta1, self.beta2, self.eps = float(lr), beta1, beta2, eps
         self.math = int(math)
+        # inference (predict / scorer / validation): the click scores must match the fp32 reference to
+        # 1e-3, which single-pass tf32 cannot guarantee for large logits -> error-compensated 3xTF32
+        self.math_infer = _ebk.MATH_TF32X3 if self.math == _ebk.MATH_TF32 else self.math
         self.seed = 0 if seed is None else int(seed)
         self.step_count = 0  # optimizer iterations
         D, A = self.D, self.att
@@ -127,10 +130,11 @@ class NRMSEngine:
         return self.count_params()
 
     # ------------------------------------------------------------------ scratch
-    def _desc(self, kind: str, n_seq: int) -> _ebk.SeqEncDesc:
+    def _desc(self, kind: str, n_seq: int, training: bool = False) -> _ebk.SeqEncDesc:
+        math = self.math if training else self.math_infer
         if kind == "news":
-            return _ebk.SeqEncDesc(n_seq, self.T, self.E, self.nh, self.dh, self.att, self.V, self.dropout, self.math)
-        return _ebk.SeqEncDesc(n_seq, self.H, self.D, self.nh, self.dh, self.att, 0, 0.0, self.math)
+            return _ebk.SeqEncDesc(n_seq, self.T, self.E, self.nh, self.dh, self.att, self.V, self.dropout, math)
+        return _ebk.SeqEncDesc(n_seq, self.H, self.D, self.nh, self.dh, self.att, 0, 0.0, math)
 
     def _workspace(self, kind: str, desc) -> torch.Tensor:
         need = _ebk.lib().ebk_seqenc_workspace_bytes(C.byref(desc))
@@ -157,7 +161,7 @@ class NRMSEngine:
         N = tok_all.shape[0]
         if Hh != self.H:
             raise ValueError(f"history length {Hh} != hparams.history_size {self.H}")
-        dn = self._desc("news", N)
+        dn = self._desc("news", N, training)
         wn = self._workspace("news", dn)
         n_all = self._buf("n_all", (N, self.D))
         _ebk.check(lib.ebk_seqenc_fwd(C.byref(dn), _ebk.ptr(tok_all), _ebk.ptr(P.p("table")),
@@ -165,7 +169,7 @@ class NRMSEngine:
                                       _ebk.ptr(P.p("news_attb")), _ebk.ptr(P.p("news_attq")),
                                       int(training), seeds[0], seeds[1], _ebk.ptr(wn), wn.numel(),
                                       _ebk.ptr(n_all), _ebk.stream()))
-        du = self._desc("user", B)
+        du = self._desc("user", B, training)
         wu = self._workspace("user", du)
         u = self._buf("u", (B, self.D))
         _ebk.check(lib.ebk_seqenc_fwd(C.byref(du), None, _ebk.ptr(n_all), _ebk.ptr(P.p("user_Wqkv")),

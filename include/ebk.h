@@ -39,7 +39,8 @@ typedef enum {
 /* Arithmetic mode of the dense contractions. */
 typedef enum {
   EBK_MATH_FP32 = 0, /* CUDA-core fp32 FMA (exact-ish; small shapes, debugging) */
-  EBK_MATH_TF32 = 1  /* tcgen05 kind::tf32 tensor cores, fp32 accumulate in TMEM */
+  EBK_MATH_TF32 = 1, /* tcgen05 kind::tf32 tensor cores (operands rounded to nearest), fp32 accumulate in TMEM */
+  EBK_MATH_TF32X3 = 2 /* error-compensated 3xTF32 (hi/lo operand split, 3 MMAs): ~fp32 accuracy; inference default */
 } ebk_math;
 
 const char* ebk_last_error(void);
