@@ -48,10 +48,13 @@ void prof_end(int tag, cudaStream_t st) {
 }
 
 int gemm_dispatch(int math, const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc,
-                  int M, int N, int K, float beta, cudaStream_t st, bool b_rounded, const float* B_lo) {
-  if (math == EBK_MATH_TF32) return gemm_tf32(A, B, ldb, transB, C, ldc, M, N, K, beta, st, b_rounded);
-  if (math == EBK_MATH_TF32X3)
-    return gemm_tf32(A, B, ldb, transB, C, ldc, M, N, K, beta, st, b_rounded && B_lo != nullptr, true, B_lo);
+                  int M, int N, int K, float beta, cudaStream_t st, int b_mode, const float* B_lo) {
+  if (math == EBK_MATH_TF32) return gemm_tf32(A, B, ldb, transB, C, ldc, M, N, K, beta, st, b_mode);
+  if (math == EBK_MATH_TF32X3) {
+    // only a B that comes with its low parts can skip the in-flight split
+    const int mode = (b_mode != GEMM_B_RAW && B_lo == nullptr) ? GEMM_B_RAW : b_mode;
+    return gemm_tf32(A, B, ldb, transB, C, ldc, M, N, K, beta, st, mode, true, B_lo);
+  }
   if (math == EBK_MATH_FP32) return gemm_f32(A, B, ldb, transB, C, ldc, M, N, K, beta, st);
   set_error("unknown math mode %d", math);
   return EBK_ERR_INVALID;
@@ -64,8 +67,10 @@ struct SeqWs {
   float *qkv, *y0, *hbuf, *w;          // saved by forward
   float *dy, *dpre, *da, *dqkv, *dx;   // backward scratch
   float* colsum;                       // column-sum partials
-  float *wqkv_r, *attw_r;              // tf32-rounded copies of the weights (B operands of the tcgen05 GEMMs)
-  float *wqkv_lo, *attw_lo;            // their 3xTF32 low parts (EBK_MATH_TF32X3)
+  // weights packed (tf32-rounded, UMMA tile layout) as B operands of the tcgen05 GEMMs:
+  float *wqkv_f, *attw_f;              //   forward  (B = W,   MN-major)
+  float *wqkv_d, *attw_d;              //   dgrad    (B = W^T, K-major)
+  float *wqkv_f_lo, *attw_f_lo;        //   3xTF32 low parts of the forward packs (EBK_MATH_TF32X3)
   size_t bytes;
 };
 
@@ -88,10 +93,12 @@ SeqWs seq_layout(const ebk_seqenc_desc& d, void* base) {
   w.dqkv = take(R * 3 * D);
   w.dx = take(R * (size_t)d.Din);
   w.colsum = take(colsum_partial_floats((int)R, d.att));
-  w.wqkv_r = take((size_t)d.Din * 3 * D);
-  w.attw_r = take(D * (size_t)d.att);
-  w.wqkv_lo = take((size_t)d.Din * 3 * D);
-  w.attw_lo = take(D * (size_t)d.att);
+  w.wqkv_f = take(gemm_tf32_packed_floats(3 * (int)D, d.Din, false));
+  w.attw_f = take(gemm_tf32_packed_floats(d.att, (int)D, false));
+  w.wqkv_d = take(gemm_tf32_packed_floats(d.Din, 3 * (int)D, true));
+  w.attw_d = take(gemm_tf32_packed_floats((int)D, d.att, true));
+  w.wqkv_f_lo = take(gemm_tf32_packed_floats(3 * (int)D, d.Din, false));
+  w.attw_f_lo = take(gemm_tf32_packed_floats(d.att, (int)D, false));
   w.bytes = off;
   return w;
 }
@@ -180,27 +187,32 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
 
   // B operands of the tensor-core GEMMs: tf32-rounded (to nearest) copies of the weights, kept in the
   // workspace for the backward pass.  The fp32 path uses the weights as they are.
+  // Tensor-core modes: the weights are packed once per call (rounded to tf32, arranged in the GEMM's
+  // shared-memory tile layout) and kept in the workspace for the backward pass.
   const bool tc = d->math != EBK_MATH_FP32;
   const bool x3 = d->math == EBK_MATH_TF32X3;
-  if (x3) {
-    EBK_TRY(split_tf32_copy(ws.wqkv_r, ws.wqkv_lo, Wqkv, (size_t)d->Din * 3 * D, st));
-    EBK_TRY(split_tf32_copy(ws.attw_r, ws.attw_lo, attW, (size_t)D * d->att, st));
-  } else if (tc) {
-    EBK_TRY(round_tf32_copy(ws.wqkv_r, Wqkv, (size_t)d->Din * 3 * D, st));
-    EBK_TRY(round_tf32_copy(ws.attw_r, attW, (size_t)D * d->att, st));
-  }
-  const float* Wqkv_b = tc ? ws.wqkv_r : Wqkv;
-  const float* attW_b = tc ? ws.attw_r : attW;
-  // (1) Q|K|V = dropout1(gather(table, tok)) . Wqkv        nrms.py:134-139, layers.py:214-230
   GemmOperandA ax{table_or_x, d->Din, false, tok, d->V, tok ? drop1 : none, d->Din};
-  EBK_PROF(T_QKV_FWD, gemm_dispatch(d->math, ax, Wqkv_b, 3 * D, false, ws.qkv, 3 * D, R, 3 * D, d->Din, 0.0f, st, tc,
-                                    x3 ? ws.wqkv_lo : nullptr));
+  GemmOperandA ay{ws.y0, D, false, nullptr, 0, drop2, D};
+  const bool pk_qkv = tc && gemm_tf32_eligible(ax, Wqkv, 3 * D, R, 3 * D, d->Din);
+  const bool pk_att = tc && gemm_tf32_eligible(ay, attW, d->att, R, d->att, D);
+  if (pk_qkv) {
+    EBK_TRY(gemm_tf32_pack_b(ws.wqkv_f, x3 ? ws.wqkv_f_lo : nullptr, Wqkv, 3 * D, false, 3 * D, d->Din, st));
+    if (!x3) EBK_TRY(gemm_tf32_pack_b(ws.wqkv_d, nullptr, Wqkv, 3 * D, true, d->Din, 3 * D, st));
+  }
+  if (pk_att) {
+    EBK_TRY(gemm_tf32_pack_b(ws.attw_f, x3 ? ws.attw_f_lo : nullptr, attW, d->att, false, d->att, D, st));
+    if (!x3) EBK_TRY(gemm_tf32_pack_b(ws.attw_d, nullptr, attW, d->att, true, D, d->att, st));
+  }
+  // (1) Q|K|V = dropout1(gather(table, tok)) . Wqkv        nrms.py:134-139, layers.py:214-230
+  EBK_PROF(T_QKV_FWD, gemm_dispatch(d->math, ax, pk_qkv ? ws.wqkv_f : Wqkv, 3 * D, false, ws.qkv, 3 * D, R, 3 * D,
+                                    d->Din, 0.0f, st, pk_qkv ? GEMM_B_PACKED : GEMM_B_RAW,
+                                    (pk_qkv && x3) ? ws.wqkv_f_lo : nullptr));
   // (2) per-head softmax(QK^T/sqrt(dh)) and the adjoint product    layers.py:231-252
   EBK_PROF(T_ATTN_FWD, attention_core_fwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st));
   // (3) pre-activation of AttLayer2: dropout2(Y0) . W              nrms.py:153-156, layers.py:65
-  GemmOperandA ay{ws.y0, D, false, nullptr, 0, drop2, D};
-  EBK_PROF(T_ATT_GEMM_FWD, gemm_dispatch(d->math, ay, attW_b, d->att, false, ws.hbuf, d->att, R, d->att, D, 0.0f, st, tc,
-                                         x3 ? ws.attw_lo : nullptr));
+  EBK_PROF(T_ATT_GEMM_FWD, gemm_dispatch(d->math, ay, pk_att ? ws.attw_f : attW, d->att, false, ws.hbuf, d->att, R,
+                                         d->att, D, 0.0f, st, pk_att ? GEMM_B_PACKED : GEMM_B_RAW,
+                                         (pk_att && x3) ? ws.attw_f_lo : nullptr));
   // (4) tanh, .q, exp, normalise (+1e-7), pool                     layers.py:65-81
   EBK_PROF(T_POOL_FWD, attpool_fwd(d->n_seq, d->L, D, d->att, ws.y0, drop2, ws.hbuf, attb, attq, ws.w, out, st));
   return EBK_OK;
@@ -231,33 +243,40 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   const Dropout drop2 = make_dropout(training != 0, d->dropout, seed2);
   const Dropout none = make_dropout(false, 0.0f, 0);
 
-  // tensor-core mode: the forward left tf32-rounded weights in the workspace, and the kernels that
-  // produce dpre / dQKV round them on store so they can be staged as B operands with cp.async.
+  // tensor-core mode: the forward left the packed weights in the workspace, and the kernels that
+  // produce dpre / dQKV round them to tf32 on store so they can be staged as B operands with cp.async.
   const bool tc = d->math != EBK_MATH_FP32;
   const bool x3 = d->math == EBK_MATH_TF32X3;
-  const float* Wqkv_b = tc ? ws.wqkv_r : Wqkv;
-  const float* attW_b = tc ? ws.attw_r : attW;
+  const bool rnd = tc && !x3;
+  GemmOperandA adp{ws.dpre, d->att, false, nullptr, 0, none, 0};
+  GemmOperandA adq{ws.dqkv, 3 * D, false, nullptr, 0, none, 0};
+  const bool pk_att = rnd && gemm_tf32_eligible(adp, attW, d->att, R, D, d->att) &&
+                      gemm_tf32_eligible(GemmOperandA{ws.y0, D, false, nullptr, 0, drop2, D}, attW, d->att, R, d->att, D);
+  const bool pk_qkv = rnd && gemm_tf32_eligible(adq, Wqkv, 3 * D, R, d->Din, 3 * D) &&
+                      gemm_tf32_eligible(GemmOperandA{table_or_x, d->Din, false, tok, d->V, tok ? drop1 : none, d->Din},
+                                         Wqkv, 3 * D, R, 3 * D, d->Din);
   // AttLayer2 backward (layers.py:55-81)
   EBK_PROF(T_POOL_BWD, attpool_bwd(d->n_seq, d->L, D, d->att, ws.y0, drop2, ws.hbuf, attq, ws.w, d_out, ws.da, ws.dpre,
-                      ws.dy, tc && !x3, st));
+                      ws.dy, rnd, st));
   EBK_PROF(T_COLSUM, colsum_accum_ws(R, d->att, ws.hbuf, d->att, ws.da, dattq, ws.colsum, st));   // dq = sum_r h_r da_r
   EBK_PROF(T_COLSUM, colsum_accum_ws(R, d->att, ws.dpre, d->att, nullptr, dattb, ws.colsum, st)); // db = sum_r dpre_r
   GemmOperandA ayT{ws.y0, D, true, nullptr, 0, drop2, D};                              // dW += X^T dpre
-  EBK_PROF(T_ATT_WGRAD, gemm_dispatch(d->math, ayT, ws.dpre, d->att, false, dattW, d->att, D, d->att, R, 1.0f, st, tc && !x3));
-  GemmOperandA adp{ws.dpre, d->att, false, nullptr, 0, none, 0};                       // dX += dpre W^T
-  EBK_PROF(T_ATT_DGRAD, gemm_dispatch(d->math, adp, attW_b, d->att, true, ws.dy, D, R, D, d->att, 1.0f, st, tc,
-                                      x3 ? ws.attw_lo : nullptr));
+  EBK_PROF(T_ATT_WGRAD, gemm_dispatch(d->math, ayT, ws.dpre, d->att, false, dattW, d->att, D, d->att, R, 1.0f, st,
+                                      rnd ? GEMM_B_ROUNDED : GEMM_B_RAW));
+  // dX += dpre W^T
+  EBK_PROF(T_ATT_DGRAD, gemm_dispatch(d->math, adp, pk_att ? ws.attw_d : attW, d->att, true, ws.dy, D, R, D, d->att,
+                                      1.0f, st, pk_att ? GEMM_B_PACKED : GEMM_B_RAW));
   // SelfAttention core backward (dropout2 mask applied while reading dy)
-  EBK_PROF(T_ATTN_BWD, attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, tc && !x3, st));
+  EBK_PROF(T_ATTN_BWD, attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, rnd, st));
   // dWqkv += X^T dQKV  (X = dropout1(gather))
   GemmOperandA axT{table_or_x, d->Din, true, tok, d->V, tok ? drop1 : none, d->Din};
-  EBK_PROF(T_QKV_WGRAD, gemm_dispatch(d->math, axT, ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din, 3 * D, R, 1.0f, st, tc && !x3));
+  EBK_PROF(T_QKV_WGRAD, gemm_dispatch(d->math, axT, ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din, 3 * D, R, 1.0f, st,
+                                      rnd ? GEMM_B_ROUNDED : GEMM_B_RAW));
   // dX = dQKV Wqkv^T
   if (tok != nullptr ? (d_table != nullptr) : (d_x != nullptr)) {
     float* dx = tok ? ws.dx : d_x;
-    GemmOperandA adq{ws.dqkv, 3 * D, false, nullptr, 0, none, 0};
-    EBK_PROF(T_QKV_DGRAD, gemm_dispatch(d->math, adq, Wqkv_b, 3 * D, true, dx, d->Din, R, d->Din, 3 * D, 0.0f, st, tc,
-                                      x3 ? ws.wqkv_lo : nullptr));
+    EBK_PROF(T_QKV_DGRAD, gemm_dispatch(d->math, adq, pk_qkv ? ws.wqkv_d : Wqkv, 3 * D, true, dx, d->Din, R, d->Din,
+                                        3 * D, 0.0f, st, pk_qkv ? GEMM_B_PACKED : GEMM_B_RAW));
     if (tok) EBK_PROF(T_SCATTER, scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
   }
   return EBK_OK;

@@ -65,23 +65,26 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- counter-based dropout (mirrors oracle/nrms_oracle.py::dropout_keep_mask) ----------
-// group g = idx >> 2 draws r = mix64(seed + (g+1)*GOLDEN); lane j = idx & 3 uses bits
-// [16j,16j+16); element kept iff bits >= thr, thr = floor(p*65536 + 0.5).
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-__host__ __device__ __forceinline__ uint64_t dropout_group_bits(uint64_t seed, uint64_t group) {
-  return mix64(seed + (group + 1ull) * 0x9E3779B97F4A7C15ull);
+// group g = idx >> 2 draws two 32-bit words (x, y) from (seed, g); lane j = idx & 3 uses
+// x[0:16], x[16:32], y[0:16], y[16:32]; element kept iff bits >= thr, thr = floor(p*65536 + 0.5).
+// Two 32-bit avalanche hashes (lowbias32-style) give the 4 x 16 random bits of a group.
+__host__ __device__ __forceinline__ void dropout_group_bits(uint64_t seed, uint64_t group, uint32_t& x, uint32_t& y) {
+  const uint32_t s0 = (uint32_t)seed, s1 = (uint32_t)(seed >> 32);
+  x = (uint32_t)group * 0x9E3779B1u + (uint32_t)(group >> 32) * 0x85EBCA77u + s0;
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  y = (x ^ s1) * 0x9E3779B1u;
+  y ^= y >> 15; y *= 0x2C1B3C6Du; y ^= y >> 12; y *= 0x297A2D39u; y ^= y >> 15;
 }
 __host__ __device__ __forceinline__ uint32_t dropout_threshold(float p) {
   return (uint32_t)floorf(p * 65536.0f + 0.5f);
 }
 // keep flag for a single element
 __host__ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t thr) {
-  uint64_t r = dropout_group_bits(seed, idx >> 2);
-  return (uint32_t)((r >> ((idx & 3ull) * 16ull)) & 0xFFFFull) >= thr;
+  uint32_t x, y;
+  dropout_group_bits(seed, idx >> 2, x, y);
+  const uint32_t lane = (uint32_t)(idx & 3ull);
+  const uint32_t w = (lane & 2u) ? y : x;
+  return ((lane & 1u) ? (w >> 16) : (w & 0xFFFFu)) >= thr;
 }
 
 struct Dropout {
@@ -93,16 +96,19 @@ struct Dropout {
   __device__ __forceinline__ float factor(uint64_t idx) const {
     return dropout_keep(seed, idx, thr) ? scale : 0.0f;
   }
-  // factors of the 4 elements of an aligned group starting at idx (idx % 4 == 0)
-  __device__ __forceinline__ float4 factor4(uint64_t idx) const {
-    uint64_t r = dropout_group_bits(seed, idx >> 2);
+  // factors of the 4 elements of group g (elements 4g .. 4g+3)
+  __device__ __forceinline__ float4 factor4_group(uint64_t g) const {
+    uint32_t x, y;
+    dropout_group_bits(seed, g, x, y);
     float4 f;
-    f.x = ((uint32_t)(r & 0xFFFF) >= thr) ? scale : 0.0f;
-    f.y = ((uint32_t)((r >> 16) & 0xFFFF) >= thr) ? scale : 0.0f;
-    f.z = ((uint32_t)((r >> 32) & 0xFFFF) >= thr) ? scale : 0.0f;
-    f.w = ((uint32_t)((r >> 48) & 0xFFFF) >= thr) ? scale : 0.0f;
+    f.x = ((x & 0xFFFFu) >= thr) ? scale : 0.0f;
+    f.y = ((x >> 16) >= thr) ? scale : 0.0f;
+    f.z = ((y & 0xFFFFu) >= thr) ? scale : 0.0f;
+    f.w = ((y >> 16) >= thr) ? scale : 0.0f;
     return f;
   }
+  // factors of the 4 elements of an aligned group starting at idx (idx % 4 == 0)
+  __device__ __forceinline__ float4 factor4(uint64_t idx) const { return factor4_group(idx >> 2); }
 };
 static inline Dropout make_dropout(bool training, float p, uint64_t seed) {
   Dropout d;
@@ -155,13 +161,22 @@ struct GemmOperandA {
 
 int gemm_f32(const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc,
              int M, int N, int K, float beta, cudaStream_t st);
-// b_rounded: B already holds tf32-rounded values (round_tf32_copy / producers that round on store)
-// x3: error-compensated 3xTF32 (needs B_lo when b_rounded: the low parts from split_tf32_copy)
+// How the B operand of the tcgen05 GEMM is supplied (see gemm_tf32_sm100.cu)
+enum GemmBMode {
+  GEMM_B_PACKED = 0,   // pre-rounded + pre-arranged by gemm_tf32_pack_b (weights): one bulk copy per stage
+  GEMM_B_ROUNDED = 1,  // row-major, values already tf32-rounded (activations): cp.async
+  GEMM_B_RAW = 2       // row-major fp32, rounded in flight through registers
+};
+// x3: error-compensated 3xTF32 (needs B_lo unless b_mode == GEMM_B_RAW)
 int gemm_tf32(const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc,
-              int M, int N, int K, float beta, cudaStream_t st, bool b_rounded = false, bool x3 = false,
+              int M, int N, int K, float beta, cudaStream_t st, int b_mode = GEMM_B_RAW, bool x3 = false,
               const float* B_lo = nullptr);
+bool gemm_tf32_eligible(const GemmOperandA& A, const float* B, int ldb, int M, int N, int K);
+size_t gemm_tf32_packed_floats(int N, int K, bool transB);
+int gemm_tf32_pack_b(float* dst_hi, float* dst_lo, const float* B, int ldb, bool transB, int N, int K,
+                     cudaStream_t st);
 int gemm_dispatch(int math, const GemmOperandA& A, const float* B, int ldb, bool transB, float* C,
-                  int ldc, int M, int N, int K, float beta, cudaStream_t st, bool b_rounded = false,
+                  int ldc, int M, int N, int K, float beta, cudaStream_t st, int b_mode = GEMM_B_RAW,
                   const float* B_lo = nullptr);
 // hi[i] = tf32(src[i]) (round to nearest), lo[i] = src[i] - hi[i]
 int split_tf32_copy(float* hi, float* lo, const float* src, size_t n, cudaStream_t st);

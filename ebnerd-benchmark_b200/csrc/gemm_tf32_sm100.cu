@@ -1,24 +1,33 @@
 // tcgen05 (5th-gen tensor core) TF32 GEMM for sm_100a with a gathered / dropout-masked /
-// transposed A operand:   C[M,N] (+)= opA(A)[M,K] . opB(B)[K,N],  fp32 in, fp32 accumulate.
+// transposed A operand:   C[M,N] (+)= alpha * opA(A)[M,K] . opB(B)[K,N],  fp32 in, fp32 accumulate.
 //
-// Why kind::tf32: the reference computes in fp32 and the parity gate is 1e-3 relative on
-// click scores.  tf32 reads the fp32 words exactly as they sit in the embedding table /
-// activations (no conversion pass, no extra HBM traffic) and keeps 10 mantissa bits.
+// Why kind::tf32: the reference computes in fp32.  tf32 reads the fp32 words as they sit in the
+// embedding table / activations (no converted copy in HBM) and keeps 10 mantissa bits.  The tensor
+// core TRUNCATES fp32 operands to tf32, which biases long dot products, so every operand is rounded to
+// nearest on its way into shared memory (+0x1000 on the bit pattern).  X3 = error-compensated 3xTF32
+// (hi/lo split of both operands, three MMAs per k-chunk) gives ~fp32 accuracy for the inference
+// forward, whose click scores must match the fp32 reference to 1e-3.
 //
-// Structure (one CTA per 128 x BN output tile, 2 CTAs resident per SM so that one CTA's
-// epilogue overlaps the other's main loop):
-//   warps 0-3  producers: 16-byte cp.async (LDGSTS) global -> shared with the UMMA
-//              SWIZZLE_128B pattern applied by hand (the A rows are *gathered* by token id,
-//              which tiled TMA cannot express); optional in-place dropout on A; then
-//              fence.proxy.async + mbarrier arrive.  After the main loop the same warps run
-//              the epilogue: tcgen05.ld (TMEM -> registers) -> global store / red.add.
-//   warp 4     allocates TMEM and issues tcgen05.mma (one elected lane), releasing stages
-//              with tcgen05.commit -> mbarrier.
-// Shared-memory operand layouts (both are "rows of 128 bytes, 16-byte chunk c stored at
-// c ^ (row & 7)", i.e. Swizzle<3,4,3> on 1024-byte aligned atoms):
-//   K-major  operand: row = m (or n), 128 B = 32 consecutive k       (SBO = 1024)
-//   MN-major operand: row = k, 128 B = 32 consecutive m (or n); SWIZZLE_128B_BASE32B atoms
-//                     [4 k][32 mn] laid out [k-group][mn-group]      (LBO = 512, SBO = groups*512)
+// Kernel structure: PERSISTENT, warp-specialised, one CTA per SM (416 threads):
+//   warps 0-7   producers.  A: ld.global.nc 16 B (rows gathered by token id -- tiled TMA cannot
+//               express the gather) into registers, PF k-steps ahead; dropout mask (zeroing only, the
+//               1/(1-p) scale is applied as alpha in the epilogue); tf32 rounding; st.shared with the
+//               UMMA swizzle applied by hand.  B: cp.async 16 B of pre-rounded data (or the register
+//               path for generic callers).  Then fence.proxy.async + mbarrier arrive.
+//   warp 8      allocates TMEM (2 x 256 columns: double-buffered accumulator) and issues tcgen05.mma
+//               (one elected lane); tcgen05.commit releases smem stages / publishes the accumulator.
+//   warps 9-12  epilogue: tcgen05.ld (TMEM -> registers) -> alpha -> global store / red.add, overlapped
+//               with the main loop of the next tile.
+// Work items = (m-tile, n-tile, k-split) enumerated n-fastest so the gathered A rows stay L2-hot.
+//
+// Shared-memory operand layouts (both "rows of 128 bytes"):
+//   K-major  (SWIZZLE_128B):         row = mn index, 128 B = 32 consecutive k; 16-byte chunk c of row r
+//                                    sits at r*128 + ((c ^ (r&7)) << 4)                 (SBO = 1024)
+//   MN-major (SWIZZLE_128B_BASE32B): row = k index, 128 B = 32 consecutive mn.  32-bit MN-major operands
+//                                    only exist in this layout (cute Layout_MN_SW128_32B_Atom): atoms of
+//                                    [4 k-rows][32 mn], 32-byte units XOR-swizzled by the k-row
+//                                    (Swizzle<2,5,2> on the byte address), atoms laid out
+//                                    [k-group][mn-group]                       (LBO = 512, SBO = groups*512)
 #include "ebk_common.cuh"
 
 namespace ebk {
@@ -27,11 +36,17 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 32;             // fp32 elements per stage along K = one 128-byte swizzle row
 constexpr int UMMA_K = 8;          // tf32
-constexpr int MAX_STAGES = 6;
-constexpr int PRODUCER_THREADS = 128;
-constexpr int THREADS = PRODUCER_THREADS + 32;
-constexpr int TMEM_COLS = 256;
-constexpr uint32_t SPIN_LIMIT = 1u << 26;  // bounded mbarrier spins: a protocol bug traps instead of hanging the GPU
+constexpr int MAX_STAGES = 8;
+constexpr int PROD_WARPS = 8;
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int MMA_WARP = PROD_WARPS;
+constexpr int EPI_THREADS = 128;
+constexpr int THREADS = PROD_THREADS + 32 + EPI_THREADS;  // 416
+constexpr int TMEM_COLS = 512;     // two 256-column accumulator buffers
+constexpr int PF = 3;              // A register prefetch depth (k-steps)
+constexpr int A_CH = BM * BK / 4 / PROD_THREADS;  // 16-byte A chunks per producer thread per k-step = 4
+constexpr int B_CH = 256 * BK / 4 / PROD_THREADS; // max B chunks per thread per k-step = 8
+constexpr uint32_t SPIN_LIMIT = 1u << 27;  // bounded mbarrier spins: a protocol bug traps instead of hanging the GPU
 
 struct Params {
   const float* A; int lda; const int32_t* a_gather; int a_gather_limit; Dropout a_drop; int a_drop_ld;
@@ -39,8 +54,9 @@ struct Params {
   const float* B_lo;  // X3 + pre-split B: the low parts (same layout as B)
   float* C; int ldc;
   int M, N, K;
-  int BN;             // tile width, multiple of 16, <= 256
-  int stages;
+  int BN;             // tile width, multiple of 16 (32 for MN-major B), <= 256
+  int stages, lag;
+  int tiles_m, tiles_n, splitk;
   int ksteps_total;   // ceil(K / BK)
   int ksteps_per_split;
   int out_mode;       // 0 store, 1 load-add-store (beta=1), 2 atomic add (split-K)
@@ -75,6 +91,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > SPIN_LIMIT) __trap();
   }
 }
+// waiting roles that are idle most of the time (MMA issuer, epilogue) back off so that their spin
+// does not steal issue slots from the producer warps
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -82,6 +107,17 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    default: cp_async_wait<6>(); break;
+  }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -103,7 +139,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14),
-// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout type [61,64).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                               uint32_t layout_type) {
   uint64_t d = 0;
@@ -129,14 +165,6 @@ __device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn, int n) {
 }
 
 // ---- producer helpers ------------------------------------------------------------------------
-// Both operand layouts are "rows of 128 bytes" in shared memory:
-//   K-major  (SWIZZLE_128B):         row = mn index, 128 B = 32 consecutive k; 16-byte chunk c of row r
-//                                    sits at r*128 + ((c ^ (r&7)) << 4)                 (SBO = 1024)
-//   MN-major (SWIZZLE_128B_BASE32B): row = k index, 128 B = 32 consecutive mn.  32-bit MN-major
-//                                    operands only exist in this layout (cute Layout_MN_SW128_32B_Atom):
-//                                    atoms of [4 k-rows][32 mn], 32-byte units XOR-swizzled by the k-row
-//                                    (Swizzle<2,5,2> on the byte address), atoms laid out
-//                                    [k-group][mn-group]                       (LBO = 512, SBO = groups*512)
 __device__ __forceinline__ uint32_t k_off(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
 __device__ __forceinline__ uint32_t mn_off(int kr, int c, int groups) {
   const uint32_t unit32 = (uint32_t)(((c & 7) >> 1) ^ (kr & 3));
@@ -149,12 +177,12 @@ __device__ __forceinline__ uint32_t mn_off(int kr, int c, int groups) {
 template <bool MN>
 __device__ __forceinline__ bool chunk_coord(int i, int ptid, int ext, int& row, int& c) {
   if (!MN) {
-    row = (ptid >> 3) + i * (PRODUCER_THREADS / 8);
+    row = (ptid >> 3) + i * (PROD_THREADS / 8);
     c = ptid & 7;
     return row < ext;
   } else {
     const int cpr = ext >> 2;
-    const int idx = ptid + i * PRODUCER_THREADS;
+    const int idx = ptid + i * PROD_THREADS;
     row = idx / cpr;
     c = idx - row * cpr;
     return row < BK;
@@ -199,6 +227,10 @@ __device__ __forceinline__ float4 ldg_chunk(const float* src, int nvalid) {
 // round-to-nearest to tf32: the tensor core TRUNCATES the low 13 mantissa bits of an fp32 word,
 // so adding half a tf32 ulp to the bit pattern beforehand makes that truncation a rounding.
 __device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+__device__ __forceinline__ float4 rn4(float4 v) {
+  v.x = rn_tf32(v.x); v.y = rn_tf32(v.y); v.z = rn_tf32(v.z); v.w = rn_tf32(v.w);
+  return v;
+}
 // 3xTF32 split: x = hi + lo with hi exactly a tf32 value (round to nearest) and lo = x - hi exact
 // in fp32 (|lo| <= 2^-11 |x|); the products hi*hi + lo*hi + hi*lo recover ~fp32 accuracy.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
@@ -214,8 +246,8 @@ template <bool MN>
 __device__ __forceinline__ void stage_async(uint32_t sdst, const float* base, int ld, int mn0, int mn_end, int ext,
                                             int k0, int K, int ptid) {
   const int groups = ext >> 5;
-#pragma unroll 4
-  for (int i = 0; i < 16; ++i) {
+#pragma unroll
+  for (int i = 0; i < B_CH; ++i) {
     int row, c, nvalid;
     if (!chunk_coord<MN>(i, ptid, ext, row, c)) break;
     const float* src = chunk_src<MN>(row, c, base, ld, nullptr, 0, mn0, mn_end, k0, K, nvalid);
@@ -236,16 +268,47 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// B_REG: B is staged through registers with in-flight tf32 rounding (generic callers); otherwise B
-// must already be tf32-rounded in memory and is staged with cp.async.
-// X3: error-compensated 3xTF32 (hi/lo split of both operands, three MMAs per k-chunk) for the
-// inference forward, whose click scores must match the fp32 reference to 1e-3.
-template <bool A_MN, bool B_MN, bool B_REG, bool X3>
-__global__ void __launch_bounds__(THREADS, X3 ? 1 : 2) gemm_tf32_kernel(const Params p) {
+// Walks this CTA's work items (m-tile, n-tile, k-split; n fastest) k-step by k-step.
+struct Cursor {
+  int item, ks, ks_end;   // current item, current k-step, end k-step of the item
+  int m0, n0;
+  __device__ __forceinline__ void load(const Params& p) {
+    const int per_m = p.tiles_n * p.splitk;
+    const int tm = item / per_m, rem = item - tm * per_m;
+    const int tn = rem / p.splitk, sp = rem - tn * p.splitk;
+    m0 = tm * BM;
+    n0 = tn * p.BN;
+    ks = sp * p.ksteps_per_split;
+    ks_end = min(p.ksteps_total, ks + p.ksteps_per_split);
+  }
+  __device__ __forceinline__ void init(const Params& p, int first, int n_items) {
+    item = first;
+    ks = ks_end = m0 = n0 = 0;
+    if (item < n_items) load(p);
+  }
+  __device__ __forceinline__ bool valid(int n_items) const { return item < n_items; }
+  // returns true when the step just consumed was the last of its item
+  __device__ __forceinline__ bool advance(const Params& p, int n_items, int stride) {
+    if (++ks < ks_end) return false;
+    item += stride;
+    if (item < n_items) load(p);
+    return true;
+  }
+};
+
+// BMODE selects how the B operand reaches shared memory:
+//   0  packed: B was pre-rounded AND pre-arranged by gemm_tf32_pack_b() into the exact UMMA tile
+//      layout, [n-tile][k-step] blocks of b_tile bytes -> ONE cp.async.bulk (TMA engine, no tensor map)
+//      per stage, completion counted on the stage's full barrier (complete_tx);
+//   1  row-major, already tf32-rounded: 16-byte cp.async per chunk (activations: dQKV, dpre);
+//   2  row-major fp32 through registers with in-flight rounding (generic callers).
+template <bool A_MN, bool B_MN, int BMODE, bool X3>
+__global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -260,23 +323,20 @@ __global__ void __launch_bounds__(THREADS, X3 ? 1 : 2) gemm_tf32_kernel(const Pa
   const uint32_t stage_bytes = a_bytes + NSPLIT * b_tile;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_base = smem_u32(smem);
-
-  const int m0 = blockIdx.y * BM;
-  const int n0 = blockIdx.x * BN;
-  const int ks_begin = blockIdx.z * p.ksteps_per_split;
-  int ks_end = ks_begin + p.ksteps_per_split;
-  if (ks_end > p.ksteps_total) ks_end = p.ksteps_total;
-  const int nk = ks_end - ks_begin;  // >= 1 by construction
+  const int n_items = p.tiles_m * p.tiles_n * p.splitk;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), PRODUCER_THREADS);
+      mbar_init(smem_u32(&full_bar[s]), PROD_THREADS + (BMODE == 0 ? 1 : 0));  // + the expect_tx arrival
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(&accum_bar), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tfull_bar[b]), 1);
+      mbar_init(smem_u32(&tempty_bar[b]), EPI_THREADS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
                  "n"(TMEM_COLS)
                  : "memory");
@@ -287,153 +347,251 @@ __global__ void __launch_bounds__(THREADS, X3 ? 1 : 2) gemm_tf32_kernel(const Pa
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (warp < 4) {
+  if (warp < PROD_WARPS) {
     // ===================== producers =====================
+    // Everything that does not depend on the k-step is hoisted: chunk coordinates and swizzled smem
+    // offsets are per-thread constants, row pointers / validity / dropout group ids are per work item.
     const int ptid = tid;
-    const int LAG = B_REG ? 0 : S - 1;  // cp.async stages kept in flight per thread
+    const int LAG = BMODE == 1 ? p.lag : 0;  // cp.async groups kept in flight before a stage is published
     const int a_groups = BM >> 5, b_groups = b_ext >> 5;
-    for (int i = 0; i < nk + LAG; ++i) {
-      if (i < nk) {
-        const int s = i % S, round = i / S;
-        const int k0 = (ks_begin + i) * BK;
-        // ---- A: global -> registers (gather by token id) BEFORE waiting for the slot ----
-        float4 av[8];
-        int arow[8], ac[8];
+    int arow[A_CH], ac[A_CH];
+    uint32_t aoff[A_CH];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          int nvalid;
-          chunk_coord<A_MN>(q, ptid, BM, arow[q], ac[q]);
-          const float* src = chunk_src<A_MN>(arow[q], ac[q], p.A, p.lda, p.a_gather, p.a_gather_limit, m0, p.M, k0,
-                                             p.K, nvalid);
-          av[q] = ldg_chunk(src, nvalid);
+    for (int q = 0; q < A_CH; ++q) {
+      chunk_coord<A_MN>(q, ptid, BM, arow[q], ac[q]);
+      aoff[q] = A_MN ? mn_off(arow[q], ac[q], a_groups) : k_off(arow[q], ac[q]);
+    }
+    int brow[B_CH], bc[B_CH];
+    uint32_t boff[B_CH];
+    bool bok[B_CH];
+    if (BMODE != 0) {
+#pragma unroll
+      for (int q = 0; q < B_CH; ++q) {
+        bok[q] = chunk_coord<B_MN>(q, ptid, b_ext, brow[q], bc[q]);
+        boff[q] = B_MN ? mn_off(brow[q], bc[q], b_groups) : k_off(brow[q], bc[q]);
+      }
+    }
+
+    Cursor ld, pr;
+    ld.init(p, blockIdx.x, n_items);
+    pr.init(p, blockIdx.x, n_items);
+    // ---- per-item state of the LOAD cursor ----
+    int ld_item = -1;
+    const float* aptr[A_CH];   // K-major: &A[row(m), 4c] or nullptr (zero row); MN-major: &A[0, m0+4c]
+    int avalid[A_CH];          // MN-major: valid floats of the chunk (0..4)
+    auto a_item_setup = [&]() {
+      ld_item = ld.item;
+#pragma unroll
+      for (int q = 0; q < A_CH; ++q) {
+        if (!A_MN) {
+          const int m = ld.m0 + arow[q];
+          long r = m;
+          bool ok = m < p.M;
+          if (p.a_gather) {
+            const int g = __ldg(p.a_gather + (ok ? m : 0));
+            ok = ok && (g >= 0) && (g < p.a_gather_limit);
+            r = g;
+          }
+          aptr[q] = ok ? p.A + r * (long)p.lda + ac[q] * 4 : nullptr;
+          avalid[q] = 4;
+        } else {
+          const int m = ld.m0 + ac[q] * 4;
+          int nv = p.M - m;
+          avalid[q] = nv < 0 ? 0 : (nv > 4 ? 4 : nv);
+          aptr[q] = p.A + m;
         }
+      }
+    };
+    // issue the A loads of the step under the load cursor into `dst`
+    auto a_load = [&](float4 (&dst)[A_CH]) {
+      if (ld.item != ld_item) a_item_setup();
+      const int k0 = ld.ks * BK;
+      if (!A_MN) {
+        if (k0 + BK <= p.K) {  // fast path: whole 128-byte row segments
+#pragma unroll
+          for (int q = 0; q < A_CH; ++q) {
+            dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (aptr[q] != nullptr) dst[q] = ldg_chunk(aptr[q] + k0, 4);
+          }
+        } else {
+          int nv = p.K - (k0 + ac[0] * 4);
+          nv = nv > 4 ? 4 : nv;
+#pragma unroll
+          for (int q = 0; q < A_CH; ++q) {
+            const bool ok = aptr[q] != nullptr && nv > 0;
+            dst[q] = ldg_chunk(ok ? aptr[q] + k0 : p.A, ok ? nv : 0);
+          }
+        }
+      } else {
+        // MN-major: the storage rows are the k indices (gathered); index loads issued back to back
+        int g[A_CH];
+        bool ok[A_CH];
+#pragma unroll
+        for (int q = 0; q < A_CH; ++q) {
+          const int k = k0 + arow[q];
+          ok[q] = k < p.K && avalid[q] > 0;
+          g[q] = k;
+          if (p.a_gather) g[q] = __ldg(p.a_gather + (ok[q] ? k : 0));
+        }
+#pragma unroll
+        for (int q = 0; q < A_CH; ++q) {
+          if (p.a_gather) ok[q] = ok[q] && g[q] >= 0 && g[q] < p.a_gather_limit;
+          dst[q] = ldg_chunk(ok[q] ? aptr[q] + (long)g[q] * p.lda : p.A, ok[q] ? avalid[q] : 0);
+        }
+      }
+    };
+    // ---- per-item state of the PROCESS cursor: dropout group id of each chunk at k-step 0 ----
+    int pr_item = -1;
+    uint64_t dgrp[A_CH];
+    uint64_t dstep = 0;  // group-id increment per k-step
+    auto d_item_setup = [&]() {
+      pr_item = pr.item;
+#pragma unroll
+      for (int q = 0; q < A_CH; ++q) {
+        const uint64_t srow = A_MN ? (uint64_t)arow[q] : (uint64_t)(pr.m0 + arow[q]);
+        const uint64_t scol = A_MN ? (uint64_t)(pr.m0 + ac[q] * 4) : (uint64_t)(ac[q] * 4);
+        dgrp[q] = (srow * (uint64_t)p.a_drop_ld + scol) >> 2;
+      }
+      dstep = A_MN ? ((uint64_t)BK * (uint64_t)p.a_drop_ld) >> 2 : (uint64_t)(BK / 4);
+    };
+
+    float4 av[PF][A_CH];
+    // prologue: A loads of the first PF-1 steps
+#pragma unroll
+    for (int u = 0; u < PF - 1; ++u) {
+#pragma unroll
+      for (int q = 0; q < A_CH; ++q) av[u][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ld.valid(n_items)) {
+        a_load(av[u]);
+        ld.advance(p, n_items, gridDim.x);
+      }
+    }
+    int g = 0;          // flat k-step counter of this CTA
+    int published = 0;  // steps whose full barrier has been arrived on
+    while (pr.valid(n_items)) {
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        if (!pr.valid(n_items)) break;
+        // ---- A loads for step g+PF-1 into the slot freed last iteration ----
+        constexpr int PFM1 = PF - 1;
+        if (ld.valid(n_items)) {
+          a_load(av[(u + PFM1) % PF]);
+          ld.advance(p, n_items, gridDim.x);
+        }
+        const int s = g % S, round = g / S;
+        const int k0 = pr.ks * BK;
         mbar_wait(smem_u32(&empty_bar[s]), (uint32_t)((round & 1) ^ 1));
         uint8_t* pa = smem + (size_t)s * stage_bytes;
+        uint8_t* pb = pa + a_bytes;
         const uint32_t sb = smem_base + (uint32_t)s * stage_bytes + a_bytes;
-        if (!B_REG) {
-          stage_async<B_MN>(sb, p.B, p.ldb, n0, p.N, b_ext, k0, p.K, ptid);
-          if (X3) stage_async<B_MN>(sb + b_tile, p.B_lo, p.ldb, n0, p.N, b_ext, k0, p.K, ptid);
-        }
-        // ---- A: dropout mask (zeroing only; 1/(1-p) is applied as alpha in the epilogue),
-        //         round to tf32, store with the UMMA swizzle ----
+        if (BMODE == 0) {
+          // ---- B: one bulk copy of the pre-packed tile (hi [+ lo]) ----
+          if (ptid == 0) {
+            const uint32_t bar = smem_u32(&full_bar[s]);
+            const uint32_t bytes = NSPLIT * b_tile;
+            const size_t blk = ((size_t)(pr.n0 / BN) * p.ksteps_total + pr.ks) * (size_t)(b_tile / 4);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb),
+                         "l"(p.B + blk), "r"(b_tile), "r"(bar)
+                         : "memory");
+            if (X3)
+              asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                               sb + b_tile),
+                           "l"(p.B_lo + blk), "r"(b_tile), "r"(bar)
+                           : "memory");
+          }
+        } else if (BMODE == 1) {
+          // ---- B: cp.async of pre-rounded row-major data ----
+          if (!B_MN) {
+            int nvk = p.K - (k0 + bc[0] * 4);
+            nvk = nvk < 0 ? 0 : (nvk > 4 ? 4 : nvk);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 v = av[q];
+            for (int q = 0; q < B_CH; ++q) {
+              if (!bok[q]) break;
+              const int n = pr.n0 + brow[q];
+              const bool ok = n < p.N;
+              const long off = ok ? (long)n * p.ldb + k0 + bc[q] * 4 : 0;
+              cp_async16(sb + boff[q], p.B + off, ok ? (uint32_t)nvk * 4u : 0u);
+              if (X3) cp_async16(sb + b_tile + boff[q], p.B_lo + off, ok ? (uint32_t)nvk * 4u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < B_CH; ++q) {
+              if (!bok[q]) break;
+              const int k = k0 + brow[q];
+              const int n = pr.n0 + bc[q] * 4;
+              int nv = p.N - n;
+              nv = (k < p.K && nv > 0) ? (nv > 4 ? 4 : nv) : 0;
+              const long off = nv ? (long)k * p.ldb + n : 0;
+              cp_async16(sb + boff[q], p.B + off, (uint32_t)nv * 4u);
+              if (X3) cp_async16(sb + b_tile + boff[q], p.B_lo + off, (uint32_t)nv * 4u);
+            }
+          }
+          cp_async_commit();
+        }
+        // ---- A: mask, round to tf32, store with the UMMA swizzle ----
+        if (p.a_drop.on() && pr.item != pr_item) d_item_setup();
+#pragma unroll
+        for (int q = 0; q < A_CH; ++q) {
+          float4 v = av[u][q];
           if (p.a_drop.on()) {
-            const uint64_t srow = A_MN ? (uint64_t)(k0 + arow[q]) : (uint64_t)(m0 + arow[q]);
-            const uint64_t scol = A_MN ? (uint64_t)(m0 + ac[q] * 4) : (uint64_t)(k0 + ac[q] * 4);
-            const float4 f = p.a_drop.factor4(srow * (uint64_t)p.a_drop_ld + scol);  // scale forced to 1
+            const uint64_t grp = dgrp[q] + (uint64_t)pr.ks * dstep;
+            const float4 f = p.a_drop.factor4_group(grp);  // scale forced to 1 by the host
             v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
           }
-          const uint32_t off = A_MN ? mn_off(arow[q], ac[q], a_groups) : k_off(arow[q], ac[q]);
           if (X3) {
             float4 hi, lo;
             split4(v, hi, lo);
-            *reinterpret_cast<float4*>(pa + off) = hi;
-            *reinterpret_cast<float4*>(pa + a_tile + off) = lo;
+            *reinterpret_cast<float4*>(pa + aoff[q]) = hi;
+            *reinterpret_cast<float4*>(pa + a_tile + aoff[q]) = lo;
           } else {
-            v.x = rn_tf32(v.x); v.y = rn_tf32(v.y); v.z = rn_tf32(v.z); v.w = rn_tf32(v.w);
-            *reinterpret_cast<float4*>(pa + off) = v;
+            *reinterpret_cast<float4*>(pa + aoff[q]) = rn4(v);
           }
         }
-        if (B_REG) {
-          uint8_t* pb = pa + a_bytes;
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            float4 bv[8];
-            int brow[8], bc[8];
-            bool bok[8];
+        if (BMODE == 2) {
+          // ---- B through registers with in-flight rounding (generic callers) ----
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              int nvalid;
-              bok[q] = chunk_coord<B_MN>(h * 8 + q, ptid, b_ext, brow[q], bc[q]);
-              bv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (bok[q]) {
-                const float* src = chunk_src<B_MN>(brow[q], bc[q], p.B, p.ldb, nullptr, 0, n0, p.N, k0, p.K, nvalid);
-                bv[q] = ldg_chunk(src, nvalid);
-              }
+          for (int h = 0; h < B_CH; h += 4) {
+            float4 bv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              int nvalid = 0;
+              const float* src = p.B;
+              if (bok[h + q])
+                src = chunk_src<B_MN>(brow[h + q], bc[h + q], p.B, p.ldb, nullptr, 0, pr.n0, p.N, k0, p.K, nvalid);
+              bv[q] = ldg_chunk(src, nvalid);
             }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (!bok[q]) continue;
-              float4 v = bv[q];
-              const uint32_t off = B_MN ? mn_off(brow[q], bc[q], b_groups) : k_off(brow[q], bc[q]);
+            for (int q = 0; q < 4; ++q) {
+              if (!bok[h + q]) continue;
               if (X3) {
                 float4 hi, lo;
-                split4(v, hi, lo);
-                *reinterpret_cast<float4*>(pb + off) = hi;
-                *reinterpret_cast<float4*>(pb + b_tile + off) = lo;
+                split4(bv[q], hi, lo);
+                *reinterpret_cast<float4*>(pb + boff[h + q]) = hi;
+                *reinterpret_cast<float4*>(pb + b_tile + boff[h + q]) = lo;
               } else {
-                v.x = rn_tf32(v.x); v.y = rn_tf32(v.y); v.z = rn_tf32(v.z); v.w = rn_tf32(v.w);
-                *reinterpret_cast<float4*>(pb + off) = v;
+                *reinterpret_cast<float4*>(pb + boff[h + q]) = rn4(bv[q]);
               }
             }
           }
         }
-      }
-      if (!B_REG) cp_async_commit();
-      const int j = i - LAG;  // step whose B copies are now guaranteed complete
-      if (j >= 0) {
-        if (!B_REG) {
-          switch (LAG) {
-            case 0: cp_async_wait<0>(); break;
-            case 1: cp_async_wait<1>(); break;
-            case 2: cp_async_wait<2>(); break;
-            case 3: cp_async_wait<3>(); break;
-            case 4: cp_async_wait<4>(); break;
-            default: cp_async_wait<5>(); break;
-          }
+        // ---- publish step g-LAG (its cp.async group is complete once <= LAG younger groups are pending) ----
+        if (g - LAG >= 0) {
+          if (BMODE == 1) cp_async_wait_dyn(LAG);
+          fence_proxy_async();  // this thread's st.shared / cp.async writes -> visible to the tensor core
+          mbar_arrive(smem_u32(&full_bar[(g - LAG) % S]));
+          published = g - LAG + 1;
         }
-        fence_proxy_async();  // this thread's st.shared / cp.async writes -> visible to the tensor core
-        mbar_arrive(smem_u32(&full_bar[j % S]));
+        pr.advance(p, n_items, gridDim.x);
+        ++g;
       }
     }
-    // ===================== epilogue =====================
-    mbar_wait(smem_u32(&accum_bar), 0);
-    tc_fence_after();
-    const int row = m0 + warp * 32 + lane;
-    const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16);
-    float* crow = p.C + (long)row * p.ldc + n0;
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((n0 & 3) == 0);
-    const float alpha = p.alpha;
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float v[16];
-      tmem_ld16(tbase + (uint32_t)c0, v);  // warp-collective: executed by all lanes
-      if (row < p.M) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int col = c0 + q * 4;
-          if (n0 + col >= p.N) break;
-          float4 o = make_float4(v[q * 4] * alpha, v[q * 4 + 1] * alpha, v[q * 4 + 2] * alpha, v[q * 4 + 3] * alpha);
-          if (vec_ok && n0 + col + 3 < p.N) {
-            float4* dst = reinterpret_cast<float4*>(crow + col);
-            if (p.out_mode == 0) {
-              *dst = o;
-            } else if (p.out_mode == 1) {
-              float4 c = *dst;
-              c.x += o.x; c.y += o.y; c.z += o.z; c.w += o.w;
-              *dst = c;
-            } else {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z),
-                           "f"(o.w)
-                           : "memory");
-            }
-          } else {
-            const float oe[4] = {o.x, o.y, o.z, o.w};
-            for (int e = 0; e < 4; ++e) {
-              if (n0 + col + e >= p.N) break;
-              float* dst = crow + col + e;
-              if (p.out_mode == 0) *dst = oe[e];
-              else if (p.out_mode == 1) *dst += oe[e];
-              else atomicAdd(dst, oe[e]);
-            }
-          }
-        }
-      }
-    }
-    tc_fence_before();
-  } else {
-    // ===================== MMA issuer (warp 4) =====================
+    // drain: publish the last LAG steps
+    if (BMODE == 1) cp_async_wait<0>();
+    fence_proxy_async();
+    for (int j = published; j < g; ++j) mbar_arrive(smem_u32(&full_bar[j % S]));
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(A_MN, B_MN, BN);
       const uint32_t a_sbo = A_MN ? (uint32_t)(BM / 32) * 512u : 1024u;
@@ -441,34 +599,122 @@ __global__ void __launch_bounds__(THREADS, X3 ? 1 : 2) gemm_tf32_kernel(const Pa
       const uint32_t a_lbo = A_MN ? 512u : 16u;
       const uint32_t b_lbo = B_MN ? 512u : 16u;
       const uint32_t a_lt = A_MN ? 1u : 2u, b_lt = B_MN ? 1u : 2u;
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % S, round = i / S;
-        mbar_wait(smem_u32(&full_bar[s]), (uint32_t)(round & 1));
+      Cursor cu;
+      cu.init(p, blockIdx.x, n_items);
+      int g = 0, t = 0;
+      while (cu.valid(n_items)) {
+        const int buf = t & 1, use = t >> 1;
+        mbar_wait_backoff(smem_u32(&tempty_bar[buf]), (uint32_t)((use & 1) ^ 1));  // epilogue drained this buffer
         tc_fence_after();
-        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-        const uint32_t sb = sa + a_bytes;
+        const uint32_t tacc = tmem + (uint32_t)buf * 256u;
+        bool first = true, last = false;
+        while (!last) {
+          const int s = g % S, round = g / S;
+          mbar_wait(smem_u32(&full_bar[s]), (uint32_t)(round & 1));
+          tc_fence_after();
+          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+          const uint32_t sb = sa + a_bytes;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // K-major: +32 bytes inside the 128-byte swizzle row; MN-major: 8 k = two 4-row k-groups
-          const uint32_t a_addr = sa + (A_MN ? (uint32_t)(2 * k) * a_sbo : (uint32_t)k * 32u);
-          const uint32_t b_addr = sb + (B_MN ? (uint32_t)(2 * k) * b_sbo : (uint32_t)k * 32u);
-          const uint64_t da = make_desc(a_addr, a_lbo, a_sbo, a_lt), db = make_desc(b_addr, b_lbo, b_sbo, b_lt);
-          if (X3) {  // small terms first: lo*hi + hi*lo + hi*hi
-            umma_tf32(tmem, make_desc(a_addr + a_tile, a_lbo, a_sbo, a_lt), db, idesc, (uint32_t)((i | k) != 0));
-            umma_tf32(tmem, da, make_desc(b_addr + b_tile, b_lbo, b_sbo, b_lt), idesc, 1u);
-            umma_tf32(tmem, da, db, idesc, 1u);
-          } else {
-            umma_tf32(tmem, da, db, idesc, (uint32_t)((i | k) != 0));
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: +32 bytes inside the 128-byte swizzle row; MN-major: 8 k = two 4-row k-groups
+            const uint32_t a_addr = sa + (A_MN ? (uint32_t)(2 * k) * a_sbo : (uint32_t)k * 32u);
+            const uint32_t b_addr = sb + (B_MN ? (uint32_t)(2 * k) * b_sbo : (uint32_t)k * 32u);
+            const uint64_t da = make_desc(a_addr, a_lbo, a_sbo, a_lt), db = make_desc(b_addr, b_lbo, b_sbo, b_lt);
+            const uint32_t acc = (first && k == 0) ? 0u : 1u;
+            if (X3) {  // small terms first: lo*hi + hi*lo + hi*hi
+              umma_tf32(tacc, make_desc(a_addr + a_tile, a_lbo, a_sbo, a_lt), db, idesc, acc);
+              umma_tf32(tacc, da, make_desc(b_addr + b_tile, b_lbo, b_sbo, b_lt), idesc, 1u);
+              umma_tf32(tacc, da, db, idesc, 1u);
+            } else {
+              umma_tf32(tacc, da, db, idesc, acc);
+            }
           }
+          umma_commit(smem_u32(&empty_bar[s]));  // frees the stage when these MMAs retire
+          first = false;
+          last = cu.advance(p, n_items, gridDim.x);
+          ++g;
         }
-        umma_commit(smem_u32(&empty_bar[s]));  // frees the stage when these MMAs retire
+        umma_commit(smem_u32(&tfull_bar[buf]));  // accumulator of this item complete
+        ++t;
       }
-      umma_commit(smem_u32(&accum_bar));       // accumulator complete
     }
     __syncwarp();
+  } else {
+    // ===================== epilogue (warps 9-12) =====================
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    Cursor cu;
+    cu.init(p, blockIdx.x, n_items);
+    int t = 0;
+    const float alpha = p.alpha;
+    while (cu.valid(n_items)) {
+      const int buf = t & 1, use = t >> 1;
+      const int m0 = cu.m0, n0 = cu.n0;
+      mbar_wait_backoff(smem_u32(&tfull_bar[buf]), (uint32_t)(use & 1));
+      tc_fence_after();
+      const int row = m0 + ew * 32 + lane;
+      const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * 256u;
+      float* crow = p.C + (long)row * p.ldc + n0;
+      const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((n0 & 3) == 0);
+      const bool vec8_ok = vec_ok && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 31) == 0) &&
+                           ((n0 & 7) == 0) && p.out_mode == 0;
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tmem_ld16(tbase + (uint32_t)c0, v);  // warp-collective: executed by all lanes
+        if (row < p.M) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= alpha;
+          if (vec8_ok && n0 + c0 + 15 < p.N) {
+            // two 256-bit stores: each fills a whole 32-byte sector of the row
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + c0), "f"(v[0]), "f"(v[1]),
+                         "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                         : "memory");
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + c0 + 8), "f"(v[8]), "f"(v[9]),
+                         "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+                         : "memory");
+            continue;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int col = c0 + q * 4;
+            if (n0 + col >= p.N) break;
+            float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            if (vec_ok && n0 + col + 3 < p.N) {
+              float4* dst = reinterpret_cast<float4*>(crow + col);
+              if (p.out_mode == 0) {
+                *dst = o;
+              } else if (p.out_mode == 1) {
+                float4 c = *dst;
+                c.x += o.x; c.y += o.y; c.z += o.z; c.w += o.w;
+                *dst = c;
+              } else {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y),
+                             "f"(o.z), "f"(o.w)
+                             : "memory");
+              }
+            } else {
+              const float oe[4] = {o.x, o.y, o.z, o.w};
+              for (int e = 0; e < 4; ++e) {
+                if (n0 + col + e >= p.N) break;
+                float* dst = crow + col + e;
+                if (p.out_mode == 0) *dst = oe[e];
+                else if (p.out_mode == 1) *dst += oe[e];
+                else atomicAdd(dst, oe[e]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tempty_bar[buf]));  // buffer may be overwritten by the MMA warp
+      // skip to this CTA's next item
+      cu.ks = cu.ks_end - 1;
+      cu.advance(p, n_items, gridDim.x);
+      ++t;
+    }
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
   }
@@ -479,75 +725,175 @@ __global__ void zero_matrix_kernel(float* C, int ldc, int M, int N) {
   if (i < (long)M * N) C[(i / N) * (long)ldc + (i % N)] = 0.0f;
 }
 
+// Writes B (row-major fp32) as [n-tile][k-step] blocks in the exact shared-memory tile layout of the
+// kernel (swizzle included), rounded to tf32 (hi) and optionally the 3xTF32 low part (lo).
+__global__ void pack_b_kernel(float* __restrict__ dst_hi, float* __restrict__ dst_lo, const float* __restrict__ B,
+                              int ldb, int b_mn, int N, int K, int BN, int b_ext, int tiles_n, int ksteps,
+                              int chunks_per_tile) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long total = (long)tiles_n * ksteps * chunks_per_tile;
+  if (i >= total) return;
+  const int L = (int)(i % chunks_per_tile);
+  const long blk = i / chunks_per_tile;
+  const int ks = (int)(blk % ksteps), tn = (int)(blk / ksteps);
+  const int n0 = tn * BN, k0 = ks * BK;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (!b_mn) {
+    const int r = L >> 3, c = (L & 7) ^ (r & 7);
+    const int n = n0 + r;
+    if (r < b_ext && n < N) {
+      for (int e = 0; e < 4; ++e) {
+        const int k = k0 + c * 4 + e;
+        if (k < K) v[e] = B[(long)n * ldb + k];
+      }
+    }
+  } else {
+    const int groups = b_ext >> 5;
+    const int atom = L >> 5, within = L & 31;
+    const int kr_lo = within >> 3, pos = within & 7;
+    const int c7 = (((pos >> 1) ^ kr_lo) << 1) | (pos & 1);
+    const int kg = atom / groups, ng = atom - kg * groups;
+    const int kr = kg * 4 + kr_lo, c = ng * 8 + c7;
+    const int k = k0 + kr;
+    if (kr < BK && k < K) {
+      for (int e = 0; e < 4; ++e) {
+        const int n = n0 + c * 4 + e;
+        if (n < N) v[e] = B[(long)k * ldb + n];
+      }
+    }
+  }
+  float4 hi, lo;
+  hi.x = round_tf32_bits(v[0]); hi.y = round_tf32_bits(v[1]); hi.z = round_tf32_bits(v[2]); hi.w = round_tf32_bits(v[3]);
+  reinterpret_cast<float4*>(dst_hi)[i] = hi;
+  if (dst_lo) {
+    lo.x = round_tf32_bits(v[0] - hi.x); lo.y = round_tf32_bits(v[1] - hi.y);
+    lo.z = round_tf32_bits(v[2] - hi.z); lo.w = round_tf32_bits(v[3] - hi.w);
+    reinterpret_cast<float4*>(dst_lo)[i] = lo;
+  }
+}
+
+int g_num_sms = 0;
+
+struct BGeom {
+  bool b_mn;
+  int BN, b_ext, tiles_n, ksteps;
+  size_t b_tile;  // bytes per packed block
+};
+BGeom b_geom(int N, int K, bool transB) {
+  BGeom g;
+  g.b_mn = !transB;
+  const int ntiles_n = ceil_div(N, 256);
+  // MN-major B is staged in 32-column swizzle atoms -> keep the UMMA N a whole number of atoms
+  const int bn_quant = g.b_mn ? 32 : 16;
+  g.BN = ceil_div(ceil_div(N, ntiles_n), bn_quant) * bn_quant;
+  g.b_ext = g.b_mn ? ((g.BN + 31) & ~31) : g.BN;
+  g.tiles_n = ceil_div(N, g.BN);
+  g.ksteps = ceil_div(K, BK);
+  g.b_tile = align_up((size_t)g.b_ext * BK * 4, 1024);
+  return g;
+}
+
 }  // namespace
 
-int gemm_tf32(const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc, int M, int N, int K,
-              float beta, cudaStream_t st, bool b_rounded, bool x3, const float* B_lo) {
-  if (M <= 0 || N <= 0) return EBK_OK;
-  EBK_CHECK_ARG(K >= 0 && A.ptr && B && C, "gemm_tf32: null operand");
-  // 16-byte cp.async needs 4-float aligned rows; tiny or unaligned problems take the fp32 FMA kernel.
+bool gemm_tf32_eligible(const GemmOperandA& A, const float* B, int ldb, int M, int N, int K) {
+  // 16-byte loads need 4-float aligned rows; tiny or unaligned problems take the fp32 FMA kernel.
   const bool aligned = (A.lda % 4 == 0) && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(A.ptr) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (!A.drop.on() || A.drop_ld % 4 == 0);
-  if (!aligned || K < 8 || (long)M * N * K < (1L << 18)) return gemm_f32(A, B, ldb, transB, C, ldc, M, N, K, beta, st);
+  return aligned && K >= 8 && (long)M * N * K >= (1L << 18);
+}
+
+size_t gemm_tf32_packed_floats(int N, int K, bool transB) {
+  const BGeom g = b_geom(N, K, transB);
+  return (size_t)g.tiles_n * g.ksteps * (g.b_tile / 4);
+}
+
+int gemm_tf32_pack_b(float* dst_hi, float* dst_lo, const float* B, int ldb, bool transB, int N, int K,
+                     cudaStream_t st) {
+  const BGeom g = b_geom(N, K, transB);
+  const int chunks_per_tile = (int)(g.b_tile / 16);
+  const long total = (long)g.tiles_n * g.ksteps * chunks_per_tile;
+  pack_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dst_hi, dst_lo, B, ldb, g.b_mn ? 1 : 0, N, K, g.BN,
+                                                                 g.b_ext, g.tiles_n, g.ksteps, chunks_per_tile);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+int gemm_tf32(const GemmOperandA& A, const float* B, int ldb, bool transB, float* C, int ldc, int M, int N, int K,
+              float beta, cudaStream_t st, int b_mode, bool x3, const float* B_lo) {
+  if (M <= 0 || N <= 0) return EBK_OK;
+  EBK_CHECK_ARG(K >= 0 && A.ptr && B && C, "gemm_tf32: null operand");
+  if (b_mode != GEMM_B_PACKED && !gemm_tf32_eligible(A, B, ldb, M, N, K))
+    return gemm_f32(A, B, ldb, transB, C, ldc, M, N, K, beta, st);
+  EBK_CHECK_ARG(!(x3 && b_mode != GEMM_B_RAW && B_lo == nullptr), "gemm_tf32: 3xTF32 with a pre-split B needs B_lo");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    EBK_CUDA(cudaGetDevice(&dev));
+    EBK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
 
   Params p;
   p.A = A.ptr; p.lda = A.lda; p.a_gather = A.gather; p.a_gather_limit = A.gather_limit; p.a_drop = A.drop;
   p.a_drop_ld = A.drop_ld;
   p.alpha = A.drop.on() ? A.drop.scale : 1.0f;  // mask in the operand, scale on the accumulator
   p.a_drop.scale = 1.0f;
-  EBK_CHECK_ARG(!(x3 && b_rounded && B_lo == nullptr), "gemm_tf32: 3xTF32 with a pre-split B needs B_lo");
   p.B = B; p.B_lo = B_lo; p.ldb = ldb; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
-  const bool a_mn = A.trans, b_mn = !transB;
-  const int ntiles_n = ceil_div(N, 256);
-  // MN-major B is staged in 32-column swizzle atoms -> keep the UMMA N a whole number of atoms
-  const int bn_quant = b_mn ? 32 : 16;
-  p.BN = ceil_div(ceil_div(N, ntiles_n), bn_quant) * bn_quant;
-  const int bn_pad = (p.BN + 31) & ~31;
-  const size_t b_bytes = align_up((size_t)(b_mn ? bn_pad : p.BN) * BK * 4, 1024);
-  const size_t stage_bytes = ((size_t)BM * BK * 4 + b_bytes) * (x3 ? 2 : 1);
-  const size_t budget = x3 ? 220 * 1024 : 111 * 1024;  // two CTAs per SM (one for the 3-pass variant)
-  int stages = (int)((budget - 1024) / stage_bytes);
+  const bool a_mn = A.trans;
+  const BGeom bg = b_geom(N, K, transB);
+  const bool b_mn = bg.b_mn;
+  p.BN = bg.BN;
+  const size_t stage_bytes = ((size_t)BM * BK * 4 + bg.b_tile) * (x3 ? 2 : 1);
+  const size_t budget = 200 * 1024;
+  int stages = (int)(budget / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  p.ksteps_total = ceil_div(K, BK);
-  dim3 grid(ceil_div(N, p.BN), ceil_div(M, BM), 1);
-  long tiles = (long)grid.x * grid.y;
+  p.lag = stages >= 4 ? 2 : (stages >= 3 ? 1 : 0);
+  p.ksteps_total = bg.ksteps;
+  p.tiles_m = ceil_div(M, BM);
+  p.tiles_n = bg.tiles_n;
+  const long tiles = (long)p.tiles_m * p.tiles_n;
   int splitk = 1;
-  if (tiles < 148 && p.ksteps_total >= 16) {
-    splitk = (int)((2L * 148 + tiles - 1) / tiles);
+  if (tiles < g_num_sms && p.ksteps_total >= 16) {
+    splitk = (int)(g_num_sms / tiles);  // fill the machine in ONE wave of equal items
     int maxsplit = p.ksteps_total / 8;
     if (splitk > maxsplit) splitk = maxsplit;
     if (splitk < 1) splitk = 1;
   }
   p.ksteps_per_split = ceil_div(p.ksteps_total, splitk);
   splitk = ceil_div(p.ksteps_total, p.ksteps_per_split);
-  grid.z = splitk;
+  p.splitk = splitk;
   p.out_mode = splitk > 1 ? 2 : (beta != 0.0f ? 1 : 0);
   if (splitk > 1 && beta == 0.0f) {
     long n = (long)M * N;
     zero_matrix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(C, ldc, M, N);
     EBK_LAUNCH_CHECK();
   }
+  const long n_items = tiles * splitk;
+  const int grid = (int)(n_items < g_num_sms ? n_items : g_num_sms);
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-#define LAUNCH4(AMN_, BMN_, BREG_, X3_)                                                                  \
+#define LAUNCH4(AMN_, BMN_, BMODE_, X3_)                                                                 \
   {                                                                                                      \
-    EBK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<AMN_, BMN_, BREG_, X3_>,                               \
+    EBK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<AMN_, BMN_, BMODE_, X3_>,                              \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-    gemm_tf32_kernel<AMN_, BMN_, BREG_, X3_><<<grid, THREADS, smem, st>>>(p);                             \
+    gemm_tf32_kernel<AMN_, BMN_, BMODE_, X3_><<<grid, THREADS, smem, st>>>(p);                            \
   }
-#define LAUNCH(AMN_, BMN_)                                   \
-  {                                                          \
-    if (b_rounded && !x3) LAUNCH4(AMN_, BMN_, false, false)  \
-    else if (b_rounded && x3) LAUNCH4(AMN_, BMN_, false, true) \
-    else if (!x3) LAUNCH4(AMN_, BMN_, true, false)           \
-    else LAUNCH4(AMN_, BMN_, true, true)                     \
+#define LAUNCH3(AMN_, BMN_, BMODE_)            \
+  {                                            \
+    if (x3) LAUNCH4(AMN_, BMN_, BMODE_, true)  \
+    else LAUNCH4(AMN_, BMN_, BMODE_, false)    \
+  }
+#define LAUNCH(AMN_, BMN_)                                        \
+  {                                                               \
+    if (b_mode == GEMM_B_PACKED) LAUNCH3(AMN_, BMN_, 0)           \
+    else if (b_mode == GEMM_B_ROUNDED) LAUNCH3(AMN_, BMN_, 1)     \
+    else LAUNCH3(AMN_, BMN_, 2)                                   \
   }
   if (!a_mn && !b_mn) LAUNCH(false, false)
   else if (!a_mn && b_mn) LAUNCH(false, true)
   else if (a_mn && !b_mn) LAUNCH(true, false)
   else LAUNCH(true, true)
 #undef LAUNCH
+#undef LAUNCH3
 #undef LAUNCH4
   EBK_LAUNCH_CHECK();
   return EBK_OK;

@@ -19,38 +19,46 @@ K_EPSILON = 1e-7  # keras.backend.epsilon(), used by AttLayer2 (layers.py:75-77)
 # defines its own counter-based mask (same function in csrc/ebk_common.cuh);
 # semantics are Keras' inverted dropout: y = x * keep / (1 - p)  (nrms.py:136,153).
 # ---------------------------------------------------------------------------
-_GOLDEN = np.uint64(0x9E3779B97F4A7C15)
-_M1 = np.uint64(0xBF58476D1CE4E5B9)
-_M2 = np.uint64(0x94D049BB133111EB)
+_U32 = np.uint64(0xFFFFFFFF)
 
 
-def _mix64(z: np.ndarray) -> np.ndarray:
-    z = z.astype(np.uint64)
-    with np.errstate(over="ignore"):
-        z = (z ^ (z >> np.uint64(30))) * _M1
-        z = (z ^ (z >> np.uint64(27))) * _M2
-        z = z ^ (z >> np.uint64(31))
-    return z
+def _mul32(a, c):
+    return (a * np.uint64(c)) & _U32
+
+
+def _group_bits(seed: int, g: np.ndarray):
+    """Two 32-bit avalanche hashes of (seed, group) -> (x, y), each uint64 holding 32 bits."""
+    s0 = np.uint64(seed & 0xFFFFFFFF)
+    s1 = np.uint64((seed >> 32) & 0xFFFFFFFF)
+    g = g.astype(np.uint64)
+    x = (_mul32(g & _U32, 0x9E3779B1) + _mul32(g >> np.uint64(32), 0x85EBCA77) + s0) & _U32
+    x ^= x >> np.uint64(16); x = _mul32(x, 0x7FEB352D)
+    x ^= x >> np.uint64(15); x = _mul32(x, 0x846CA68B)
+    x ^= x >> np.uint64(16)
+    y = _mul32(x ^ s1, 0x9E3779B1)
+    y ^= y >> np.uint64(15); y = _mul32(y, 0x2C1B3C6D)
+    y ^= y >> np.uint64(12); y = _mul32(y, 0x297A2D39)
+    y ^= y >> np.uint64(15)
+    return x, y
 
 
 def dropout_threshold(p: float) -> int:
     """16-bit keep threshold: element kept iff its 16 random bits >= threshold."""
-    return int(np.floor(p * 65536.0 + 0.5))
+    return int(np.floor(np.float32(p) * np.float32(65536.0) + np.float32(0.5)))
 
 
 def dropout_keep_mask(seed: int, n_elems: int, p: float) -> np.ndarray:
     """Boolean keep mask over a flat element index space [0, n_elems).
 
-    Elements are grouped by 4 (g = idx >> 2); group g draws
-    r = splitmix64 output number g of the stream seeded with ``seed``:
-    r = mix64(seed + (g + 1) * GOLDEN); lane j = idx & 3 uses bits [16j, 16j+16).
+    Elements are grouped by 4 (g = idx >> 2); group g draws two 32-bit words (x, y) from
+    (seed, g) with lowbias32-style hashes; lane j = idx & 3 uses x[0:16], x[16:32], y[0:16],
+    y[16:32].  Same function as csrc/ebk_common.cuh::dropout_group_bits.
     """
     idx = np.arange(n_elems, dtype=np.uint64)
-    g = idx >> np.uint64(2)
-    with np.errstate(over="ignore"):
-        r = _mix64(np.uint64(seed) + (g + np.uint64(1)) * _GOLDEN)
-    lane = (idx & np.uint64(3)) * np.uint64(16)
-    bits = (r >> lane) & np.uint64(0xFFFF)
+    x, y = _group_bits(int(seed) & ((1 << 64) - 1), idx >> np.uint64(2))
+    lane = idx & np.uint64(3)
+    w = np.where(lane >= np.uint64(2), y, x)
+    bits = np.where((lane & np.uint64(1)) == np.uint64(1), w >> np.uint64(16), w & np.uint64(0xFFFF))
     return bits >= np.uint64(dropout_threshold(p))
 
 
