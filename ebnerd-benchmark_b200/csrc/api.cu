@@ -71,6 +71,7 @@ struct SeqWs {
   float *wqkv_f, *attw_f;              //   forward  (B = W,   MN-major)
   float *wqkv_d, *attw_d;              //   dgrad    (B = W^T, K-major)
   float *wqkv_f_lo, *attw_f_lo;        //   3xTF32 low parts of the forward packs (EBK_MATH_TF32X3)
+  float* dqkv_pk;                      // dQKV again, in the packed B layout of the weight-gradient GEMM
   size_t bytes;
 };
 
@@ -99,6 +100,7 @@ SeqWs seq_layout(const ebk_seqenc_desc& d, void* base) {
   w.attw_d = take(gemm_tf32_packed_floats((int)D, d.att, true));
   w.wqkv_f_lo = take(gemm_tf32_packed_floats(3 * (int)D, d.Din, false));
   w.attw_f_lo = take(gemm_tf32_packed_floats(d.att, (int)D, false));
+  w.dqkv_pk = take(gemm_tf32_packed_floats(3 * (int)D, (int)R, false));
   w.bytes = off;
   return w;
 }
@@ -267,11 +269,15 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   EBK_PROF(T_ATT_DGRAD, gemm_dispatch(d->math, adp, pk_att ? ws.attw_d : attW, d->att, true, ws.dy, D, R, D, d->att,
                                       1.0f, st, pk_att ? GEMM_B_PACKED : GEMM_B_RAW));
   // SelfAttention core backward (dropout2 mask applied while reading dy)
-  EBK_PROF(T_ATTN_BWD, attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, rnd, st));
-  // dWqkv += X^T dQKV  (X = dropout1(gather))
   GemmOperandA axT{table_or_x, d->Din, true, tok, d->V, tok ? drop1 : none, d->Din};
-  EBK_PROF(T_QKV_WGRAD, gemm_dispatch(d->math, axT, ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din, 3 * D, R, 1.0f, st,
-                                      rnd ? GEMM_B_ROUNDED : GEMM_B_RAW));
+  const bool pk_dq = rnd && gemm_tf32_eligible(axT, ws.dqkv, 3 * D, d->Din, 3 * D, R) &&
+                     (d->dh == 8 || d->dh == 16 || d->dh == 20 || d->dh == 32);
+  EBK_PROF(T_ATTN_BWD, attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, rnd, st,
+                                          pk_dq ? ws.dqkv_pk : nullptr, pk_dq ? gemm_tf32_bn(3 * D, R, false) : 0));
+  // dWqkv += X^T dQKV  (X = dropout1(gather))
+  EBK_PROF(T_QKV_WGRAD, gemm_dispatch(d->math, axT, pk_dq ? ws.dqkv_pk : ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din,
+                                      3 * D, R, 1.0f, st,
+                                      pk_dq ? GEMM_B_PACKED : (rnd ? GEMM_B_ROUNDED : GEMM_B_RAW)));
   // dX = dQKV Wqkv^T
   if (tok != nullptr ? (d_table != nullptr) : (d_x != nullptr)) {
     float* dx = tok ? ws.dx : d_x;

@@ -173,6 +173,7 @@ int gemm_tf32(const GemmOperandA& A, const float* B, int ldb, bool transB, float
               const float* B_lo = nullptr);
 bool gemm_tf32_eligible(const GemmOperandA& A, const float* B, int ldb, int M, int N, int K);
 size_t gemm_tf32_packed_floats(int N, int K, bool transB);
+int gemm_tf32_bn(int N, int K, bool transB);  // tile width the GEMM will use for this B
 int gemm_tf32_pack_b(float* dst_hi, float* dst_lo, const float* B, int ldb, bool transB, int N, int K,
                      cudaStream_t st);
 int gemm_dispatch(int math, const GemmOperandA& A, const float* B, int ldb, bool transB, float* C,
@@ -185,8 +186,10 @@ int round_tf32_copy(float* dst, const float* src, size_t n, cudaStream_t st);
 
 int attention_core_fwd(int n_seq, int L, int nh, int dh, const float* qkv, float* y, cudaStream_t st);
 // round_out: store dqkv rounded to tf32 (it is the cp.async-staged B operand of the wgrad GEMM)
+// dqkv_packed (optional): second copy of dqkv in the packed B layout of the wgrad GEMM (tile width packed_bn)
 int attention_core_bwd(int n_seq, int L, int nh, int dh, const float* qkv, const float* dy,
-                       Dropout drop, float* dqkv, bool round_out, cudaStream_t st);
+                       Dropout drop, float* dqkv, bool round_out, cudaStream_t st, float* dqkv_packed = nullptr,
+                       int packed_bn = 0);
 
 // AttLayer2 pieces
 int attpool_fwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, float* hbuf /*[R,att] in: pre-act, out: tanh*/,

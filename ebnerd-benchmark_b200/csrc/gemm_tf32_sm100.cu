@@ -802,6 +802,8 @@ bool gemm_tf32_eligible(const GemmOperandA& A, const float* B, int ldb, int M, i
   return aligned && K >= 8 && (long)M * N * K >= (1L << 18);
 }
 
+int gemm_tf32_bn(int N, int K, bool transB) { return b_geom(N, K, transB).BN; }
+
 size_t gemm_tf32_packed_floats(int N, int K, bool transB) {
   const BGeom g = b_geom(N, K, transB);
   return (size_t)g.tiles_n * g.ksteps * (g.b_tile / 4);
