@@ -1,6 +1,7 @@
 // C-ABI entry points: error plumbing, the sequence encoder (news / user encoder)
 // forward + backward composed from the kernels of this directory, and test exports.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <vector>
@@ -123,6 +124,13 @@ int check_desc(const ebk_seqenc_desc* d) {
 using namespace ebk;
 
 extern "C" const char* ebk_last_error(void) { return g_err; }
+namespace ebk { void gemm_tf32_set_debug(long long* buf, int target); }
+// debugging aid: device buffer of 3*96*4 int64 receiving clock64() stamps of CTA 0 of the target-th
+// tcgen05 GEMM launched after this call (NULL disarms)
+extern "C" int ebk_debug_gemm_timeline(long long* device_buf, int target) {
+  ebk::gemm_tf32_set_debug(device_buf, target);
+  return 0;
+}
 extern "C" long long ebk_launch_count(void) { return g_launches.load(); }
 extern "C" int ebk_prof_enable(int on) {
   g_prof = on != 0;
@@ -183,12 +191,9 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   cudaStream_t st = (cudaStream_t)stream;
   g_prof_user = tok == nullptr;
   const int R = d->n_seq * d->L, D = d->nh * d->dh;
-  const Dropout drop1 = make_dropout(training != 0, d->dropout, seed1);
-  const Dropout drop2 = make_dropout(training != 0, d->dropout, seed2);
+  Dropout drop1 = make_dropout(training != 0, d->dropout, seed1);
+  Dropout drop2 = make_dropout(training != 0, d->dropout, seed2);
   const Dropout none = make_dropout(false, 0.0f, 0);
-
-  // B operands of the tensor-core GEMMs: tf32-rounded (to nearest) copies of the weights, kept in the
-  // workspace for the backward pass.  The fp32 path uses the weights as they are.
   // Tensor-core modes: the weights are packed once per call (rounded to tf32, arranged in the GEMM's
   // shared-memory tile layout) and kept in the workspace for the backward pass.
   const bool tc = d->math != EBK_MATH_FP32;
@@ -241,8 +246,8 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   cudaStream_t st = (cudaStream_t)stream;
   g_prof_user = tok == nullptr;
   const int R = d->n_seq * d->L, D = d->nh * d->dh;
-  const Dropout drop1 = make_dropout(training != 0, d->dropout, seed1);
-  const Dropout drop2 = make_dropout(training != 0, d->dropout, seed2);
+  Dropout drop1 = make_dropout(training != 0, d->dropout, seed1);
+  Dropout drop2 = make_dropout(training != 0, d->dropout, seed2);
   const Dropout none = make_dropout(false, 0.0f, 0);
 
   // tensor-core mode: the forward left the packed weights in the workspace, and the kernels that

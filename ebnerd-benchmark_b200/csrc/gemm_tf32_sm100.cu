@@ -61,7 +61,15 @@ struct Params {
   int ksteps_per_split;
   int out_mode;       // 0 store, 1 load-add-store (beta=1), 2 atomic add (split-K)
   float alpha;        // output scale (carries the dropout 1/(1-p) of a masked A operand)
+  uint32_t a_prefetch_bytes;  // K-major A: bytes of each row to prefetch into L2 per item (0 = off)
+  long long* dbg;             // optional timeline buffer (CTA 0): [role][step][4] clock64 stamps
 };
+constexpr int DBG_STEPS = 96;
+__device__ __forceinline__ void dbg_stamp(long long* dbg, int role, int step, int slot) {
+#ifdef EBK_GEMM_TIMELINE  // tools/gemm_timeline.py; compiled out of the product build
+  if (dbg != nullptr && blockIdx.x == 0 && step < DBG_STEPS) dbg[(role * DBG_STEPS + step) * 4 + slot] = clock64();
+#endif
+}
 
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -271,11 +279,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 // Walks this CTA's work items (m-tile, n-tile, k-split; n fastest) k-step by k-step.
 struct Cursor {
   int item, ks, ks_end;   // current item, current k-step, end k-step of the item
-  int m0, n0;
+  int m0, n0, tn;
   __device__ __forceinline__ void load(const Params& p) {
     const int per_m = p.tiles_n * p.splitk;
     const int tm = item / per_m, rem = item - tm * per_m;
-    const int tn = rem / p.splitk, sp = rem - tn * p.splitk;
+    tn = rem / p.splitk;
+    const int sp = rem - tn * p.splitk;
     m0 = tm * BM;
     n0 = tn * p.BN;
     ks = sp * p.ksteps_per_split;
@@ -283,7 +292,7 @@ struct Cursor {
   }
   __device__ __forceinline__ void init(const Params& p, int first, int n_items) {
     item = first;
-    ks = ks_end = m0 = n0 = 0;
+    ks = ks_end = m0 = n0 = tn = 0;
     if (item < n_items) load(p);
   }
   __device__ __forceinline__ bool valid(int n_items) const { return item < n_items; }
@@ -394,6 +403,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
           }
           aptr[q] = ok ? p.A + r * (long)p.lda + ac[q] * 4 : nullptr;
           avalid[q] = 4;
+          // One thread per row asks the L2 for the whole row (all k-steps of this item): DRAM then sees
+          // one sequential burst per gathered row instead of K/32 scattered 128-byte reads.
+          if (ok && ac[q] == 0 && p.a_prefetch_bytes)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(aptr[q]), "r"(p.a_prefetch_bytes) : "memory");
         } else {
           const int m = ld.m0 + ac[q] * 4;
           int nv = p.M - m;
@@ -441,6 +454,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
       }
     };
     // ---- per-item state of the PROCESS cursor: dropout group id of each chunk at k-step 0 ----
+    // (the mask is re-hashed here: measured on B200, fetching precomputed keep bits is not faster)
     int pr_item = -1;
     uint64_t dgrp[A_CH];
     uint64_t dstep = 0;  // group-id increment per k-step
@@ -454,7 +468,6 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
       }
       dstep = A_MN ? ((uint64_t)BK * (uint64_t)p.a_drop_ld) >> 2 : (uint64_t)(BK / 4);
     };
-
     float4 av[PF][A_CH];
     // prologue: A loads of the first PF-1 steps
 #pragma unroll
@@ -468,6 +481,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
     }
     int g = 0;          // flat k-step counter of this CTA
     int published = 0;  // steps whose full barrier has been arrived on
+    int s = 0;          // stage of step g, and the parity of its use (no runtime div/mod in the loop)
+    uint32_t ph = 0;
+    int ps = 0;         // stage of the next step to publish
     while (pr.valid(n_items)) {
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
@@ -478,9 +494,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
           a_load(av[(u + PFM1) % PF]);
           ld.advance(p, n_items, gridDim.x);
         }
-        const int s = g % S, round = g / S;
         const int k0 = pr.ks * BK;
-        mbar_wait(smem_u32(&empty_bar[s]), (uint32_t)((round & 1) ^ 1));
+        if (ptid == 0) dbg_stamp(p.dbg, 0, g, 0);
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        if (ptid == 0) dbg_stamp(p.dbg, 0, g, 1);
         uint8_t* pa = smem + (size_t)s * stage_bytes;
         uint8_t* pb = pa + a_bytes;
         const uint32_t sb = smem_base + (uint32_t)s * stage_bytes + a_bytes;
@@ -489,7 +506,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
           if (ptid == 0) {
             const uint32_t bar = smem_u32(&full_bar[s]);
             const uint32_t bytes = NSPLIT * b_tile;
-            const size_t blk = ((size_t)(pr.n0 / BN) * p.ksteps_total + pr.ks) * (size_t)(b_tile / 4);
+            const size_t blk = ((size_t)pr.tn * p.ksteps_total + pr.ks) * (size_t)(b_tile / 4);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb),
                          "l"(p.B + blk), "r"(b_tile), "r"(bar)
@@ -535,8 +552,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
         for (int q = 0; q < A_CH; ++q) {
           float4 v = av[u][q];
           if (p.a_drop.on()) {
-            const uint64_t grp = dgrp[q] + (uint64_t)pr.ks * dstep;
-            const float4 f = p.a_drop.factor4_group(grp);  // scale forced to 1 by the host
+            const float4 f = p.a_drop.factor4_group(dgrp[q] + (uint64_t)pr.ks * dstep);  // scale forced to 1
             v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
           }
           if (X3) {
@@ -575,21 +591,31 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
             }
           }
         }
+        if (ptid == 0) dbg_stamp(p.dbg, 0, g, 2);
         // ---- publish step g-LAG (its cp.async group is complete once <= LAG younger groups are pending) ----
         if (g - LAG >= 0) {
           if (BMODE == 1) cp_async_wait_dyn(LAG);
           fence_proxy_async();  // this thread's st.shared / cp.async writes -> visible to the tensor core
-          mbar_arrive(smem_u32(&full_bar[(g - LAG) % S]));
+          mbar_arrive(smem_u32(&full_bar[ps]));
+          if (++ps == S) ps = 0;
           published = g - LAG + 1;
         }
+        if (ptid == 0) dbg_stamp(p.dbg, 0, g, 3);
         pr.advance(p, n_items, gridDim.x);
         ++g;
+        if (++s == S) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
     // drain: publish the last LAG steps
     if (BMODE == 1) cp_async_wait<0>();
     fence_proxy_async();
-    for (int j = published; j < g; ++j) mbar_arrive(smem_u32(&full_bar[j % S]));
+    for (int j = published; j < g; ++j) {
+      mbar_arrive(smem_u32(&full_bar[ps]));
+      if (++ps == S) ps = 0;
+    }
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -601,7 +627,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
       const uint32_t a_lt = A_MN ? 1u : 2u, b_lt = B_MN ? 1u : 2u;
       Cursor cu;
       cu.init(p, blockIdx.x, n_items);
-      int g = 0, t = 0;
+      int g = 0, t = 0, s = 0;
+      uint32_t ph = 0;
       while (cu.valid(n_items)) {
         const int buf = t & 1, use = t >> 1;
         mbar_wait_backoff(smem_u32(&tempty_bar[buf]), (uint32_t)((use & 1) ^ 1));  // epilogue drained this buffer
@@ -609,8 +636,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
         const uint32_t tacc = tmem + (uint32_t)buf * 256u;
         bool first = true, last = false;
         while (!last) {
-          const int s = g % S, round = g / S;
-          mbar_wait(smem_u32(&full_bar[s]), (uint32_t)(round & 1));
+          dbg_stamp(p.dbg, 1, g, 0);
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          dbg_stamp(p.dbg, 1, g, 1);
           tc_fence_after();
           const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
           const uint32_t sb = sa + a_bytes;
@@ -630,9 +658,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
             }
           }
           umma_commit(smem_u32(&empty_bar[s]));  // frees the stage when these MMAs retire
+          dbg_stamp(p.dbg, 1, g, 2);
           first = false;
           last = cu.advance(p, n_items, gridDim.x);
           ++g;
+          if (++s == S) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
         umma_commit(smem_u32(&tfull_bar[buf]));  // accumulator of this item complete
         ++t;
@@ -649,7 +682,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
     while (cu.valid(n_items)) {
       const int buf = t & 1, use = t >> 1;
       const int m0 = cu.m0, n0 = cu.n0;
+      if (ew == 0 && lane == 0) dbg_stamp(p.dbg, 2, t, 0);
       mbar_wait_backoff(smem_u32(&tfull_bar[buf]), (uint32_t)(use & 1));
+      if (ew == 0 && lane == 0) dbg_stamp(p.dbg, 2, t, 1);
       tc_fence_after();
       const int row = m0 + ew * 32 + lane;
       const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * 256u;
@@ -706,6 +741,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tf32_kernel(const Params p) {
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&tempty_bar[buf]));  // buffer may be overwritten by the MMA warp
+      if (ew == 0 && lane == 0) dbg_stamp(p.dbg, 2, t, 2);
       // skip to this CTA's next item
       cu.ks = cu.ks_end - 1;
       cu.advance(p, n_items, gridDim.x);
@@ -773,6 +809,8 @@ __global__ void pack_b_kernel(float* __restrict__ dst_hi, float* __restrict__ ds
 }
 
 int g_num_sms = 0;
+long long* g_dbg = nullptr;
+int g_dbg_target = 0, g_dbg_count = 0;  // only the g_dbg_target-th GEMM launch after arming is traced
 
 struct BGeom {
   bool b_mn;
@@ -794,6 +832,12 @@ BGeom b_geom(int N, int K, bool transB) {
 }
 
 }  // namespace
+
+void gemm_tf32_set_debug(long long* buf, int target) {
+  g_dbg = buf;
+  g_dbg_target = target;
+  g_dbg_count = 0;
+}
 
 bool gemm_tf32_eligible(const GemmOperandA& A, const float* B, int ldb, int M, int N, int K) {
   // 16-byte loads need 4-float aligned rows; tiny or unaligned problems take the fp32 FMA kernel.
@@ -838,6 +882,9 @@ int gemm_tf32(const GemmOperandA& A, const float* B, int ldb, bool transB, float
   p.a_drop_ld = A.drop_ld;
   p.alpha = A.drop.on() ? A.drop.scale : 1.0f;  // mask in the operand, scale on the accumulator
   p.a_drop.scale = 1.0f;
+  // whole-row L2 prefetch pays when the rows are scattered (gather) or strided; rows must be 16B multiples
+  p.a_prefetch_bytes = (!A.trans && K >= 64) ? (uint32_t)((K * 4) & ~15) : 0u;
+  p.dbg = (g_dbg != nullptr && g_dbg_count++ == g_dbg_target) ? g_dbg : nullptr;
   p.B = B; p.B_lo = B_lo; p.ldb = ldb; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
   const bool a_mn = A.trans;
   const BGeom bg = b_geom(N, K, transB);
