@@ -37,7 +37,7 @@ constexpr int BM = 128;
 constexpr int BK = 32;             // fp32 elements per stage along K = one 128-byte swizzle row
 constexpr int UMMA_K = 8;          // tf32
 constexpr int MAX_STAGES = 8;
-constexpr int PROD_WARPS = 8;
+constexpr int PROD_WARPS = 16;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int MMA_WARP = PROD_WARPS;
 constexpr int EPI_THREADS = 128;
