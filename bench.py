@@ -23,7 +23,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -77,50 +76,51 @@ def flops_per_impression_fwd(w):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML DURING the timed region (B200_PROFILING.md)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, gpu_index: int):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.h, self.sm, self.mask, self.run, self.t = gpu_index, None, [], 0, False, None
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception as e:  # NVML missing: report it, never fake a clock
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while self.run:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.mask |= int(get(self.h))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.h is None:
+            return
+        self.run = True
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self.run = False
+        self.t.join(timeout=2)
+        mx = self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": mx, "samples": len(self.sm),
+                "reasons": sorted(v for k, v in self.REASONS.items() if self.mask & k)}
 
 
 # ------------------------------------------------------------------------------------------

@@ -1,0 +1,215 @@
+"""CPU tests of the host side: reference helper known-answers, the dataloader contract (ported from the
+reference's test/dataloader/test_newsrec.py), hparams surface, C-ABI symbol export, facade error behaviour,
+and the data-parallel gradient identity over gloo (world_size 2)."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+GOLD = Path(__file__).parent / "golden"
+
+
+# ---- reference docstring known answers -------------------------------------------------------------------
+def test_repeat_by_list_values_from_matrix_docstring_example():
+    from ebrec.models.newsrec.dataloader import repeat_by_list_values_from_matrix
+
+    out = repeat_by_list_values_from_matrix(np.array([[1, 0], [0, 0]]), np.array([[7, 8, 9], [10, 11, 12]]), np.array([1, 2]))
+    want = np.array([[[10, 11, 12], [7, 8, 9]], [[7, 8, 9], [7, 8, 9]], [[7, 8, 9], [7, 8, 9]]])  # _python.py:376-386
+    assert np.array_equal(out, want)
+
+
+def test_create_lookup_objects_docstring_example():
+    from ebrec.models.newsrec.dataloader import create_lookup_objects
+
+    data = {10: np.array([0.1, 0.2, 0.3]), 20: np.array([0.4, 0.5, 0.6]), 30: np.array([0.7, 0.8, 0.9])}
+    idx, mat = create_lookup_objects(data, "zeros")  # _python.py:440-465
+    assert idx == {10: 1, 20: 2, 30: 3}
+    np.testing.assert_allclose(mat, [[0, 0, 0], [0.1, 0.2, 0.3], [0.4, 0.5, 0.6], [0.7, 0.8, 0.9]])
+    _, mat_mean = create_lookup_objects(data, "mean")
+    np.testing.assert_allclose(mat_mean[0], [0.4, 0.5, 0.6])
+    with pytest.raises(ValueError):
+        create_lookup_objects(data, "median")
+
+
+# ---- dataloader contract (test/dataloader/test_newsrec.py:66-105) ---------------------------------------------
+@pytest.fixture(scope="module")
+def sample():
+    d = json.loads((GOLD / "ebnerd_sample.json").read_text())
+    beh = d["behaviors"]
+    mapping = {int(k): v for k, v in d["article_tokens"].items()}
+    return beh, mapping
+
+
+def test_nrms_dataloader_contract(sample):
+    from ebrec.models.newsrec.dataloader import NRMSDataLoader, NRMSDataLoaderPretransform
+
+    beh, mapping = sample
+    BATCH = 100
+    nmin = min(len(r) for r in beh["article_ids_inview"])
+    keep = [i for i, r in enumerate(beh["article_ids_inview"]) if len(r) == nmin]
+    train = {k: [v[i] for i in keep] for k, v in beh.items()}
+    for cls in (NRMSDataLoader, NRMSDataLoaderPretransform):
+        dl = cls(behaviors=train, article_dict=mapping, history_column="article_id_fixed",
+                 unknown_representation="zeros", eval_mode=False, batch_size=BATCH)
+        batch = next(iter(dl))
+        assert len(dl) == int(np.ceil(len(keep) / BATCH))
+        assert len(batch) == 2 and len(batch[0]) == 2
+        his, pred = batch[0]
+        assert isinstance(his.ravel()[0], np.integer) and isinstance(batch[1].ravel()[0], np.integer)
+        n0 = min(BATCH, len(keep))
+        assert his.shape == (n0, 3, 10) and pred.shape == (n0, nmin, 10) and batch[1].shape == (n0, nmin)
+    test = NRMSDataLoader(behaviors=beh, article_dict=mapping, history_column="article_id_fixed",
+                          unknown_representation="zeros", eval_mode=True, batch_size=BATCH)
+    (his, pred), y = next(iter(test))
+    n = sum(len(r) for r in beh["article_ids_inview"][:BATCH])
+    assert len(y) == n and y.shape == (n, 1) and his.shape == (n, 3, 10) and pred.shape == (n, 1, 10)
+    # history rows are repeated once per candidate of the impression
+    n_first = len(beh["article_ids_inview"][0])
+    assert np.array_equal(his[0], his[n_first - 1])
+    # last batch may be short
+    last = test[len(test) - 1]
+    assert len(last[1]) == sum(len(r) for r in beh["article_ids_inview"][(len(test) - 1) * BATCH:])
+
+
+def test_unknown_article_ids_map_to_row_zero(sample):
+    from ebrec.models.newsrec.dataloader import NRMSDataLoader
+
+    beh, mapping = sample
+    two = {k: [v[0], v[1]] for k, v in beh.items()}
+    two["article_id_fixed"] = [[-1, -2, -3], two["article_id_fixed"][1]]
+    n = min(len(r) for r in two["article_ids_inview"])
+    two["article_ids_inview"] = [r[:n] for r in two["article_ids_inview"]]
+    two["labels"] = [r[:n] for r in two["labels"]]
+    (his, _), _ = NRMSDataLoader(behaviors=two, article_dict=mapping, history_column="article_id_fixed",
+                                 unknown_representation="zeros", batch_size=2)[0]
+    assert not his[0].any() and his[1].any()
+
+
+def test_naml_dataloader_contract(sample):
+    from ebrec.models.newsrec.dataloader import NAMLDataLoader
+
+    beh, mapping = sample
+    nmin = min(len(r) for r in beh["article_ids_inview"])
+    keep = [i for i, r in enumerate(beh["article_ids_inview"]) if len(r) == nmin][:40]
+    train = {k: [v[i] for i in keep] for k, v in beh.items()}
+    cat = {a: (a % 7) + 1 for a in mapping}
+    kw = dict(behaviors=train, article_dict=mapping, body_mapping=mapping, category_mapping=cat, subcategory_mapping=cat,
+              history_column="article_id_fixed", unknown_representation="zeros", batch_size=16)
+    dl = NAMLDataLoader(**kw)
+    x, y = dl[0]
+    assert len(x) == 8  # test_newsrec.py:175-190
+    assert x[0].shape == (16, 3, 10) and x[2].shape == (16, 3, 1) and x[4].shape == (16, nmin, 10) and x[7].shape == (16, nmin, 1)
+    with pytest.raises(ValueError):
+        NAMLDataLoader(**{**kw, "eval_mode": True})  # dataloader.py:289-290
+
+
+# ---- hparams surface ----------------------------------------------------------------------------------------
+def test_hparams_defaults_match_reference():
+    from ebrec.models.newsrec.model_config import hparams_naml, hparams_nrms, hparams_nrms_docvec, hparams_to_dict
+
+    d = hparams_to_dict(hparams_nrms)  # model_config.py:82-97
+    assert d == {"title_size": 30, "history_size": 20, "head_num": 20, "head_dim": 20, "attention_hidden_dim": 200,
+                 "optimizer": "adam", "loss": "cross_entropy_loss", "dropout": 0.2, "learning_rate": 1e-4,
+                 "newsencoder_units_per_layer": None, "newsencoder_l2_regularization": 1e-4}
+    assert hparams_nrms_docvec.title_size == 768 and hparams_nrms_docvec.newsencoder_units_per_layer == [512, 512, 512]
+    assert hparams_naml.filter_num == 400 and hparams_naml.window_size == 3 and hparams_naml.body_size == 40
+
+
+# ---- C-ABI library ------------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    hdr = (ROOT / "include" / "ebk.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ebk_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    lib_path = ROOT / "ebnerd-benchmark_b200" / "csrc" / "libebk.so"
+    if not lib_path.exists():
+        subprocess.run(["make", "-C", str(lib_path.parent), "-j8"], check=True, capture_output=True)
+    lib = ctypes.CDLL(str(lib_path))
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    from ebrec.models.newsrec import _ebk
+
+    assert set(_ebk.SYMBOLS) <= declared
+    assert lib.ebk_version() >= 100  # pure host call; no compute without a GPU
+
+
+def test_product_path_fails_loudly_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ebrec.models.newsrec import _ebk
+    from ebrec.models.newsrec.model_config import hparams_nrms
+    from ebrec.models.newsrec.nrms import NRMSModel
+
+    with pytest.raises(_ebk.EbkError):
+        NRMSModel(hparams_nrms, word2vec_embedding=np.random.rand(50, 8))
+
+
+def test_facade_rejects_unknown_loss_and_optimizer():
+    from ebrec.models.newsrec.model_config import hparams_nrms
+    from ebrec.models.newsrec.nrms import NRMSModel
+
+    class bad_loss(hparams_nrms):
+        loss = "hinge"
+
+    class bad_opt(hparams_nrms):
+        optimizer = "sgd"
+
+    with pytest.raises(ValueError, match="this loss not defined"):  # nrms.py:66
+        NRMSModel(bad_loss, word2vec_embedding=np.random.rand(50, 8))
+    with pytest.raises(ValueError, match="this optimizer not defined"):  # nrms.py:79
+        NRMSModel(bad_opt, word2vec_embedding=np.random.rand(50, 8))
+
+
+def test_keras_auc_matches_trapezoid_definition():
+    from ebrec.models.newsrec._keraslike import keras_auc
+
+    rng = np.random.default_rng(0)
+    y = rng.integers(0, 2, 5000)
+    p = np.clip(0.35 * y + rng.random(5000) * 0.65, 0, 1)
+    from sklearn.metrics import roc_auc_score
+
+    assert abs(keras_auc(y, p) - roc_auc_score(y, p)) < 5e-3  # 200-threshold approximation
+    assert abs(keras_auc(y, np.full(5000, 0.5)) - 0.5) < 1e-9
+
+
+# ---- data parallel: sum over ranks of (1/world)-scaled shard gradients == global-batch mean gradient -------------
+_DP_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["EBK_ROOT"])
+from oracle import nrms_oracle as O
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(0)
+V, E, nh, dh, att, B, H, C, T = 40, 8, 2, 4, 6, 4, 3, 3, 5
+P = O.init_nrms_params(rng, V, E, nh, dh, att, dtype=np.float64)
+his = rng.integers(0, V, (B, H, T)); pred = rng.integers(0, V, (B, C, T))
+y = np.zeros((B, C)); y[np.arange(B), rng.integers(0, C, B)] = 1
+sl = slice(rank * B // world, (rank + 1) * B // world)          # contiguous shard of the global batch
+_, _, G = O.nrms_loss_and_grads(his[sl], pred[sl], y[sl], P, nh, dh, training=False, loss_scale=1.0 / world)
+flat = torch.from_numpy(np.concatenate([G[k].ravel() for k in O.NRMS_PARAM_ORDER]))
+dist.all_reduce(flat)                                            # the one collective of a step
+_, _, Gfull = O.nrms_loss_and_grads(his, pred, y, P, nh, dh, training=False)
+want = np.concatenate([Gfull[k].ravel() for k in O.NRMS_PARAM_ORDER])
+err = float(np.abs(flat.numpy() - want).max())
+assert err < 1e-12, err
+if rank == 0: print("DP_OK", err)
+dist.destroy_process_group()
+'''
+
+
+def test_data_parallel_gradient_identity_gloo_world2(tmp_path):
+    script = tmp_path / "dp_worker.py"
+    script.write_text(_DP_WORKER)
+    env = dict(os.environ, EBK_ROOT=str(ROOT), MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29517", str(script)], env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "DP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
