@@ -215,7 +215,12 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
                                     d->Din, 0.0f, st, pk_qkv ? GEMM_B_PACKED : GEMM_B_RAW,
                                     (pk_qkv && x3) ? ws.wqkv_f_lo : nullptr));
   // (2) per-head softmax(QK^T/sqrt(dh)) and the adjoint product    layers.py:231-252
-  EBK_PROF(T_ATTN_FWD, attention_core_fwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st));
+  // training with tf32 contractions: warp-level tensor-core attention; otherwise the exact fp32 kernel
+  if (d->math == EBK_MATH_TF32 && training && attention_mma_supported(d->L, d->dh, ws.qkv, ws.y0, ws.qkv)) {
+    EBK_PROF(T_ATTN_FWD, attention_core_fwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st));
+  } else {
+    EBK_PROF(T_ATTN_FWD, attention_core_fwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st));
+  }
   // (3) pre-activation of AttLayer2: dropout2(Y0) . W              nrms.py:153-156, layers.py:65
   EBK_PROF(T_ATT_GEMM_FWD, gemm_dispatch(d->math, ay, pk_att ? ws.attw_f : attW, d->att, false, ws.hbuf, d->att, R,
                                          d->att, D, 0.0f, st, pk_att ? GEMM_B_PACKED : GEMM_B_RAW,
@@ -277,8 +282,15 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   GemmOperandA axT{table_or_x, d->Din, true, tok, d->V, tok ? drop1 : none, d->Din};
   const bool pk_dq = rnd && gemm_tf32_eligible(axT, ws.dqkv, 3 * D, d->Din, 3 * D, R) &&
                      (d->dh == 8 || d->dh == 16 || d->dh == 20 || d->dh == 32);
-  EBK_PROF(T_ATTN_BWD, attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, rnd, st,
-                                          pk_dq ? ws.dqkv_pk : nullptr, pk_dq ? gemm_tf32_bn(3 * D, R, false) : 0));
+  if (d->math == EBK_MATH_TF32 && training && attention_mma_supported(d->L, d->dh, ws.qkv, ws.dy, ws.dqkv)) {
+    EBK_PROF(T_ATTN_BWD, attention_core_bwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, rnd, st,
+                                                pk_dq ? ws.dqkv_pk : nullptr,
+                                                pk_dq ? gemm_tf32_bn(3 * D, R, false) : 0));
+  } else {
+    EBK_PROF(T_ATTN_BWD, attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, rnd, st,
+                                            pk_dq ? ws.dqkv_pk : nullptr,
+                                            pk_dq ? gemm_tf32_bn(3 * D, R, false) : 0));
+  }
   // dWqkv += X^T dQKV  (X = dropout1(gather))
   EBK_PROF(T_QKV_WGRAD, gemm_dispatch(d->math, axT, pk_dq ? ws.dqkv_pk : ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din,
                                       3 * D, R, 1.0f, st,

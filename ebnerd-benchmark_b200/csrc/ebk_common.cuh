@@ -191,6 +191,13 @@ int attention_core_bwd(int n_seq, int L, int nh, int dh, const float* qkv, const
                        Dropout drop, float* dqkv, bool round_out, cudaStream_t st, float* dqkv_packed = nullptr,
                        int packed_bn = 0);
 
+// warp-level tensor-core (mma.sync tf32) variants for training, L <= 32 (attention_mma.cu)
+bool attention_mma_supported(int L, int dh, const void* p0, const void* p1, const void* p2);
+int attention_core_fwd_mma(int n_seq, int L, int nh, int dh, const float* qkv, float* y, cudaStream_t st);
+int attention_core_bwd_mma(int n_seq, int L, int nh, int dh, const float* qkv, const float* dy, Dropout drop,
+                           float* dqkv, bool round_out, cudaStream_t st, float* dqkv_packed = nullptr,
+                           int packed_bn = 0);
+
 // AttLayer2 pieces
 int attpool_fwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, float* hbuf /*[R,att] in: pre-act, out: tanh*/,
                 const float* attb, const float* attq, float* w /*[R]*/, float* out /*[n_seq,D]*/, cudaStream_t st);
