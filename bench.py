@@ -260,13 +260,15 @@ def run_ours(args, w, wname):
     h2d = host[0][0].nbytes + host[0][1].nbytes + host[0][2].nbytes
 
     # ---- per-kernel profile pass (library CUDA-event profiler; not part of the numbers above) --
+    # (every rank runs the steps -- they contain the gradient collective -- only rank 0 records events)
     prof = {}
+    psteps = min(args.steps, 10)
     if rank == 0:
-        psteps = min(args.steps, 10)
         lib.ebk_prof_enable(1)
-        for i in range(psteps):
-            eng.train_step_dev(dev[i % n_pool][0], dev[i % n_pool][1], B, C_)
-        torch.cuda.synchronize()
+    for i in range(psteps):
+        eng.train_step_dev(dev[i % n_pool][0], dev[i % n_pool][1], B, C_)
+    torch.cuda.synchronize()
+    if rank == 0:
         prof = {k: (ms_ / psteps, c // psteps) for k, (ms_, c) in _ebk.prof_collect().items()}
         lib.ebk_prof_enable(0)
     sync_all()

@@ -47,6 +47,7 @@ class FlatParams:
         for name, shape in spec:
             self.offsets[name] = off
             off += (int(np.prod(shape)) + _ALIGN - 1) // _ALIGN * _ALIGN
+        off = (off + 1023) // 1024 * 1024  # divisible into 16-byte aligned shards for any world size <= 64
         self.n = off
         self.theta = torch.zeros(off, dtype=torch.float32, device=device)
         self.grad = torch.zeros_like(self.theta)
@@ -275,14 +276,30 @@ class NRMSEngine:
         return loss, probs
 
     def apply_adam(self) -> None:
-        """One Keras-form Adam iteration over the whole flat buffer (clears grad in the same pass)."""
+        """One Keras-form Adam iteration over the whole flat buffer (clears grad in the same pass).
+
+        Data parallel (world > 1): the gradient exchange is a reduce-scatter of the flat buffer (sum; the
+        loss is pre-scaled by 1/world), each rank runs the dense Keras Adam on ITS 1/world slice of
+        theta/m/v only (the 5.4 GB/step optimizer traffic is divided by world instead of replicated), and an
+        in-place all-gather republishes theta.  Wire volume equals one all-reduce."""
         P = self.params
-        if self.world > 1:
-            torch.distributed.all_reduce(P.grad)  # the one collective of the step (sum; loss pre-scaled by 1/world)
         self.step_count += 1
         alpha = keras_adam_alpha(self.lr, self.step_count, self.beta1, self.beta2)
-        _ebk.check(_ebk.lib().ebk_adam_keras_step(_ebk.ptr(P.theta), _ebk.ptr(P.grad), _ebk.ptr(P.m), _ebk.ptr(P.v),
-                                                  P.n, alpha, self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
+        lib = _ebk.lib()
+        if self.world == 1:
+            _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(P.theta), _ebk.ptr(P.grad), _ebk.ptr(P.m), _ebk.ptr(P.v),
+                                               P.n, alpha, self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
+            return
+        dist = torch.distributed
+        shard = P.n // self.world
+        lo = self.rank * shard
+        gsh = self._buf("grad_shard", (shard,))
+        dist.reduce_scatter_tensor(gsh, P.grad)
+        th, m, v = P.theta[lo: lo + shard], P.m[lo: lo + shard], P.v[lo: lo + shard]
+        _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(th), _ebk.ptr(gsh), _ebk.ptr(m), _ebk.ptr(v), shard, alpha,
+                                           self.beta1, self.beta2, self.eps, 0, _ebk.stream()))
+        dist.all_gather_into_tensor(P.theta, th)
+        P.grad.zero_()
 
     def train_step_dev(self, tok_all, labels, B, C_):
         loss, probs = self.loss_and_grads_dev(tok_all, labels, B, C_, training=True)
