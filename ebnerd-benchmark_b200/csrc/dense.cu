@@ -1,0 +1,314 @@
+// Dense(+ReLU) -> BatchNormalization -> Dropout layer of the NRMSDocVec news encoder
+// (reference nrms_docvec.py:118-130) forward and backward.  The contraction runs on the tcgen05 GEMM;
+// this file holds the HBM-bound elementwise / column-reduction kernels around it:
+//   fwd: a = relu(x W + b);  [mean, var over the rows of THIS call];  y = dropout(gamma (a-mean)/sqrt(var+eps) + beta)
+//   bwd: dyd = dropout'(dy); dgamma, dbeta; da (training-mode BN backward); dz = da [a>0]; db; dW = x^T dz (+2 l2 W); dx = dz W^T
+// Keras semantics: biased batch variance for both normalisation and the moving average; moving stats
+// updated per call: m = m*momentum + batch*(1-momentum).
+#include "ebk_common.cuh"
+
+namespace ebk {
+namespace {
+
+constexpr int ROWS_PER_BLK = 128;
+
+// a = act(z + b) in place, 128-bit
+__global__ void bias_act_kernel(float4* __restrict__ z, const float4* __restrict__ b, long n4, int U4, int relu) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = z[i];
+  const float4 bb = b[i % U4];
+  v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+  if (relu) {
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+  }
+  z[i] = v;
+}
+
+// partial[blk][0][j] = sum_r a[r,j], partial[blk][1][j] = sum_r a[r,j]^2 over the block's rows
+__global__ void col_stats_partial_kernel(const float* __restrict__ a, int N, int U, float* __restrict__ partial) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= U) return;
+  const int r0 = blockIdx.y * ROWS_PER_BLK, r1 = min(N, r0 + ROWS_PER_BLK);
+  float s = 0.f, q = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float v = a[(long)r * U + j];
+    s += v;
+    q = fmaf(v, v, q);
+  }
+  partial[((long)blockIdx.y * 2 + 0) * U + j] = s;
+  partial[((long)blockIdx.y * 2 + 1) * U + j] = q;
+}
+// mean / invstd of this call and the Keras moving-average update
+__global__ void col_stats_final_kernel(const float* __restrict__ partial, int nblk, int N, int U, float eps, float momentum,
+                                       float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ mov_mean,
+                                       float* __restrict__ mov_var) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= U) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += partial[((long)b * 2 + 0) * U + j];
+    q += partial[((long)b * 2 + 1) * U + j];
+  }
+  const double m = s / N;
+  double var = q / N - m * m;
+  var = var < 0.0 ? 0.0 : var;
+  mean[j] = (float)m;
+  invstd[j] = (float)(1.0 / sqrt(var + (double)eps));
+  mov_mean[j] = mov_mean[j] * momentum + (float)m * (1.0f - momentum);
+  mov_var[j] = mov_var[j] * momentum + (float)var * (1.0f - momentum);
+}
+__global__ void inference_stats_kernel(int U, float eps, const float* __restrict__ mov_mean,
+                                       const float* __restrict__ mov_var, float* __restrict__ mean,
+                                       float* __restrict__ invstd) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= U) return;
+  mean[j] = mov_mean[j];
+  invstd[j] = rsqrtf(mov_var[j] + eps);
+}
+// y = dropout(gamma * (a - mean) * invstd + beta)
+__global__ void bn_apply_kernel(const float4* __restrict__ a, long n4, int U4, const float4* __restrict__ mean,
+                                const float4* __restrict__ invstd, const float4* __restrict__ gamma,
+                                const float4* __restrict__ beta, Dropout drop, float4* __restrict__ y) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int c = (int)(i % U4);
+  const float4 v = a[i], m = mean[c], is = invstd[c], g = gamma[c], b = beta[c];
+  float4 o;
+  o.x = fmaf((v.x - m.x) * is.x, g.x, b.x);
+  o.y = fmaf((v.y - m.y) * is.y, g.y, b.y);
+  o.z = fmaf((v.z - m.z) * is.z, g.z, b.z);
+  o.w = fmaf((v.w - m.w) * is.w, g.w, b.w);
+  if (drop.on()) {
+    const float4 f = drop.factor4_group((uint64_t)i);
+    o.x *= f.x; o.y *= f.y; o.z *= f.z; o.w *= f.w;
+  }
+  y[i] = o;
+}
+
+// partial sums of dyd and dyd*xhat per column (dyd = dy * dropout factor)
+__global__ void bn_bwd_partial_kernel(const float* __restrict__ dy, const float* __restrict__ a, int N, int U,
+                                      const float* __restrict__ mean, const float* __restrict__ invstd, Dropout drop,
+                                      float* __restrict__ partial) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= U) return;
+  const int r0 = blockIdx.y * ROWS_PER_BLK, r1 = min(N, r0 + ROWS_PER_BLK);
+  const float m = mean[j], is = invstd[j];
+  float s1 = 0.f, s2 = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const long idx = (long)r * U + j;
+    float g = dy[idx];
+    if (drop.on()) g *= drop.factor((uint64_t)idx);
+    s1 += g;
+    s2 = fmaf(g, (a[idx] - m) * is, s2);
+  }
+  partial[((long)blockIdx.y * 2 + 0) * U + j] = s1;
+  partial[((long)blockIdx.y * 2 + 1) * U + j] = s2;
+}
+__global__ void bn_bwd_final_kernel(const float* __restrict__ partial, int nblk, int U, float* __restrict__ sums,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= U) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int b = 0; b < nblk; ++b) {
+    s1 += partial[((long)b * 2 + 0) * U + j];
+    s2 += partial[((long)b * 2 + 1) * U + j];
+  }
+  sums[j] = s1;
+  sums[U + j] = s2;
+  dbeta[j] += s1;
+  dgamma[j] += s2;
+}
+// dz = relu'(a) * invstd * gamma * (dyd - s1/N - xhat * s2/N)      (training-mode BN backward)
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ a, long n, int N, int U,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ sums, Dropout drop,
+                                    int relu, int round_out, float* __restrict__ dz) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int j = (int)(i % U);
+  float g = dy[i];
+  if (drop.on()) g *= drop.factor((uint64_t)i);
+  const float av = a[i];
+  const float xhat = (av - mean[j]) * invstd[j];
+  const float invN = 1.0f / (float)N;
+  float v = invstd[j] * gamma[j] * (g - sums[j] * invN - xhat * sums[U + j] * invN);
+  if (relu && !(av > 0.f)) v = 0.f;
+  dz[i] = round_out ? round_tf32_bits(v) : v;
+}
+// no BN: dz = dy * dropout' * relu'(y)
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ yv, long n, Dropout drop, int relu,
+                               int round_out, float* __restrict__ dz) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float g = dy[i];
+  if (drop.on()) g *= drop.factor((uint64_t)i);
+  if (relu && !(yv[i] > 0.f)) g = 0.f;
+  dz[i] = round_out ? round_tf32_bits(g) : g;
+}
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, long n, float a) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fmaf(a, x[i], y[i]);
+}
+__global__ void sumsq_kernel(const float* __restrict__ x, long n, float scale, float* __restrict__ out) {
+  float acc = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) acc = fmaf(x[i], x[i], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc * scale);
+}
+
+struct DenseWs {
+  float *a, *dz, *mean, *invstd, *sums, *partial, *w_f, *w_d, *colsum;
+  size_t bytes;
+};
+DenseWs dense_layout(const ebk_dense_desc& d, void* base) {
+  size_t off = 0;
+  auto take = [&](size_t nfloat) {
+    float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
+    off += align_up(nfloat * sizeof(float), 256);
+    return p;
+  };
+  const size_t N = d.N, U = d.U;
+  const size_t nblk = (N + ROWS_PER_BLK - 1) / ROWS_PER_BLK;
+  DenseWs w;
+  w.a = take(N * U);
+  w.dz = take(N * U);
+  w.mean = take(U);
+  w.invstd = take(U);
+  w.sums = take(2 * U);
+  w.partial = take(nblk * 2 * U);
+  w.w_f = take(gemm_tf32_packed_floats(d.U, d.K, false));
+  w.w_d = take(gemm_tf32_packed_floats(d.K, d.U, true));
+  w.colsum = take(colsum_partial_floats((int)N, (int)U));
+  w.bytes = off;
+  return w;
+}
+int check_dense(const ebk_dense_desc* d) {
+  EBK_CHECK_ARG(d != nullptr, "dense: null descriptor");
+  EBK_CHECK_ARG(d->N >= 0 && d->K >= 4 && d->U >= 4 && d->K % 4 == 0 && d->U % 4 == 0,
+                "dense: need K, U positive multiples of 4 (N=%d K=%d U=%d)", d->N, d->K, d->U);
+  EBK_CHECK_ARG(d->dropout >= 0.f && d->dropout < 1.f, "dense: dropout=%f", d->dropout);
+  return EBK_OK;
+}
+
+}  // namespace
+}  // namespace ebk
+
+using namespace ebk;
+
+extern "C" size_t ebk_dense_workspace_bytes(const ebk_dense_desc* d) {
+  if (check_dense(d) != EBK_OK) return 0;
+  return dense_layout(*d, nullptr).bytes;
+}
+
+extern "C" int ebk_dense_fwd(const ebk_dense_desc* d, const float* x, const float* W, const float* b, const float* gamma,
+                             const float* beta, float* mov_mean, float* mov_var, int training, uint64_t seed,
+                             void* workspace, size_t workspace_bytes, float* y, void* stream) {
+  EBK_TRY(check_dense(d));
+  if (d->N == 0) return EBK_OK;
+  EBK_CHECK_ARG(x && W && b && y && workspace, "dense_fwd: null pointer");
+  EBK_CHECK_ARG(!d->bn || (gamma && beta && mov_mean && mov_var), "dense_fwd: BatchNorm needs gamma/beta/moving stats");
+  DenseWs ws = dense_layout(*d, workspace);
+  if (workspace_bytes < ws.bytes) {
+    set_error("dense_fwd: workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
+    return EBK_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = d->N, K = d->K, U = d->U;
+  const long n = (long)N * U;
+  const Dropout none = make_dropout(false, 0.f, 0);
+  const Dropout drop = make_dropout(training != 0, d->dropout, seed);
+  const bool tc = d->math != EBK_MATH_FP32;
+  const bool x3 = d->math == EBK_MATH_TF32X3;
+  GemmOperandA ax{x, K, false, nullptr, 0, none, 0};
+  const bool pk = tc && !x3 && gemm_tf32_eligible(ax, W, U, N, U, K);
+  float* a = d->bn ? ws.a : y;  // without BN the activation IS the output
+  if (pk) {
+    EBK_TRY(gemm_tf32_pack_b(ws.w_f, nullptr, W, U, false, U, K, st));
+    EBK_TRY(gemm_tf32_pack_b(ws.w_d, nullptr, W, U, true, K, U, st));
+  }
+  EBK_TRY(gemm_dispatch(d->math, ax, pk ? ws.w_f : W, U, false, a, U, N, U, K, 0.0f, st, pk ? GEMM_B_PACKED : GEMM_B_RAW));
+  bias_act_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(a),
+                                                                   reinterpret_cast<const float4*>(b), n / 4, U / 4, d->relu);
+  EBK_LAUNCH_CHECK();
+  if (!d->bn) return EBK_OK;
+  if (training) {
+    const int nblk = ceil_div(N, ROWS_PER_BLK);
+    col_stats_partial_kernel<<<dim3(ceil_div(U, 128), nblk), 128, 0, st>>>(a, N, U, ws.partial);
+    EBK_LAUNCH_CHECK();
+    col_stats_final_kernel<<<ceil_div(U, 128), 128, 0, st>>>(ws.partial, nblk, N, U, d->bn_eps, d->bn_momentum, ws.mean,
+                                                             ws.invstd, mov_mean, mov_var);
+    EBK_LAUNCH_CHECK();
+  } else {
+    inference_stats_kernel<<<ceil_div(U, 128), 128, 0, st>>>(U, d->bn_eps, mov_mean, mov_var, ws.mean, ws.invstd);
+    EBK_LAUNCH_CHECK();
+  }
+  bn_apply_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const float4*>(a), n / 4, U / 4, reinterpret_cast<const float4*>(ws.mean),
+      reinterpret_cast<const float4*>(ws.invstd), reinterpret_cast<const float4*>(gamma),
+      reinterpret_cast<const float4*>(beta), drop, reinterpret_cast<float4*>(y));
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+extern "C" int ebk_dense_bwd(const ebk_dense_desc* d, const float* x, const float* W, const float* gamma, const float* y,
+                             int training, uint64_t seed, void* workspace, size_t workspace_bytes, const float* dy,
+                             float l2_grad_scale, float* dW, float* db, float* dgamma, float* dbeta, float* dx,
+                             void* stream) {
+  EBK_TRY(check_dense(d));
+  if (d->N == 0) return EBK_OK;
+  EBK_CHECK_ARG(x && W && dy && dW && db && workspace, "dense_bwd: null pointer");
+  EBK_CHECK_ARG(!d->bn || (gamma && dgamma && dbeta), "dense_bwd: BatchNorm needs gamma/dgamma/dbeta");
+  EBK_CHECK_ARG(d->bn || y, "dense_bwd: the layer output y is needed when there is no BatchNorm");
+  EBK_CHECK_ARG(!d->bn || training, "dense_bwd: BatchNorm backward is defined for training mode");
+  DenseWs ws = dense_layout(*d, workspace);
+  if (workspace_bytes < ws.bytes) {
+    set_error("dense_bwd: workspace %zu < %zu bytes", workspace_bytes, ws.bytes);
+    return EBK_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = d->N, K = d->K, U = d->U;
+  const long n = (long)N * U;
+  const Dropout none = make_dropout(false, 0.f, 0);
+  const Dropout drop = make_dropout(training != 0, d->dropout, seed);
+  const bool tc = d->math != EBK_MATH_FP32;
+  const bool x3 = d->math == EBK_MATH_TF32X3;
+  const bool rnd = tc && !x3;
+  if (d->bn) {
+    const int nblk = ceil_div(N, ROWS_PER_BLK);
+    bn_bwd_partial_kernel<<<dim3(ceil_div(U, 128), nblk), 128, 0, st>>>(dy, ws.a, N, U, ws.mean, ws.invstd, drop, ws.partial);
+    EBK_LAUNCH_CHECK();
+    bn_bwd_final_kernel<<<ceil_div(U, 128), 128, 0, st>>>(ws.partial, nblk, U, ws.sums, dgamma, dbeta);
+    EBK_LAUNCH_CHECK();
+    bn_bwd_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dy, ws.a, n, N, U, ws.mean, ws.invstd, gamma, ws.sums,
+                                                                     drop, d->relu, rnd ? 1 : 0, ws.dz);
+    EBK_LAUNCH_CHECK();
+  } else {
+    act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dy, y, n, drop, d->relu, rnd ? 1 : 0, ws.dz);
+    EBK_LAUNCH_CHECK();
+  }
+  EBK_TRY(colsum_accum_ws(N, U, ws.dz, U, nullptr, db, ws.colsum, st));
+  // dW += x^T dz  (+ 2 l2 W)
+  GemmOperandA axT{x, K, true, nullptr, 0, none, 0};
+  EBK_TRY(gemm_dispatch(d->math, axT, ws.dz, U, false, dW, U, K, U, N, 1.0f, st, rnd ? GEMM_B_ROUNDED : GEMM_B_RAW));
+  if (d->l2 > 0.f && l2_grad_scale != 0.f) {
+    const long nw = (long)K * U;
+    axpy_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(dW, W, nw, 2.0f * d->l2 * l2_grad_scale);
+    EBK_LAUNCH_CHECK();
+  }
+  if (dx) {
+    GemmOperandA adz{ws.dz, U, false, nullptr, 0, none, 0};
+    GemmOperandA ax{x, K, false, nullptr, 0, none, 0};
+    const bool pk = rnd && gemm_tf32_eligible(ax, W, U, N, U, K) && gemm_tf32_eligible(adz, W, U, N, K, U);
+    EBK_TRY(gemm_dispatch(d->math, adz, pk ? ws.w_d : W, U, true, dx, K, N, K, U, 0.0f, st, pk ? GEMM_B_PACKED : GEMM_B_RAW));
+  }
+  return EBK_OK;
+}
+
+extern "C" int ebk_sumsq_accum(const float* x, size_t n, float scale, float* out, void* stream) {
+  if (n == 0) return EBK_OK;
+  EBK_CHECK_ARG(x && out, "sumsq: null pointer");
+  sumsq_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(x, (long)n, scale, out);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}

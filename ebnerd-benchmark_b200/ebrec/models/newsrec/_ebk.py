@@ -24,6 +24,7 @@ SYMBOLS = [
     "ebk_last_error", "ebk_version", "ebk_device_ok",
     "ebk_seqenc_workspace_bytes", "ebk_seqenc_fwd", "ebk_seqenc_bwd",
     "ebk_score_softmax_ce", "ebk_score_sigmoid", "ebk_adam_keras_step",
+    "ebk_dense_workspace_bytes", "ebk_dense_fwd", "ebk_dense_bwd", "ebk_sumsq_accum",
     "ebk_launch_count", "ebk_prof_enable", "ebk_prof_num_tags", "ebk_prof_tag_name", "ebk_prof_collect",
     "ebk_gemm", "ebk_attention_core_fwd", "ebk_attention_core_bwd", "ebk_dropout_mask",
 ]
@@ -38,6 +39,15 @@ class SeqEncDesc(C.Structure):
     _fields_ = [
         ("n_seq", C.c_int32), ("L", C.c_int32), ("Din", C.c_int32), ("nh", C.c_int32),
         ("dh", C.c_int32), ("att", C.c_int32), ("V", C.c_int32), ("dropout", C.c_float),
+        ("math", C.c_int32),
+    ]
+
+
+class DenseDesc(C.Structure):
+    """Mirror of ebk_dense_desc (include/ebk.h)."""
+    _fields_ = [
+        ("N", C.c_int32), ("K", C.c_int32), ("U", C.c_int32), ("relu", C.c_int32), ("bn", C.c_int32),
+        ("bn_momentum", C.c_float), ("bn_eps", C.c_float), ("dropout", C.c_float), ("l2", C.c_float),
         ("math", C.c_int32),
     ]
 
@@ -66,6 +76,12 @@ def lib() -> C.CDLL:
     l.ebk_seqenc_fwd.argtypes = [dp, vp, vp, vp, vp, vp, vp, C.c_int, u64, u64, vp, sz, vp, vp]
     l.ebk_seqenc_bwd.argtypes = [dp, vp, vp, vp, vp, vp, vp, C.c_int, u64, u64, vp, sz, vp,
                                  vp, vp, vp, vp, vp, vp, vp]
+    ddp = C.POINTER(DenseDesc)
+    l.ebk_dense_workspace_bytes.restype = sz
+    l.ebk_dense_workspace_bytes.argtypes = [ddp]
+    l.ebk_dense_fwd.argtypes = [ddp, vp, vp, vp, vp, vp, vp, vp, C.c_int, u64, vp, sz, vp, vp]
+    l.ebk_dense_bwd.argtypes = [ddp, vp, vp, vp, vp, C.c_int, u64, vp, sz, vp, f32, vp, vp, vp, vp, vp, vp]
+    l.ebk_sumsq_accum.argtypes = [vp, sz, f32, vp, vp]
     l.ebk_score_softmax_ce.argtypes = [i32, i32, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp]
     l.ebk_score_sigmoid.argtypes = [i32, i32, i32, vp, vp, vp, vp]
     l.ebk_adam_keras_step.argtypes = [vp, vp, vp, vp, sz, f32, f64, f64, f32, C.c_int, vp]
@@ -75,7 +91,7 @@ def lib() -> C.CDLL:
     l.ebk_dropout_mask.argtypes = [u64, f32, sz, vp, vp]
     for name in SYMBOLS:
         fn = getattr(l, name)
-        if name not in ("ebk_last_error", "ebk_seqenc_workspace_bytes"):
+        if name not in ("ebk_last_error", "ebk_seqenc_workspace_bytes", "ebk_dense_workspace_bytes"):
             fn.restype = C.c_int
     l.ebk_launch_count.restype = C.c_longlong
     l.ebk_prof_tag_name.restype = C.c_char_p

@@ -94,6 +94,38 @@ int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, const float* ta
                    float* d_table, float* d_x, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Dense(+ReLU) -> [BatchNormalization] -> [Dropout] layer of the NRMSDocVec news encoder
+ * (nrms_docvec.py:118-130: Dense(units, relu, l2) + BatchNormalization() + Dropout(p); :130 the
+ * output Dense(D, relu) is the same call with bn = 0, dropout = 0).
+ *   x [N, K], W [K, U], b [U], gamma/beta/mov_mean/mov_var [U], y [N, U]
+ *   training != 0: batch statistics over the N rows of THIS call (biased variance) and the Keras
+ *   moving-average update mov = mov*momentum + batch*(1-momentum) written to mov_mean/mov_var;
+ *   training == 0: moving statistics, no dropout.
+ * Backward ACCUMULATES dW, db, dgamma, dbeta; dW also receives 2*l2*l2_grad_scale*W; dx (nullable) is
+ * overwritten.  `y` (the forward output) is only read when bn == 0.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t N, K, U;        /* rows, input width, units (K, U multiples of 4) */
+  int32_t relu;           /* 1: relu after the bias */
+  int32_t bn;             /* 1: BatchNormalization after the activation */
+  float bn_momentum;      /* Keras default 0.99 */
+  float bn_eps;           /* Keras default 1e-3 */
+  float dropout;          /* after BN; training only */
+  float l2;               /* kernel_regularizer l2 factor (nrms_docvec.py:122-124) */
+  int32_t math;           /* ebk_math */
+} ebk_dense_desc;
+
+size_t ebk_dense_workspace_bytes(const ebk_dense_desc* d);
+int ebk_dense_fwd(const ebk_dense_desc* d, const float* x, const float* W, const float* b, const float* gamma,
+                  const float* beta, float* mov_mean, float* mov_var, int training, uint64_t seed,
+                  void* workspace, size_t workspace_bytes, float* y, void* stream);
+int ebk_dense_bwd(const ebk_dense_desc* d, const float* x, const float* W, const float* gamma, const float* y,
+                  int training, uint64_t seed, void* workspace, size_t workspace_bytes, const float* dy,
+                  float l2_grad_scale, float* dW, float* db, float* dgamma, float* dbeta, float* dx, void* stream);
+/* out[0] += scale * sum_i x[i]^2   (the l2 kernel-regulariser term of the loss) */
+int ebk_sumsq_accum(const float* x, size_t n, float scale, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Click score + loss.  Replaces Dot(axes=-1) + Activation("softmax") +
  * categorical_crossentropy (nrms.py:201-202, 61-62) and its gradient.
  *   news [B, C, D], user [B, D], labels [B, C] fp32 (one-hot)
