@@ -35,9 +35,11 @@ cudaEvent_t prof_event() {
 }
 const char* kTagNames[T_NUM_TAGS] = {"qkv_gemm_fwd", "attn_core_fwd", "att_gemm_fwd", "attpool_fwd", "attpool_bwd",
                                      "colsum", "att_wgrad_gemm", "att_dgrad_gemm", "attn_core_bwd", "qkv_wgrad_gemm",
-                                     "qkv_dgrad_gemm", "embed_scatter", "score_ce", "adam"};
+                                     "qkv_dgrad_gemm", "embed_scatter", "score_ce", "adam", "embed_pad",
+                                     "conv_gemm_fwd", "conv_dz", "conv_wgrad_gemm", "conv_dgrad_gemm", "catview"};
 }  // namespace
 bool prof_on() { return g_prof; }
+void prof_set_group(int g) { g_prof_user = g; }
 void prof_begin(int tag, cudaStream_t st) {
   ProfRec r{tag, g_prof_user, prof_event(), prof_event()};
   cudaEventRecord(r.a, st);

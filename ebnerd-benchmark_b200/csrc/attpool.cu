@@ -15,7 +15,8 @@ __global__ void __launch_bounds__(PT) attpool_fwd_kernel(int L, int D, int att, 
                                                           Dropout drop, float* __restrict__ hbuf,
                                                           const float* __restrict__ attb,
                                                           const float* __restrict__ attq,
-                                                          float* __restrict__ w, float* __restrict__ out) {
+                                                          float* __restrict__ w, float* __restrict__ out,
+                                                          int out_ld) {
   __shared__ float a_s[64];
   __shared__ float w_s[64];
   const int n = blockIdx.x;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(PT) attpool_fwd_kernel(int L, int D, int att, 
       if (drop.on()) x *= drop.factor((uint64_t)r * (uint64_t)D + (uint64_t)d);
       acc = fmaf(w_s[t], x, acc);
     }
-    out[(long)n * D + d] = acc;
+    out[(long)n * out_ld + d] = acc;
   }
 }
 
@@ -67,14 +68,14 @@ __global__ void __launch_bounds__(PT) attpool_bwd_kernel(int L, int D, int att, 
                                                           Dropout drop, const float* __restrict__ hbuf,
                                                           const float* __restrict__ attq,
                                                           const float* __restrict__ w,
-                                                          const float* __restrict__ d_out,
+                                                          const float* __restrict__ d_out, int dout_ld,
                                                           float* __restrict__ da, float* __restrict__ dpre,
                                                           float* __restrict__ dy, bool round_dpre) {
   __shared__ float dw_s[64];
   __shared__ float da_s[64];
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = PT / 32;
-  const float* g = d_out + (long)n * D;
+  const float* g = d_out + (long)n * dout_ld;
   for (int t = warp; t < L; t += nwarp) {
     long r = (long)n * L + t;
     float wt = w[r];
@@ -174,20 +175,21 @@ __global__ void scatter_rows_add_kernel(int R, int E4, int V, const int32_t* __r
 }  // namespace
 
 int attpool_fwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, float* hbuf, const float* attb,
-                const float* attq, float* w, float* out, cudaStream_t st) {
+                const float* attq, float* w, float* out, cudaStream_t st, int out_ld) {
   if (n_seq <= 0) return EBK_OK;
   EBK_CHECK_ARG(L <= 64, "attpool: L=%d > 64", L);
-  attpool_fwd_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, drop, hbuf, attb, attq, w, out);
+  attpool_fwd_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, drop, hbuf, attb, attq, w, out, out_ld > 0 ? out_ld : D);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }
 
 int attpool_bwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, const float* hbuf,
                 const float* attq, const float* w, const float* d_out, float* da, float* dpre, float* dy,
-                bool round_dpre, cudaStream_t st) {
+                bool round_dpre, cudaStream_t st, int dout_ld) {
   if (n_seq <= 0) return EBK_OK;
   EBK_CHECK_ARG(L <= 64, "attpool: L=%d > 64", L);
-  attpool_bwd_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, drop, hbuf, attq, w, d_out, da, dpre, dy, round_dpre);
+  attpool_bwd_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, drop, hbuf, attq, w, d_out, dout_ld > 0 ? dout_ld : D, da, dpre, dy,
+                                           round_dpre);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

@@ -192,6 +192,21 @@ int check_dense(const ebk_dense_desc* d) {
 }
 
 }  // namespace
+
+// launchers shared with naml.cu
+int bias_act(float* z, const float* b, long n, int U, int relu, cudaStream_t st) {
+  if (n == 0) return EBK_OK;
+  bias_act_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(z),
+                                                                   reinterpret_cast<const float4*>(b), n / 4, U / 4, relu);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+int act_bwd(const float* dy, const float* y, long n, Dropout drop, int relu, int round_out, float* dz, cudaStream_t st) {
+  if (n == 0) return EBK_OK;
+  act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dy, y, n, drop, relu, round_out, dz);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
 }  // namespace ebk
 
 using namespace ebk;

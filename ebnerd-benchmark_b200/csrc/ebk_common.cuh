@@ -47,8 +47,11 @@ void note_launch();
 // ---- optional per-kernel profiling (CUDA events on the launching stream) ------------------
 enum ProfTag {
   T_QKV_FWD = 0, T_ATTN_FWD, T_ATT_GEMM_FWD, T_POOL_FWD, T_POOL_BWD, T_COLSUM, T_ATT_WGRAD, T_ATT_DGRAD,
-  T_ATTN_BWD, T_QKV_WGRAD, T_QKV_DGRAD, T_SCATTER, T_SCORE, T_ADAM, T_NUM_TAGS
+  T_ATTN_BWD, T_QKV_WGRAD, T_QKV_DGRAD, T_SCATTER, T_SCORE, T_ADAM,
+  T_EMBED_PAD, T_CONV_FWD, T_CONV_DZ, T_CONV_WGRAD, T_CONV_DGRAD, T_CATVIEW, T_NUM_TAGS
 };
+// profiler group of the following launches: 0 = "news." slots, 1 = "user." slots
+void prof_set_group(int g);
 bool prof_on();
 void prof_begin(int tag, cudaStream_t st);
 void prof_end(int tag, cudaStream_t st);
@@ -200,15 +203,21 @@ int attention_core_bwd_mma(int n_seq, int L, int nh, int dh, const float* qkv, c
 
 // AttLayer2 pieces
 int attpool_fwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, float* hbuf /*[R,att] in: pre-act, out: tanh*/,
-                const float* attb, const float* attq, float* w /*[R]*/, float* out /*[n_seq,D]*/, cudaStream_t st);
+                const float* attb, const float* attq, float* w /*[R]*/, float* out /*[n_seq,out_ld]*/, cudaStream_t st,
+                int out_ld = 0 /*0 => D*/);
 int attpool_bwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, const float* hbuf,
                 const float* attq, const float* w, const float* d_out, float* da /*[R]*/,
-                float* dpre /*[R,att]*/, float* dy /*[R,D] = w_t*d_out*/, bool round_dpre, cudaStream_t st);
+                float* dpre /*[R,att]*/, float* dy /*[R,D] = w_t*d_out*/, bool round_dpre, cudaStream_t st,
+                int dout_ld = 0 /*0 => D*/);
 // column sums: out[j] += sum_r coef[r] * X[r,j]   (coef may be NULL => 1); deterministic
 // two-stage reduction through `partial` (colsum_partial_floats(R, Ncols) floats of scratch)
 int colsum_accum_ws(int R, int Ncols, const float* X, int ldx, const float* coef, float* out, float* partial,
                     cudaStream_t st);
 size_t colsum_partial_floats(int R, int Ncols);
+
+// z = act(z + b) in place (n = rows*U elements, U % 4 == 0);  dz = dy * dropout' * relu'(y)
+int bias_act(float* z, const float* b, long n, int U, int relu, cudaStream_t st);
+int act_bwd(const float* dy, const float* y, long n, Dropout drop, int relu, int round_out, float* dz, cudaStream_t st);
 
 // d_table[tok[r], :] += dX[r, :] * dropout(r*E + e)
 int scatter_rows_add(int R, int E, int V, const int32_t* tok, const float* dX, Dropout drop,

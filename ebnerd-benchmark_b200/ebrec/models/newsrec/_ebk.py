@@ -25,6 +25,9 @@ SYMBOLS = [
     "ebk_seqenc_workspace_bytes", "ebk_seqenc_fwd", "ebk_seqenc_bwd",
     "ebk_score_softmax_ce", "ebk_score_sigmoid", "ebk_adam_keras_step",
     "ebk_dense_workspace_bytes", "ebk_dense_fwd", "ebk_dense_bwd", "ebk_sumsq_accum",
+    "ebk_attlayer_workspace_bytes", "ebk_attlayer_fwd", "ebk_attlayer_bwd",
+    "ebk_conv1d_workspace_bytes", "ebk_conv1d_fwd", "ebk_conv1d_bwd",
+    "ebk_catview_workspace_bytes", "ebk_catview_fwd", "ebk_catview_bwd",
     "ebk_launch_count", "ebk_prof_enable", "ebk_prof_num_tags", "ebk_prof_tag_name", "ebk_prof_collect",
     "ebk_gemm", "ebk_attention_core_fwd", "ebk_attention_core_bwd", "ebk_dropout_mask",
 ]
@@ -50,6 +53,18 @@ class DenseDesc(C.Structure):
         ("bn_momentum", C.c_float), ("bn_eps", C.c_float), ("dropout", C.c_float), ("l2", C.c_float),
         ("math", C.c_int32),
     ]
+
+
+class AttLayerDesc(C.Structure):
+    """Mirror of ebk_attlayer_desc (include/ebk.h)."""
+    _fields_ = [("n_seq", C.c_int32), ("L", C.c_int32), ("D", C.c_int32), ("att", C.c_int32),
+                ("dropout", C.c_float), ("math", C.c_int32)]
+
+
+class Conv1dDesc(C.Structure):
+    """Mirror of ebk_conv1d_desc (include/ebk.h)."""
+    _fields_ = [("n_seq", C.c_int32), ("L", C.c_int32), ("E", C.c_int32), ("F", C.c_int32), ("window", C.c_int32),
+                ("V", C.c_int32), ("dropout", C.c_float), ("relu", C.c_int32), ("math", C.c_int32)]
 
 
 _lib = None
@@ -82,6 +97,19 @@ def lib() -> C.CDLL:
     l.ebk_dense_fwd.argtypes = [ddp, vp, vp, vp, vp, vp, vp, vp, C.c_int, u64, vp, sz, vp, vp]
     l.ebk_dense_bwd.argtypes = [ddp, vp, vp, vp, vp, C.c_int, u64, vp, sz, vp, f32, vp, vp, vp, vp, vp, vp]
     l.ebk_sumsq_accum.argtypes = [vp, sz, f32, vp, vp]
+    adp, cdp = C.POINTER(AttLayerDesc), C.POINTER(Conv1dDesc)
+    l.ebk_attlayer_workspace_bytes.restype = sz
+    l.ebk_attlayer_workspace_bytes.argtypes = [adp]
+    l.ebk_attlayer_fwd.argtypes = [adp, vp, vp, vp, vp, C.c_int, u64, vp, sz, vp, i32, vp]
+    l.ebk_attlayer_bwd.argtypes = [adp, vp, vp, vp, C.c_int, u64, vp, sz, vp, i32, vp, vp, vp, vp, vp]
+    l.ebk_conv1d_workspace_bytes.restype = sz
+    l.ebk_conv1d_workspace_bytes.argtypes = [cdp]
+    l.ebk_conv1d_fwd.argtypes = [cdp, vp, vp, vp, vp, C.c_int, u64, vp, sz, vp, vp]
+    l.ebk_conv1d_bwd.argtypes = [cdp, vp, vp, vp, C.c_int, u64, u64, vp, sz, vp, vp, vp, vp, vp]
+    l.ebk_catview_workspace_bytes.restype = sz
+    l.ebk_catview_workspace_bytes.argtypes = [i32, i32]
+    l.ebk_catview_fwd.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp, i32, vp]
+    l.ebk_catview_bwd.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp, i32, vp, vp, vp, vp]
     l.ebk_score_softmax_ce.argtypes = [i32, i32, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp]
     l.ebk_score_sigmoid.argtypes = [i32, i32, i32, vp, vp, vp, vp]
     l.ebk_adam_keras_step.argtypes = [vp, vp, vp, vp, sz, f32, f64, f64, f32, C.c_int, vp]
@@ -91,7 +119,7 @@ def lib() -> C.CDLL:
     l.ebk_dropout_mask.argtypes = [u64, f32, sz, vp, vp]
     for name in SYMBOLS:
         fn = getattr(l, name)
-        if name not in ("ebk_last_error", "ebk_seqenc_workspace_bytes", "ebk_dense_workspace_bytes"):
+        if name != "ebk_last_error" and not name.endswith("_workspace_bytes"):
             fn.restype = C.c_int
     l.ebk_launch_count.restype = C.c_longlong
     l.ebk_prof_tag_name.restype = C.c_char_p

@@ -126,6 +126,75 @@ int ebk_dense_bwd(const ebk_dense_desc* d, const float* x, const float* W, const
 int ebk_sumsq_accum(const float* x, size_t n, float scale, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * AttLayer2 on its own (layers.py:7-104; call 55-81) with an optional Dropout on its input:
+ * the NAML title/body pooling (naml.py:167-168, 198-199), the 4-view fusion (naml.py:133-138) and the
+ * NAML user encoder (naml.py:79-84).
+ *   x [n_seq*L, D], W [D, att], b [att], q [att]; out row n is written at out + n*out_ld (out_ld >= D,
+ *   so several views can fill one [n_seq, 4, D] buffer).  L <= 64.
+ *   training != 0 and dropout > 0: x is masked on read with the counter-based mask (element r*D + d).
+ * Backward ACCUMULATES dW, db, dq and OVERWRITES dx [n_seq*L, D] with the gradient w.r.t. the MASKED
+ * input dropout(x); the layer that produced x applies the same mask (ebk_conv1d_bwd: seed_out).
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_seq, L, D, att;
+  float dropout;
+  int32_t math; /* ebk_math */
+} ebk_attlayer_desc;
+
+size_t ebk_attlayer_workspace_bytes(const ebk_attlayer_desc* d);
+int ebk_attlayer_fwd(const ebk_attlayer_desc* d, const float* x, const float* W, const float* b, const float* q,
+                     int training, uint64_t seed, void* workspace, size_t workspace_bytes, float* out,
+                     int32_t out_ld, void* stream);
+int ebk_attlayer_bwd(const ebk_attlayer_desc* d, const float* x, const float* W, const float* q, int training,
+                     uint64_t seed, void* workspace, size_t workspace_bytes, const float* d_out, int32_t d_out_ld,
+                     float* dW, float* db, float* dq, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * NAML text view up to the pooling: Embedding -> Dropout -> Conv1D(F, window, padding="same",
+ * activation) (naml.py:155-166 title, 186-197 body; table shared, naml.py:318-323).
+ *   tok [n_seq, L] int32 (ids outside [0,V) -> zero row, no gradient), table [V, E],
+ *   Wc [window*E, F] = the Keras kernel [window, E, F] flattened, bc [F],
+ *   y [n_seq*L, F] = act(conv + bc)  -- BEFORE the output Dropout of naml.py:167/198, which the
+ *   consumer (ebk_attlayer_*) applies on read with seed_out.
+ *   "same" padding: (window-1)/2 zero rows on the left, the rest on the right (TF convention).
+ * The conv is ONE tensor-core GEMM with K = window*E over a zero-padded copy of the dropped embeddings
+ * (rows of one article are contiguous, so a window is a contiguous K-slice).
+ * Backward: dy [n_seq*L, F] = gradient w.r.t. dropout_out(y) (unmasked, from ebk_attlayer_bwd);
+ * ACCUMULATES dWc, dbc and scatter-adds the embedding gradient into d_table [V, E] (nullable).
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_seq, L, E, F, window, V; /* E, F multiples of 4 */
+  float dropout;                     /* rate of both Dropout layers; training only */
+  int32_t relu;                      /* cnn_activation == "relu" */
+  int32_t math;                      /* ebk_math */
+} ebk_conv1d_desc;
+
+size_t ebk_conv1d_workspace_bytes(const ebk_conv1d_desc* d);
+int ebk_conv1d_fwd(const ebk_conv1d_desc* d, const int32_t* tok, const float* table, const float* Wc,
+                   const float* bc, int training, uint64_t seed_in, void* workspace, size_t workspace_bytes,
+                   float* y, void* stream);
+int ebk_conv1d_bwd(const ebk_conv1d_desc* d, const int32_t* tok, const float* Wc, const float* y, int training,
+                   uint64_t seed_in, uint64_t seed_out, void* workspace, size_t workspace_bytes, const float* dy,
+                   float* dWc, float* dbc, float* d_table, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * NAML categorical view: Embedding(n_cat, dim) -> Dense(F, activation) (naml.py:205-252).
+ * Only n_cat distinct inputs exist, so the layer is evaluated once per category
+ * (T = act(emb W + b), [n_cat+1, F]; row n_cat = act(b) serves ids outside [0, n_cat)) and gathered;
+ * the backward segment-sums the row gradients per category first.
+ *   ids [N] int32, emb [n_cat, dim], W [dim, F], b [F]; out row n at out + n*out_ld.
+ *   workspace: ebk_catview_workspace_bytes(n_cat, F); backward needs the forward's workspace.
+ * Backward ACCUMULATES d_emb, dW, db.
+ * ---------------------------------------------------------------------------------- */
+size_t ebk_catview_workspace_bytes(int32_t n_cat, int32_t F);
+int ebk_catview_fwd(int32_t N, int32_t n_cat, int32_t dim, int32_t F, int32_t relu, const int32_t* ids,
+                    const float* emb, const float* W, const float* b, void* workspace, size_t workspace_bytes,
+                    float* out, int32_t out_ld, void* stream);
+int ebk_catview_bwd(int32_t N, int32_t n_cat, int32_t dim, int32_t F, int32_t relu, const int32_t* ids,
+                    const float* emb, const float* W, void* workspace, size_t workspace_bytes, const float* d_out,
+                    int32_t d_out_ld, float* d_emb, float* dW, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Click score + loss.  Replaces Dot(axes=-1) + Activation("softmax") +
  * categorical_crossentropy (nrms.py:201-202, 61-62) and its gradient.
  *   news [B, C, D], user [B, D], labels [B, C] fp32 (one-hot)
