@@ -315,6 +315,13 @@ extern "C" int ebk_gemm(int32_t math, int32_t transA, int32_t transB, int32_t M,
   return gemm_dispatch(math, a, B, ldb, transB != 0, C, ldc, M, N, K, beta, (cudaStream_t)stream);
 }
 
+extern "C" int ebk_gemm_tma(int32_t transA, int32_t transB, int32_t tall, int32_t M, int32_t N, int32_t K,
+                            const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
+                            float beta, float alpha, void* stream) {
+  EBK_CHECK_ARG(M >= 0 && N >= 0 && K >= 1 && A && B && C, "gemm_tma: bad argument");
+  return gemm_tma(A, lda, transA != 0, B, ldb, transB != 0, C, ldc, M, N, K, beta, alpha, (cudaStream_t)stream, tall);
+}
+
 extern "C" int ebk_attention_core_fwd(int32_t n_seq, int32_t L, int32_t nh, int32_t dh, const float* qkv,
                                       float* y, void* stream) {
   EBK_CHECK_ARG(qkv && y, "attention_core_fwd: null pointer");

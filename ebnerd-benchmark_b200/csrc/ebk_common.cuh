@@ -182,6 +182,11 @@ int gemm_tf32_pack_b(float* dst_hi, float* dst_lo, const float* B, int ldb, bool
 int gemm_dispatch(int math, const GemmOperandA& A, const float* B, int ldb, bool transB, float* C,
                   int ldc, int M, int N, int K, float beta, cudaStream_t st, int b_mode = GEMM_B_RAW,
                   const float* B_lo = nullptr);
+// All-TMA tcgen05 GEMM on dense operands that already hold tf32-representable values (gemm_tma_sm100.cu):
+// C (+)= alpha * opA(A) . opB(B); beta in {0,1}; tall: 256-row tiles (halves the L2 traffic of B)
+bool gemm_tma_eligible(const float* A, int lda, const float* B, int ldb, int M, int N, int K);
+int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool transB, float* C, int ldc, int M,
+             int N, int K, float beta, float alpha, cudaStream_t st, int tall = 0);
 // hi[i] = tf32(src[i]) (round to nearest), lo[i] = src[i] - hi[i]
 int split_tf32_copy(float* hi, float* lo, const float* src, size_t n, cudaStream_t st);
 // dst[i] = round-to-nearest-tf32(src[i])  (so that the tensor core's truncation is exact)

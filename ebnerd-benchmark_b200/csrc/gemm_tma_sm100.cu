@@ -1,0 +1,550 @@
+// All-TMA tcgen05 TF32 GEMM for sm_100a (the TRAINING hot path):
+//   C[M,N] (+)= alpha * opA(A)[M,K] . opB(B)[K,N],  fp32 storage, tf32 tensor cores, fp32 accumulate in TMEM.
+//
+// Why a second GEMM next to gemm_tf32_sm100.cu: ncu showed the register-path GEMM (gather + dropout hash
+// + rounding in 16 producer warps) to be ISSUE-bound -- 4160 warp instructions per k-step against the
+// 1920 issue slots of the 480-cycle MMA window.  Here every operand is a dense fp32 matrix that the
+// layer before it already wrote masked and rounded to tf32 (embed_rows_kernel, attention / attpool
+// epilogues), so the operand feed needs no ALU work at all: ONE thread issues cp.async.bulk.tensor
+// (TMA) copies that land in shared memory in the UMMA swizzled layouts, one thread issues tcgen05.mma,
+// four warps drain the accumulators.  192 threads per CTA, persistent, one CTA per SM.
+//
+// Operand layouts in shared memory (per pipeline stage, BK = 32 fp32 = one 128-byte swizzle row):
+//   K-major  (A not transposed / B transposed: storage [mn, k], k contiguous)
+//            ONE 2-D box {32 k, rows}, CU_TENSOR_MAP_SWIZZLE_128B  -> rows x 128 B, UMMA SWIZZLE_128B,
+//            SBO = 1024 (8-row atoms), k-advance = +32 B per MMA.
+//   MN-major (A transposed / B not transposed: storage [k, mn], mn contiguous)
+//            one 2-D box {32 mn, 32 k} per group of 32 mn, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B -> 4 KB
+//            blocks [k][32 mn] = the only UMMA layout for 32-bit MN-major operands
+//            (SWIZZLE_128B_BASE32B: atoms of 4 k-rows x 128 B, 32-byte units XOR-swizzled by the k-row);
+//            blocks of consecutive mn groups follow each other: LBO = 4096, SBO = 512, k-advance = +1024 B.
+//   Out-of-range box elements are zero-filled by the TMA unit, so no tail code exists for M, N or K.
+//
+// MT = 1: 128 x BN tiles, double-buffered accumulator (2 x 256 TMEM columns): the epilogue of tile i
+//         overlaps the main loop of tile i+1.
+// MT = 2: 256 x BN tiles (two M=128 MMAs per k-step sharing the B tile, 2 x 256 TMEM columns, single
+//         buffered): halves the L2->SM traffic of the B operand; used where B is the re-read operand.
+#include <cuda.h>  // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
+
+#include <unordered_map>
+
+#include "ebk_common.cuh"
+
+namespace ebk {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;
+constexpr int UMMA_K = 8;
+constexpr int MAX_STAGES = 8;
+constexpr int THREADS = 192;       // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int EPI_THREADS = 128;
+constexpr int TMEM_COLS = 512;
+constexpr uint32_t SPIN_LIMIT = 1u << 27;
+
+struct TParams {
+  float* C; int ldc;
+  int M, N, K;
+  int BN;              // UMMA N of a tile (multiple of 16, <= 256)
+  int b_rows;          // B rows (K-major) or padded columns (MN-major, multiple of 32) staged per tile
+  int stages;
+  int tiles_m, tiles_n, splitk;
+  int ksteps_total, ksteps_per_split;
+  int out_mode;        // 0 store, 1 load-add-store (beta = 1), 2 red.add (split-K)
+  float alpha;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > SPIN_LIMIT) __trap();  // a protocol bug traps instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A,B=tf32 [7,10)=[10,13)=2,
+// a_major bit15, b_major bit16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29).
+__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn, int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= 2u << 7;
+  d |= 2u << 10;
+  d |= (a_mn ? 1u : 0u) << 15;
+  d |= (b_mn ? 1u : 0u) << 16;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(BM >> 4) << 24;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Walks this CTA's work items (m-tile, n-tile, k-split; n fastest so the CTAs that run at the same
+// time share the A rows in L2) k-step by k-step.
+template <int MT>
+struct Cursor {
+  int item, ks, ks_end, m0, n0;
+  __device__ __forceinline__ void load(const TParams& p) {
+    const int per_m = p.tiles_n * p.splitk;
+    const int tm = item / per_m, rem = item - tm * per_m;
+    const int tn = rem / p.splitk, sp = rem - tn * p.splitk;
+    m0 = tm * BM * MT;
+    n0 = tn * p.BN;
+    ks = sp * p.ksteps_per_split;
+    ks_end = min(p.ksteps_total, ks + p.ksteps_per_split);
+  }
+  __device__ __forceinline__ void init(const TParams& p, int first, int n_items) {
+    item = first;
+    ks = ks_end = m0 = n0 = 0;
+    if (item < n_items) load(p);
+  }
+  __device__ __forceinline__ bool valid(int n_items) const { return item < n_items; }
+  __device__ __forceinline__ bool advance(const TParams& p, int n_items, int stride) {  // true: item finished
+    if (++ks < ks_end) return false;
+    item += stride;
+    if (item < n_items) load(p);
+    return true;
+  }
+  __device__ __forceinline__ void next_item(const TParams& p, int n_items, int stride) {
+    item += stride;
+    if (item < n_items) load(p);
+  }
+};
+
+template <bool A_MN, bool B_MN, int MT>
+__global__ void __launch_bounds__(THREADS, 1)
+    gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  constexpr int NBUF = MT == 1 ? 2 : 1;  // accumulator buffers
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.stages;
+  const int BN = p.BN;
+  constexpr uint32_t a_bytes = (uint32_t)MT * BM * BK * 4;
+  const uint32_t b_bytes = (uint32_t)p.b_rows * BK * 4;          // multiple of 1024 (b_rows % 8 == 0)
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int n_items = p.tiles_m * p.tiles_n * p.splitk;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tfull_bar[b]), 1);
+      mbar_init(smem_u32(&tempty_bar[b]), EPI_THREADS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      Cursor<MT> cu;
+      cu.init(p, blockIdx.x, n_items);
+      int s = 0;
+      uint32_t ph = 0;
+      while (cu.valid(n_items)) {
+        const int k0 = cu.ks * BK;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        mbar_expect_tx(bar, stage_bytes);
+        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+        const uint32_t sb = sa + a_bytes;
+        if (!A_MN) {
+          tma_load_2d(sa, &tmA, k0, cu.m0, bar);                       // box {32 k, 128*MT rows}
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4 * MT; ++g) tma_load_2d(sa + (uint32_t)g * 4096u, &tmA, cu.m0 + 32 * g, k0, bar);
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &tmB, k0, cu.n0, bar);                       // box {32 k, b_rows rows}
+        } else {
+          const int groups = p.b_rows >> 5;
+          for (int g = 0; g < groups; ++g) tma_load_2d(sb + (uint32_t)g * 4096u, &tmB, cu.n0 + 32 * g, k0, bar);
+        }
+        cu.advance(p, n_items, gridDim.x);
+        if (++s == S) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(A_MN, B_MN, BN);
+      constexpr uint32_t a_lbo = A_MN ? 4096u : 16u, a_sbo = A_MN ? 512u : 1024u, a_lt = A_MN ? 1u : 2u;
+      constexpr uint32_t b_lbo = B_MN ? 4096u : 16u, b_sbo = B_MN ? 512u : 1024u, b_lt = B_MN ? 1u : 2u;
+      constexpr uint32_t a_kadv = A_MN ? 1024u : 32u, b_kadv = B_MN ? 1024u : 32u;  // bytes per UMMA_K
+      Cursor<MT> cu;
+      cu.init(p, blockIdx.x, n_items);
+      int t = 0, s = 0;
+      uint32_t ph = 0;
+      while (cu.valid(n_items)) {
+        const int buf = NBUF == 2 ? (t & 1) : 0, use = NBUF == 2 ? (t >> 1) : t;
+        mbar_wait_backoff(smem_u32(&tempty_bar[buf]), (uint32_t)((use & 1) ^ 1));  // epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t tacc = tmem + (NBUF == 2 ? (uint32_t)buf * 256u : 0u);
+        bool first = true, last = false;
+        while (!last) {
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t db = make_desc(sb + (uint32_t)k * b_kadv, b_lbo, b_sbo, b_lt);
+            const uint32_t acc = (first && k == 0) ? 0u : 1u;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint32_t a_addr = sa + (uint32_t)mt * (uint32_t)(BM * BK * 4) + (uint32_t)k * a_kadv;
+              umma_tf32(tacc + (uint32_t)mt * 256u, make_desc(a_addr, a_lbo, a_sbo, a_lt), db, idesc, acc);
+            }
+          }
+          umma_commit(smem_u32(&empty_bar[s]));  // frees the stage when these MMAs retire
+          first = false;
+          last = cu.advance(p, n_items, gridDim.x);
+          if (++s == S) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        umma_commit(smem_u32(&tfull_bar[buf]));  // accumulator(s) of this item complete
+        ++t;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2-5; TMEM lane quarter = warp & 3) =====================
+    const int ew = warp & 3;
+    Cursor<MT> cu;
+    cu.init(p, blockIdx.x, n_items);
+    int t = 0;
+    const float alpha = p.alpha;
+    const bool vec_base = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool vec8_base = vec_base && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 31) == 0) && p.out_mode == 0;
+    while (cu.valid(n_items)) {
+      const int buf = NBUF == 2 ? (t & 1) : 0, use = NBUF == 2 ? (t >> 1) : t;
+      const int n0 = cu.n0;
+      mbar_wait_backoff(smem_u32(&tfull_bar[buf]), (uint32_t)(use & 1));
+      tc_fence_after();
+      const bool vec_ok = vec_base && ((n0 & 3) == 0);
+      const bool vec8_ok = vec8_base && ((n0 & 7) == 0);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int row = cu.m0 + mt * BM + ew * 32 + lane;
+        const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (NBUF == 2 ? (uint32_t)buf * 256u : (uint32_t)mt * 256u);
+        float* crow = p.C + (long)row * p.ldc + n0;
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          if (n0 + c0 >= p.N) break;  // warp-uniform
+          float v[16];
+          tmem_ld16(tbase + (uint32_t)c0, v);  // warp-collective
+          if (row < p.M) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= alpha;
+            if (vec8_ok && n0 + c0 + 15 < p.N) {
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + c0), "f"(v[0]), "f"(v[1]),
+                           "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                           : "memory");
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + c0 + 8), "f"(v[8]),
+                           "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+                           : "memory");
+              continue;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int col = c0 + q * 4;
+              if (n0 + col >= p.N) break;
+              float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+              if (vec_ok && n0 + col + 3 < p.N) {
+                float4* dst = reinterpret_cast<float4*>(crow + col);
+                if (p.out_mode == 0) {
+                  *dst = o;
+                } else if (p.out_mode == 1) {
+                  float4 c = *dst;
+                  c.x += o.x; c.y += o.y; c.z += o.z; c.w += o.w;
+                  *dst = c;
+                } else {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y),
+                               "f"(o.z), "f"(o.w)
+                               : "memory");
+                }
+              } else {
+                const float oe[4] = {o.x, o.y, o.z, o.w};
+                for (int e = 0; e < 4; ++e) {
+                  if (n0 + col + e >= p.N) break;
+                  float* dst = crow + col + e;
+                  if (p.out_mode == 0) *dst = oe[e];
+                  else if (p.out_mode == 1) *dst += oe[e];
+                  else atomicAdd(dst, oe[e]);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tempty_bar[buf]));  // buffer may be overwritten by the MMA warp
+      cu.next_item(p, n_items, gridDim.x);
+      ++t;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+__global__ void zero_c_kernel(float* C, int ldc, int M, int N) {
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < (long)M * N) C[(i / N) * (long)ldc + (i % N)] = 0.0f;
+}
+
+// ---- host side: tensor maps --------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int inner, outer, ld, box_outer, mn;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_outer == o.box_outer && mn == o.mn;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&h](size_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+    mix((size_t)k.inner); mix((size_t)k.outer); mix((size_t)k.ld); mix((size_t)k.box_outer); mix((size_t)k.mn);
+    return h;
+  }
+};
+thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// 2-D map of a row-major fp32 matrix [outer, inner] (row stride ld floats); box {32, box_outer}.
+// mn = 1 selects the 32-byte-atom swizzle of MN-major 32-bit UMMA operands.
+int get_map(const float* ptr, int inner, int outer, int ld, int box_outer, bool mn, CUtensorMap* out) {
+  const MapKey key{ptr, inner, outer, ld, box_outer, mn ? 1 : 0};
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) {
+    *out = it->second;
+    return EBK_OK;
+  }
+  EncodeTiledFn enc = encode_fn();
+  if (enc == nullptr) {
+    set_error("gemm_tma: cuTensorMapEncodeTiled is not available from the driver");
+    return EBK_ERR_UNSUPPORTED;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4ull};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tma: cuTensorMapEncodeTiled failed (%d) for [%d x %d] ld %d box %d", (int)r, outer, inner, ld, box_outer);
+    return EBK_ERR_CUDA;
+  }
+  if (g_maps.size() > 512) g_maps.clear();
+  g_maps.emplace(key, m);
+  *out = m;
+  return EBK_OK;
+}
+
+int g_sms = 0;
+
+}  // namespace
+
+bool gemm_tma_eligible(const float* A, int lda, const float* B, int ldb, int M, int N, int K) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return al(A) && al(B) && (lda % 4 == 0) && (ldb % 4 == 0) && M >= 1 && N >= 1 && K >= 1 && encode_fn() != nullptr;
+}
+
+// Operands must already hold tf32-representable values (the tensor core truncates the low 13 mantissa
+// bits of whatever it is given).  transA: A is stored [K, M]; transB: B is stored [N, K].
+// tall != 0 selects 256-row tiles (MT = 2).
+int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool transB, float* C, int ldc, int M,
+             int N, int K, float beta, float alpha, cudaStream_t st, int tall) {
+  if (M <= 0 || N <= 0) return EBK_OK;
+  EBK_CHECK_ARG(A && B && C && K >= 1, "gemm_tma: null operand or K < 1");
+  EBK_CHECK_ARG(gemm_tma_eligible(A, lda, B, ldb, M, N, K), "gemm_tma: operands must be 16-byte aligned with ld %% 4 == 0");
+  EBK_CHECK_ARG(beta == 0.0f || beta == 1.0f, "gemm_tma: beta must be 0 or 1");
+  if (g_sms == 0) {
+    int dev = 0;
+    EBK_CUDA(cudaGetDevice(&dev));
+    EBK_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const bool a_mn = transA, b_mn = !transB;
+  const int MT = tall ? 2 : 1;
+  TParams p;
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.alpha = alpha;
+  const int ntn = ceil_div(N, 256);
+  p.BN = ceil_div(ceil_div(N, ntn), 16) * 16;
+  p.tiles_n = ceil_div(N, p.BN);
+  p.b_rows = b_mn ? ((p.BN + 31) & ~31) : p.BN;
+  p.tiles_m = ceil_div(M, BM * MT);
+  p.ksteps_total = ceil_div(K, BK);
+  const size_t stage_bytes = (size_t)MT * BM * BK * 4 + (size_t)p.b_rows * BK * 4;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const long tiles = (long)p.tiles_m * p.tiles_n;
+  int splitk = 1;
+  if (tiles < g_sms && p.ksteps_total >= 16) {
+    splitk = (int)(g_sms / tiles);  // fill the machine in ONE wave of equal items
+    const int maxsplit = p.ksteps_total / 8;
+    if (splitk > maxsplit) splitk = maxsplit;
+    if (splitk < 1) splitk = 1;
+  }
+  p.ksteps_per_split = ceil_div(p.ksteps_total, splitk);
+  splitk = ceil_div(p.ksteps_total, p.ksteps_per_split);
+  p.splitk = splitk;
+  p.out_mode = splitk > 1 ? 2 : (beta != 0.0f ? 1 : 0);
+  if (splitk > 1 && beta == 0.0f) {
+    const long n = (long)M * N;
+    zero_c_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(C, ldc, M, N);
+    EBK_LAUNCH_CHECK();
+  }
+  CUtensorMap tmA, tmB;
+  if (!a_mn) EBK_TRY(get_map(A, K, M, lda, BM * MT, false, &tmA));   // storage [M, K]
+  else       EBK_TRY(get_map(A, M, K, lda, 32, true, &tmA));         // storage [K, M]
+  if (!b_mn) EBK_TRY(get_map(B, K, N, ldb, p.b_rows, false, &tmB));  // storage [N, K]
+  else       EBK_TRY(get_map(B, N, K, ldb, 32, true, &tmB));         // storage [K, N]
+  const long n_items = tiles * splitk;
+  const int grid = (int)(n_items < g_sms ? n_items : g_sms);
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+#define LAUNCH3(AMN_, BMN_, MT_)                                                                               \
+  {                                                                                                            \
+    EBK_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<AMN_, BMN_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smem));                                                                 \
+    gemm_tma_kernel<AMN_, BMN_, MT_><<<grid, THREADS, smem, st>>>(tmA, tmB, p);                                \
+  }
+#define LAUNCH2(AMN_, BMN_)                  \
+  {                                          \
+    if (MT == 2) LAUNCH3(AMN_, BMN_, 2)      \
+    else LAUNCH3(AMN_, BMN_, 1)              \
+  }
+  if (!a_mn && !b_mn) LAUNCH2(false, false)
+  else if (!a_mn && b_mn) LAUNCH2(false, true)
+  else if (a_mn && !b_mn) LAUNCH2(true, false)
+  else LAUNCH2(true, true)
+#undef LAUNCH2
+#undef LAUNCH3
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+}  // namespace ebk

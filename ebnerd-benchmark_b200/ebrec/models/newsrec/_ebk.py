@@ -29,7 +29,7 @@ SYMBOLS = [
     "ebk_conv1d_workspace_bytes", "ebk_conv1d_fwd", "ebk_conv1d_bwd",
     "ebk_catview_workspace_bytes", "ebk_catview_fwd", "ebk_catview_bwd",
     "ebk_launch_count", "ebk_prof_enable", "ebk_prof_num_tags", "ebk_prof_tag_name", "ebk_prof_collect",
-    "ebk_gemm", "ebk_attention_core_fwd", "ebk_attention_core_bwd", "ebk_dropout_mask",
+    "ebk_gemm", "ebk_gemm_tma", "ebk_attention_core_fwd", "ebk_attention_core_bwd", "ebk_dropout_mask",
 ]
 
 
@@ -114,6 +114,7 @@ def lib() -> C.CDLL:
     l.ebk_score_sigmoid.argtypes = [i32, i32, i32, vp, vp, vp, vp]
     l.ebk_adam_keras_step.argtypes = [vp, vp, vp, vp, sz, f32, f64, f64, f32, C.c_int, vp]
     l.ebk_gemm.argtypes = [i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, f32, vp]
+    l.ebk_gemm_tma.argtypes = [i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, f32, f32, vp]
     l.ebk_attention_core_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp]
     l.ebk_attention_core_bwd.argtypes = [i32, i32, i32, i32, vp, vp, f32, u64, vp, vp]
     l.ebk_dropout_mask.argtypes = [u64, f32, sz, vp, vp]

@@ -242,6 +242,14 @@ int ebk_gemm(int32_t math, int32_t transA, int32_t transB, int32_t M, int32_t N,
              const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
              float beta, void* stream);
 
+/* The training-path GEMM on its own: all-TMA tcgen05 kind::tf32, C (+)= alpha * op(A) . op(B), beta in {0,1}.
+ * A and B must hold tf32-representable values (the tensor core truncates); transA: A stored [K, M];
+ * transB: B stored [N, K]; tall != 0: 256-row tiles.  Replaces the K.dot / tf.matmul contractions of
+ * layers.py:65, 214-230 and their autodiff transposes. */
+int ebk_gemm_tma(int32_t transA, int32_t transB, int32_t tall, int32_t M, int32_t N, int32_t K,
+                 const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
+                 float beta, float alpha, void* stream);
+
 /* Multi-head attention core on packed projections (layers.py:231-252).
  *   qkv [n_seq*L, 3*D] -> y [n_seq*L, D] */
 int ebk_attention_core_fwd(int32_t n_seq, int32_t L, int32_t nh, int32_t dh, const float* qkv,
