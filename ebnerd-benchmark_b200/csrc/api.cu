@@ -36,7 +36,8 @@ cudaEvent_t prof_event() {
 const char* kTagNames[T_NUM_TAGS] = {"qkv_gemm_fwd", "attn_core_fwd", "att_gemm_fwd", "attpool_fwd", "attpool_bwd",
                                      "colsum", "att_wgrad_gemm", "att_dgrad_gemm", "attn_core_bwd", "qkv_wgrad_gemm",
                                      "qkv_dgrad_gemm", "embed_scatter", "score_ce", "adam", "embed_pad",
-                                     "conv_gemm_fwd", "conv_dz", "conv_wgrad_gemm", "conv_dgrad_gemm", "catview"};
+                                     "conv_gemm_fwd", "conv_dz", "conv_wgrad_gemm", "conv_dgrad_gemm", "catview",
+                                     "embed_gather"};
 }  // namespace
 bool prof_on() { return g_prof; }
 void prof_set_group(int g) { g_prof_user = g; }
@@ -75,6 +76,9 @@ struct SeqWs {
   float *wqkv_d, *attw_d;              //   dgrad    (B = W^T, K-major)
   float *wqkv_f_lo, *attw_f_lo;        //   3xTF32 low parts of the forward packs (EBK_MATH_TF32X3)
   float* dqkv_pk;                      // dQKV again, in the packed B layout of the weight-gradient GEMM
+  // TMA path (EBK_MATH_TF32): dense tf32-rounded operands
+  float *xd;                           //   dropout(gather(table, tok)) or the dense input, [R, Din]
+  float *wqkv_r, *attw_r;              //   rounded copies of the weights
   size_t bytes;
 };
 
@@ -104,8 +108,18 @@ SeqWs seq_layout(const ebk_seqenc_desc& d, void* base) {
   w.wqkv_f_lo = take(gemm_tf32_packed_floats(3 * (int)D, d.Din, false));
   w.attw_f_lo = take(gemm_tf32_packed_floats(d.att, (int)D, false));
   w.dqkv_pk = take(gemm_tf32_packed_floats(3 * (int)D, (int)R, false));
+  w.xd = take(R * (size_t)d.Din + 64);  // + 64: TMA boxes of the last row may touch (zero-filled) columns past it
+  w.wqkv_r = take((size_t)d.Din * 3 * D + 64);
+  w.attw_r = take(D * (size_t)d.att + 64);
   w.bytes = off;
   return w;
+}
+
+// The all-TMA GEMM path: tf32 tensor-core math, every row stride a multiple of 16 bytes.
+bool tma_path(const ebk_seqenc_desc& d, const SeqWs& ws) {
+  const int D = d.nh * d.dh;
+  return d.math == EBK_MATH_TF32 && d.att % 4 == 0 &&
+         gemm_tma_eligible(ws.xd, d.Din, ws.wqkv_r, 3 * D, 1, 1, 1) && gemm_tma_eligible(ws.y0, D, ws.attw_r, d.att, 1, 1, 1);
 }
 
 int check_desc(const ebk_seqenc_desc* d) {
@@ -196,6 +210,30 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   Dropout drop1 = make_dropout(training != 0, d->dropout, seed1);
   Dropout drop2 = make_dropout(training != 0, d->dropout, seed2);
   const Dropout none = make_dropout(false, 0.0f, 0);
+  if (tma_path(*d, ws)) {
+    // ---- all-TMA path: every GEMM operand is materialised dense, masked and tf32-rounded by the layer
+    // before it, so the tensor-core kernels spend no issue slots on operand preparation ----
+    EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st));
+    EBK_TRY(round_tf32_copy(ws.wqkv_r, Wqkv, (size_t)d->Din * 3 * D, st));
+    EBK_TRY(round_tf32_copy(ws.attw_r, attW, (size_t)D * d->att, st));
+    // (1) Q|K|V = dropout1(gather(table, tok)) . Wqkv        nrms.py:134-139, layers.py:214-230
+    EBK_PROF(T_QKV_FWD, gemm_tma(ws.xd, d->Din, false, ws.wqkv_r, 3 * D, false, ws.qkv, 3 * D, R, 3 * D, d->Din, 0.0f,
+                                 1.0f, st, -1));
+    // (2) attention core; its output is stored as tf32(dropout2(Y0)) -- the only form AttLayer2 reads
+    if (attention_mma_supported(d->L, d->dh, ws.qkv, ws.y0, ws.qkv)) {
+      EBK_PROF(T_ATTN_FWD, attention_core_fwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st, drop2, true));
+    } else {
+      EBK_CHECK_ARG(!drop2.on(), "seqenc_fwd: dropout needs L <= 32 and dh <= 32 on the tensor-core path");
+      EBK_PROF(T_ATTN_FWD, attention_core_fwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st));
+      EBK_TRY(round_tf32_copy(ws.y0, ws.y0, (size_t)R * D, st));
+    }
+    // (3) pre-activation of AttLayer2                                nrms.py:153-156, layers.py:65
+    EBK_PROF(T_ATT_GEMM_FWD, gemm_tma(ws.y0, D, false, ws.attw_r, d->att, false, ws.hbuf, d->att, R, d->att, D, 0.0f,
+                                      1.0f, st, -1));
+    // (4) tanh, .q, exp, normalise (+1e-7), pool                     layers.py:65-81
+    EBK_PROF(T_POOL_FWD, attpool_fwd(d->n_seq, d->L, D, d->att, ws.y0, none, ws.hbuf, attb, attq, ws.w, out, st));
+    return EBK_OK;
+  }
   // Tensor-core modes: the weights are packed once per call (rounded to tf32, arranged in the GEMM's
   // shared-memory tile layout) and kept in the workspace for the backward pass.
   const bool tc = d->math != EBK_MATH_FP32;
@@ -257,6 +295,35 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   Dropout drop2 = make_dropout(training != 0, d->dropout, seed2);
   const Dropout none = make_dropout(false, 0.0f, 0);
 
+  if (tma_path(*d, ws)) {
+    // ---- all-TMA path (see ebk_seqenc_fwd): ws.xd, ws.y0 (= tf32(dropout2(Y0))), ws.wqkv_r, ws.attw_r are
+    // the forward's; dpre and dQKV are rounded to tf32 by the kernels that produce them ----
+    EBK_PROF(T_POOL_BWD, attpool_bwd(d->n_seq, d->L, D, d->att, ws.y0, none, ws.hbuf, attq, ws.w, d_out, ws.da, ws.dpre,
+                                     ws.dy, true, st));
+    EBK_PROF(T_COLSUM, colsum_accum_ws(R, d->att, ws.hbuf, d->att, ws.da, dattq, ws.colsum, st));   // dq = sum_r h_r da_r
+    EBK_PROF(T_COLSUM, colsum_accum_ws(R, d->att, ws.dpre, d->att, nullptr, dattb, ws.colsum, st)); // db = sum_r dpre_r
+    // dW += X^T dpre
+    EBK_PROF(T_ATT_WGRAD, gemm_tma(ws.y0, D, true, ws.dpre, d->att, false, dattW, d->att, D, d->att, R, 1.0f, 1.0f, st, -1));
+    // dX += dpre W^T
+    EBK_PROF(T_ATT_DGRAD, gemm_tma(ws.dpre, d->att, false, ws.attw_r, d->att, true, ws.dy, D, R, D, d->att, 1.0f, 1.0f, st, -1));
+    // SelfAttention core backward (dropout2 mask and scale applied while reading dy)
+    if (attention_mma_supported(d->L, d->dh, ws.qkv, ws.dy, ws.dqkv)) {
+      EBK_PROF(T_ATTN_BWD, attention_core_bwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, true, st));
+    } else {
+      EBK_PROF(T_ATTN_BWD, attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, true, st));
+    }
+    // dWqkv += X^T dQKV  (X = dropout1(gather))
+    EBK_PROF(T_QKV_WGRAD, gemm_tma(ws.xd, d->Din, true, ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din, 3 * D, R, 1.0f, 1.0f,
+                                   st, -1));
+    // dX = dQKV Wqkv^T
+    if (tok != nullptr ? (d_table != nullptr) : (d_x != nullptr)) {
+      float* dx = tok ? ws.dx : d_x;
+      EBK_PROF(T_QKV_DGRAD, gemm_tma(ws.dqkv, 3 * D, false, ws.wqkv_r, 3 * D, true, dx, d->Din, R, d->Din, 3 * D, 0.0f, 1.0f,
+                                     st, -1));
+      if (tok) EBK_PROF(T_SCATTER, scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
+    }
+    return EBK_OK;
+  }
   // tensor-core mode: the forward left the packed weights in the workspace, and the kernels that
   // produce dpre / dQKV round them to tf32 on store so they can be staged as B operands with cp.async.
   const bool tc = d->math != EBK_MATH_FP32;

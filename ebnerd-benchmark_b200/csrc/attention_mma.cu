@@ -187,7 +187,8 @@ __device__ __forceinline__ void store_frag(float* P, const float (&acc)[2][4][4]
 
 template <int DP>
 __global__ void __launch_bounds__(WARPS * 32) attn_fwd_mma_kernel(int n_seq, int L, int nh, int dh,
-                                                                  const float* __restrict__ qkv, float* __restrict__ y) {
+                                                                  const float* __restrict__ qkv, float* __restrict__ y,
+                                                                  Dropout drop, bool round_out) {
   extern __shared__ __align__(16) float smem[];
   constexpr int QS = Str<DP>::QS, VS = Str<DP>::VS, PS = Str<DP>::PS;
   constexpr int QK_FLOATS = (2 * LP * QS > LP * PS) ? 2 * LP * QS : LP * PS;
@@ -244,9 +245,23 @@ __global__ void __launch_bounds__(WARPS * 32) attn_fwd_mma_kernel(int n_seq, int
       for (int nt = 0; nt < DP / 8; ++nt) {
         const int col = nt * 8 + 2 * t;
         if (col < dh) {
-          const int r0 = mt * 16 + g, r1 = r0 + 8;
-          if (r0 < L) *reinterpret_cast<float2*>(out + (long)r0 * D + col) = make_float2(o[mt][nt][0], o[mt][nt][1]);
-          if (r1 < L) *reinterpret_cast<float2*>(out + (long)r1 * D + col) = make_float2(o[mt][nt][2], o[mt][nt][3]);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int r = mt * 16 + g + hf * 8;
+            if (r >= L) continue;
+            float2 v = make_float2(o[mt][nt][hf * 2], o[mt][nt][hf * 2 + 1]);
+            if (drop.on()) {  // the layer after the attention only ever reads dropout(y): store it masked
+              const uint64_t idx = (uint64_t)((long)n * L + r) * (uint64_t)D + (uint64_t)(h * dh + col);
+              const float4 f = drop.factor4_group(idx >> 2);
+              v.x *= (idx & 2ull) ? f.z : f.x;
+              v.y *= (idx & 2ull) ? f.w : f.y;
+            }
+            if (round_out) {
+              v.x = round_tf32_bits(v.x);
+              v.y = round_tf32_bits(v.y);
+            }
+            *reinterpret_cast<float2*>(out + (long)r * D + col) = v;
+          }
         }
       }
     __syncwarp();
@@ -439,7 +454,8 @@ bool attention_mma_supported(int L, int dh, const void* p0, const void* p1, cons
   return L >= 1 && L <= 32 && dh >= 4 && dh <= 32 && (dh % 4 == 0) && al(p0) && al(p1) && al(p2);
 }
 
-int attention_core_fwd_mma(int n_seq, int L, int nh, int dh, const float* qkv, float* y, cudaStream_t st) {
+int attention_core_fwd_mma(int n_seq, int L, int nh, int dh, const float* qkv, float* y, cudaStream_t st,
+                           Dropout drop_out, bool round_out) {
   if (n_seq <= 0) return EBK_OK;
   EBK_CHECK_ARG(attention_mma_supported(L, dh, qkv, y, qkv) && (nh * dh) % 4 == 0, "attention_mma: unsupported shape L=%d dh=%d", L, dh);
   const long total = (long)n_seq * nh;
@@ -449,7 +465,7 @@ int attention_core_fwd_mma(int n_seq, int L, int nh, int dh, const float* qkv, f
     constexpr int QKF = (2 * LP * Str<DP_>::QS > LP * Str<DP_>::PS) ? 2 * LP * Str<DP_>::QS : LP * Str<DP_>::PS; \
     size_t smem = (size_t)WARPS * (QKF + LP * Str<DP_>::VS) * sizeof(float);                                  \
     EBK_TRY(cfg(attn_fwd_mma_kernel<DP_>, smem, total, &grid));                                               \
-    attn_fwd_mma_kernel<DP_><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, dh, qkv, y);                       \
+    attn_fwd_mma_kernel<DP_><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, dh, qkv, y, drop_out, round_out);  \
   }
   if (dh <= 16) RUN(16) else if (dh <= 24) RUN(24) else RUN(32)
 #undef RUN

@@ -152,6 +152,32 @@ __global__ void split_tf32_copy_kernel(float* __restrict__ hi, float* __restrict
   lo[i] = round_tf32_bits(x - h);
 }
 
+// Materialises the A operand of the QKV projection for the TMA GEMM: gather + dropout + tf32 rounding.
+__global__ void embed_rows_kernel(long n4, int E4, int V, const int32_t* __restrict__ tok,
+                                  const float4* __restrict__ src, Dropout drop, float4* __restrict__ xd) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int r = (int)(i / E4), c4 = (int)(i - (long)r * E4);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tok != nullptr) {
+    const int t = __ldg(tok + r);
+    if (t >= 0 && t < V) {
+      const float4* p = src + (long)t * E4 + c4;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                   : "l"(p));
+    }
+  } else {
+    v = __ldg(src + i);
+  }
+  if (drop.on()) {
+    const float4 f = drop.factor4_group((uint64_t)i);
+    v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
+  }
+  v.x = round_tf32_bits(v.x); v.y = round_tf32_bits(v.y); v.z = round_tf32_bits(v.z); v.w = round_tf32_bits(v.w);
+  xd[i] = v;
+}
+
 __global__ void scatter_rows_add_kernel(int R, int E4, int V, const int32_t* __restrict__ tok,
                                         const float4* __restrict__ dX, Dropout drop,
                                         float* __restrict__ d_table) {
@@ -223,6 +249,18 @@ int round_tf32_copy(float* dst, const float* src, size_t n, cudaStream_t st) {
 int split_tf32_copy(float* hi, float* lo, const float* src, size_t n, cudaStream_t st) {
   if (n == 0) return EBK_OK;
   split_tf32_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(hi, lo, src, n);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+int embed_rows(int R, int E, int V, const int32_t* tok, const float* table_or_x, Dropout drop, float* xd,
+               cudaStream_t st) {
+  if (R <= 0) return EBK_OK;
+  EBK_CHECK_ARG(E % 4 == 0, "embed_rows: E=%d must be a multiple of 4", E);
+  const long n4 = (long)R * (E / 4);
+  embed_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, E / 4, V, tok,
+                                                                 reinterpret_cast<const float4*>(table_or_x), drop,
+                                                                 reinterpret_cast<float4*>(xd));
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

@@ -48,7 +48,7 @@ void note_launch();
 enum ProfTag {
   T_QKV_FWD = 0, T_ATTN_FWD, T_ATT_GEMM_FWD, T_POOL_FWD, T_POOL_BWD, T_COLSUM, T_ATT_WGRAD, T_ATT_DGRAD,
   T_ATTN_BWD, T_QKV_WGRAD, T_QKV_DGRAD, T_SCATTER, T_SCORE, T_ADAM,
-  T_EMBED_PAD, T_CONV_FWD, T_CONV_DZ, T_CONV_WGRAD, T_CONV_DGRAD, T_CATVIEW, T_NUM_TAGS
+  T_EMBED_PAD, T_CONV_FWD, T_CONV_DZ, T_CONV_WGRAD, T_CONV_DGRAD, T_CATVIEW, T_EMBED_GATHER, T_NUM_TAGS
 };
 // profiler group of the following launches: 0 = "news." slots, 1 = "user." slots
 void prof_set_group(int g);
@@ -201,7 +201,10 @@ int attention_core_bwd(int n_seq, int L, int nh, int dh, const float* qkv, const
 
 // warp-level tensor-core (mma.sync tf32) variants for training, L <= 32 (attention_mma.cu)
 bool attention_mma_supported(int L, int dh, const void* p0, const void* p1, const void* p2);
-int attention_core_fwd_mma(int n_seq, int L, int nh, int dh, const float* qkv, float* y, cudaStream_t st);
+// drop_out / round_out: store dropout(y) (mask and 1/(1-p) scale) and/or round it to tf32 -- what the
+// TMA GEMM of the following AttLayer2 consumes
+int attention_core_fwd_mma(int n_seq, int L, int nh, int dh, const float* qkv, float* y, cudaStream_t st,
+                           Dropout drop_out = Dropout{0, 0, 1.0f}, bool round_out = false);
 int attention_core_bwd_mma(int n_seq, int L, int nh, int dh, const float* qkv, const float* dy, Dropout drop,
                            float* dqkv, bool round_out, cudaStream_t st, float* dqkv_packed = nullptr,
                            int packed_bn = 0);
@@ -224,6 +227,9 @@ size_t colsum_partial_floats(int R, int Ncols);
 int bias_act(float* z, const float* b, long n, int U, int relu, cudaStream_t st);
 int act_bwd(const float* dy, const float* y, long n, Dropout drop, int relu, int round_out, float* dz, cudaStream_t st);
 
+// Xd[r, :] = tf32(dropout(table[tok[r], :]))  (ids outside [0, V) -> zero row); tok == NULL: Xd = tf32(x)
+int embed_rows(int R, int E, int V, const int32_t* tok, const float* table_or_x, Dropout drop, float* xd,
+               cudaStream_t st);
 // d_table[tok[r], :] += dX[r, :] * dropout(r*E + e)
 int scatter_rows_add(int R, int E, int V, const int32_t* tok, const float* dX, Dropout drop,
                      float* d_table, cudaStream_t st);

@@ -474,7 +474,7 @@ bool gemm_tma_eligible(const float* A, int lda, const float* B, int ldb, int M, 
 
 // Operands must already hold tf32-representable values (the tensor core truncates the low 13 mantissa
 // bits of whatever it is given).  transA: A is stored [K, M]; transB: B is stored [N, K].
-// tall != 0 selects 256-row tiles (MT = 2).
+// tall: 1 selects 256-row tiles (MT = 2), 0 128-row tiles, -1 picks by problem size.
 int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool transB, float* C, int ldc, int M,
              int N, int K, float beta, float alpha, cudaStream_t st, int tall) {
   if (M <= 0 || N <= 0) return EBK_OK;
@@ -487,6 +487,13 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
     EBK_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const bool a_mn = transA, b_mn = !transB;
+  if (tall < 0) {
+    // auto: 256-row tiles halve the L2 traffic of B; use them when they still fill the machine, or when
+    // split-K fills it anyway
+    const long tn = ceil_div(N, ceil_div(ceil_div(N, ceil_div(N, 256)), 16) * 16);
+    const long t1 = (long)ceil_div(M, BM) * tn, t2 = (long)ceil_div(M, 2 * BM) * tn;
+    tall = (t2 >= 2L * g_sms || t1 < g_sms) ? 1 : 0;
+  }
   const int MT = tall ? 2 : 1;
   TParams p;
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.alpha = alpha;
