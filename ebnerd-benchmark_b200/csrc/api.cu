@@ -79,6 +79,7 @@ struct SeqWs {
   // TMA path (EBK_MATH_TF32): dense tf32-rounded operands
   float *xd;                           //   dropout(gather(table, tok)) or the dense input, [R, Din]
   float *wqkv_r, *attw_r;              //   rounded copies of the weights
+  float *colpart, *colsum2;            //   per-sequence column-sum partials [n_seq, 2 att] and their reduction scratch
   size_t bytes;
 };
 
@@ -111,6 +112,8 @@ SeqWs seq_layout(const ebk_seqenc_desc& d, void* base) {
   w.xd = take(R * (size_t)d.Din + 64);  // + 64: TMA boxes of the last row may touch (zero-filled) columns past it
   w.wqkv_r = take((size_t)d.Din * 3 * D + 64);
   w.attw_r = take(D * (size_t)d.att + 64);
+  w.colpart = take((size_t)d.n_seq * 2 * d.att);
+  w.colsum2 = take(colsum_partial_floats(d.n_seq, 2 * d.att));
   w.bytes = off;
   return w;
 }
@@ -217,10 +220,14 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
     EBK_TRY(round_tf32_copy(ws.wqkv_r, Wqkv, (size_t)d->Din * 3 * D, st));
     EBK_TRY(round_tf32_copy(ws.attw_r, attW, (size_t)D * d->att, st));
     // (1) Q|K|V = dropout1(gather(table, tok)) . Wqkv        nrms.py:134-139, layers.py:214-230
+    // (stored rounded to tf32: the attention kernels feed it to mma.sync without touching it again)
+    const GemmEpilogue round_epi{nullptr, nullptr, 0, 1, none, 0, true};
     EBK_PROF(T_QKV_FWD, gemm_tma(ws.xd, d->Din, false, ws.wqkv_r, 3 * D, false, ws.qkv, 3 * D, R, 3 * D, d->Din, 0.0f,
-                                 1.0f, st, -1));
+                                 1.0f, st, -1, &round_epi));
     // (2) attention core; its output is stored as tf32(dropout2(Y0)) -- the only form AttLayer2 reads
-    if (attention_mma_supported(d->L, d->dh, ws.qkv, ws.y0, ws.qkv)) {
+    if (attention_pre_supported(d->L, d->dh, ws.qkv, ws.y0, ws.qkv)) {
+      EBK_PROF(T_ATTN_FWD, attention_core_fwd_pre(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, drop2, st));
+    } else if (attention_mma_supported(d->L, d->dh, ws.qkv, ws.y0, ws.qkv)) {
       EBK_PROF(T_ATTN_FWD, attention_core_fwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st, drop2, true));
     } else {
       EBK_CHECK_ARG(!drop2.on(), "seqenc_fwd: dropout needs L <= 32 and dh <= 32 on the tensor-core path");
@@ -298,19 +305,25 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   if (tma_path(*d, ws)) {
     // ---- all-TMA path (see ebk_seqenc_fwd): ws.xd, ws.y0 (= tf32(dropout2(Y0))), ws.wqkv_r, ws.attw_r are
     // the forward's; dpre and dQKV are rounded to tf32 by the kernels that produce them ----
-    EBK_PROF(T_POOL_BWD, attpool_bwd(d->n_seq, d->L, D, d->att, ws.y0, none, ws.hbuf, attq, ws.w, d_out, ws.da, ws.dpre,
-                                     ws.dy, true, st));
-    EBK_PROF(T_COLSUM, colsum_accum_ws(R, d->att, ws.hbuf, d->att, ws.da, dattq, ws.colsum, st));   // dq = sum_r h_r da_r
-    EBK_PROF(T_COLSUM, colsum_accum_ws(R, d->att, ws.dpre, d->att, nullptr, dattb, ws.colsum, st)); // db = sum_r dpre_r
+    EBK_PROF(T_POOL_BWD, attpool_bwd_fused(d->n_seq, d->L, D, d->att, ws.y0, ws.hbuf, attq, ws.w, d_out, ws.da, ws.dpre,
+                                           ws.colpart, st));
+    // db += sum_r dpre_r ; dq += sum_r h_r da_r   (second, deterministic stage over the per-sequence partials)
+    EBK_PROF(T_COLSUM, colsum_accum_ws(d->n_seq, d->att, ws.colpart, 2 * d->att, nullptr, dattb, ws.colsum2, st));
+    EBK_PROF(T_COLSUM, colsum_accum_ws(d->n_seq, d->att, ws.colpart + d->att, 2 * d->att, nullptr, dattq, ws.colsum2, st));
     // dW += X^T dpre
     EBK_PROF(T_ATT_WGRAD, gemm_tma(ws.y0, D, true, ws.dpre, d->att, false, dattW, d->att, D, d->att, R, 1.0f, 1.0f, st, -1));
-    // dX += dpre W^T
-    EBK_PROF(T_ATT_DGRAD, gemm_tma(ws.dpre, d->att, false, ws.attw_r, d->att, true, ws.dy, D, R, D, d->att, 1.0f, 1.0f, st, -1));
-    // SelfAttention core backward (dropout2 mask and scale applied while reading dy)
-    if (attention_mma_supported(d->L, d->dh, ws.qkv, ws.dy, ws.dqkv)) {
-      EBK_PROF(T_ATTN_BWD, attention_core_bwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, true, st));
+    // dY0 = tf32(dropout2'(w_t d_out + dpre W^T)): pooling term, dropout backward and the rounding for the
+    // attention kernel all happen in the GEMM epilogue
+    const GemmEpilogue dy_epi{ws.w, d_out, D, d->L, drop2, D, true};
+    EBK_PROF(T_ATT_DGRAD, gemm_tma(ws.dpre, d->att, false, ws.attw_r, d->att, true, ws.dy, D, R, D, d->att, 0.0f, 1.0f, st,
+                                   -1, &dy_epi));
+    // SelfAttention core backward
+    if (attention_pre_supported(d->L, d->dh, ws.qkv, ws.dy, ws.dqkv)) {
+      EBK_PROF(T_ATTN_BWD, attention_core_bwd_pre(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, ws.dqkv, st));
+    } else if (attention_mma_supported(d->L, d->dh, ws.qkv, ws.dy, ws.dqkv)) {
+      EBK_PROF(T_ATTN_BWD, attention_core_bwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, none, ws.dqkv, true, st));
     } else {
-      EBK_PROF(T_ATTN_BWD, attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, true, st));
+      EBK_PROF(T_ATTN_BWD, attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, none, ws.dqkv, true, st));
     }
     // dWqkv += X^T dQKV  (X = dropout1(gather))
     EBK_PROF(T_QKV_WGRAD, gemm_tma(ws.xd, d->Din, true, ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din, 3 * D, R, 1.0f, 1.0f,

@@ -1,0 +1,439 @@
+// Attention core of the all-TMA training path (layers.py:231-252, adjoint_a=True) and its backward, for
+// operands that are ALREADY tf32 values: the QKV projection and the AttLayer2 dgrad GEMM round (and, for dY,
+// dropout-mask) their outputs in their epilogues, so this file only moves data and multiplies:
+//   * one warp per (sequence, head); Q, K, V (and dO) go global -> shared with 16-byte cp.async straight
+//     into the fragment-friendly layout, DOUBLE-BUFFERED: the loads of the warp's next item are in flight
+//     while the current one is computed (the previous kernels exposed one full memory round trip per item);
+//   * 32x32xDH products on mma.sync.m16n8k8 tf32; the softmax / dS algebra stays in the accumulator
+//     registers;
+//   * A and dS feed the next products (dV = A dO, dQ = dS K) DIRECTLY from the accumulator registers:
+//     the MMA's k index is permuted (slot t <-> key 2t, slot t+4 <-> key 2t+1) so that each thread's
+//     accumulator pair is exactly its A-fragment; only the transposed uses (O = A^T V, dK = dS^T Q) go
+//     through a 32x40 shared tile.
+// Shared-memory row stride ST: DH (=20) or DH+4, chosen so that the 8 rows x 4 columns touched by one
+// fragment load fall into 32 distinct banks.
+#include "ebk_common.cuh"
+
+namespace ebk {
+namespace {
+
+constexpr int WARPS = 4;
+constexpr int LP = 32;   // padded sequence length
+constexpr int PS = 40;   // stride of the 32x32 score-shaped tile
+
+template <int DH> struct Cfg {
+  static constexpr int ST = (DH == 20) ? 20 : DH + 4;
+  static constexpr int KF = DH / 8;            // full k-steps over the head dim
+  static constexpr bool KH = (DH % 8) != 0;    // plus one half k-step (4 columns)
+  static constexpr int NT = (DH + 7) / 8;      // n-tiles over the head dim
+  static constexpr int MAT = LP * ST;          // floats per staged matrix
+};
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t u(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ uint32_t ur(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }  // tf32 round
+__device__ __forceinline__ void cp16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// issue the cp.async copies of NM [L, DH] slices (global row strides ld[m]) into dst + m * MAT
+template <int DH, int NM>
+__device__ __forceinline__ void stage_async(float* dst, const float* const (&src)[NM], const long (&ld)[NM], int L, int lane) {
+  constexpr int CPR = DH / 4, ST = Cfg<DH>::ST, MAT = Cfg<DH>::MAT;
+  for (int i = lane; i < L * CPR; i += 32) {
+    const int t = i / CPR, j = i - t * CPR;
+#pragma unroll
+    for (int m = 0; m < NM; ++m) cp16(dst + m * MAT + t * ST + j * 4, src[m] + (long)t * ld[m] + j * 4);
+  }
+}
+
+// acc (32x32 fragments) = X Y^T over the head dim; X, Y staged row-major with stride ST
+template <int DH>
+__device__ __forceinline__ void gemm_xyT(float (&acc)[2][4][4], const float* X, const float* Y, int g, int t) {
+  constexpr int ST = Cfg<DH>::ST;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.0f;
+#pragma unroll
+  for (int ks = 0; ks < Cfg<DH>::KF + (Cfg<DH>::KH ? 1 : 0); ++ks) {
+    const bool half = ks >= Cfg<DH>::KF;  // compile-time after unrolling: only columns ks*8 .. ks*8+3 exist
+    uint32_t a[2][4], b[4][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const float* p = X + (mt * 16 + g) * ST + ks * 8 + t;
+      a[mt][0] = u(p[0]);
+      a[mt][1] = u(p[8 * ST]);
+      a[mt][2] = half ? 0u : u(p[4]);
+      a[mt][3] = half ? 0u : u(p[8 * ST + 4]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float* p = Y + (nt * 8 + g) * ST + ks * 8 + t;
+      b[nt][0] = u(p[0]);
+      b[nt][1] = half ? 0u : u(p[4]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[mt][nt], a[mt], b[nt]);
+  }
+}
+
+// out[32 x DH] (fragments o[mt][nt]) = P M, P given as accumulator fragments (rounded here), M staged
+// [key][d] with stride ST.  k-slot permutation: slot t <-> key 8ks+2t, slot t+4 <-> key 8ks+2t+1.
+template <int DH>
+__device__ __forceinline__ void gemm_regP(float (&o)[2][Cfg<DH>::NT][4], const float (&P)[2][4][4], const float* M, int g,
+                                          int t) {
+  constexpr int ST = Cfg<DH>::ST, NT = Cfg<DH>::NT;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.0f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[2][4], b[NT][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      a[mt][0] = ur(P[mt][ks][0]);
+      a[mt][1] = ur(P[mt][ks][2]);
+      a[mt][2] = ur(P[mt][ks][1]);
+      a[mt][3] = ur(P[mt][ks][3]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float* p = M + (ks * 8 + 2 * t) * ST + nt * 8 + g;
+      b[nt][0] = u(p[0]);
+      b[nt][1] = u(p[ST]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma_tf32(o[mt][nt], a[mt], b[nt]);
+  }
+}
+
+// out[32 x DH] = T^T M, T a 32x32 tile in shared memory (stride PS, already tf32), M staged [q][d] (stride ST)
+template <int DH>
+__device__ __forceinline__ void gemm_smemT(float (&o)[2][Cfg<DH>::NT][4], const float* T, const float* M, int g, int t) {
+  constexpr int ST = Cfg<DH>::ST, NT = Cfg<DH>::NT;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.0f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[2][4], b[NT][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const float* p = T + (ks * 8 + t) * PS + mt * 16 + g;   // A(row, col) = T[col][row]
+      a[mt][0] = u(p[0]);
+      a[mt][1] = u(p[8]);
+      a[mt][2] = u(p[4 * PS]);
+      a[mt][3] = u(p[4 * PS + 8]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float* p = M + (ks * 8 + t) * ST + nt * 8 + g;
+      b[nt][0] = u(p[0]);
+      b[nt][1] = u(p[4 * ST]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma_tf32(o[mt][nt], a[mt], b[nt]);
+  }
+}
+
+// in-register row softmax of S*inv over the first L columns (fragment layout); masked columns -> 0
+__device__ __forceinline__ void softmax_rows(float (&acc)[2][4][4], float inv, int L, int t) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = nt * 8 + 2 * t + e;
+          float s = acc[mt][nt][hf * 2 + e] * inv;
+          s = col < L ? s : -INFINITY;
+          acc[mt][nt][hf * 2 + e] = s;
+          mx = fmaxf(mx, s);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.0f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float ex = __expf(acc[mt][nt][hf * 2 + e] - mx);
+          acc[mt][nt][hf * 2 + e] = ex;
+          sum += ex;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float r = 1.0f / sum;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) acc[mt][nt][hf * 2 + e] *= r;
+    }
+}
+
+// store a 32x32 accumulator-fragment matrix to smem [32][PS], rounded to tf32
+__device__ __forceinline__ void store_frag(float* P, const float (&acc)[2][4][4], int g, int t) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int col = nt * 8 + 2 * t;
+      *reinterpret_cast<uint2*>(P + (mt * 16 + g) * PS + col) = make_uint2(ur(acc[mt][nt][0]), ur(acc[mt][nt][1]));
+      *reinterpret_cast<uint2*>(P + (mt * 16 + g + 8) * PS + col) = make_uint2(ur(acc[mt][nt][2]), ur(acc[mt][nt][3]));
+    }
+}
+
+// write a [32 x DH] fragment matrix (rows = tokens) to out[(row0 + r) * ld + col0 + c], rounded to tf32
+template <int DH>
+__device__ __forceinline__ void store_rows(const float (&acc)[2][Cfg<DH>::NT][4], float scale, float* __restrict__ out,
+                                           long row0, int ld, int col0, int L, int g, int t) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < Cfg<DH>::NT; ++nt) {
+      const int col = nt * 8 + 2 * t;
+      if (col >= DH) continue;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int r = mt * 16 + g + hf * 8;
+        if (r >= L) continue;
+        const uint2 v = make_uint2(ur(acc[mt][nt][hf * 2] * scale), ur(acc[mt][nt][hf * 2 + 1] * scale));
+        *reinterpret_cast<uint2*>(out + (row0 + r) * ld + col0 + col) = v;
+      }
+    }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(WARPS * 32) attn_fwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
+                                                                  float* __restrict__ y, Dropout drop) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int MAT = Cfg<DH>::MAT;
+  constexpr int PER_WARP = 2 * 3 * MAT + LP * PS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float* base_s = smem + warp * PER_WARP;
+  float* Ps = base_s + 2 * 3 * MAT;
+  for (int i = lane; i < 2 * 3 * MAT; i += 32) base_s[i] = 0.0f;  // zero padding rows / columns once
+  __syncwarp();
+  const int D = nh * DH;
+  const float inv = rsqrtf((float)DH);
+  const long total = (long)n_seq * nh;
+  const long stride = (long)gridDim.x * WARPS;
+  long item = (long)blockIdx.x * WARPS + warp;
+  auto issue = [&](long it, int buf) {
+    const int n = (int)(it / nh), h = (int)(it - (long)n * nh);
+    const float* b = qkv + (long)n * L * 3 * D + h * DH;
+    const float* const src[3] = {b, b + D, b + 2 * D};
+    const long ld[3] = {3L * D, 3L * D, 3L * D};
+    stage_async<DH, 3>(base_s + buf * 3 * MAT, src, ld, L, lane);
+    cp_commit();
+  };
+  int buf = 0;
+  if (item < total) issue(item, 0);
+  for (; item < total; item += stride) {
+    const long next = item + stride;
+    if (next < total) {
+      issue(next, buf ^ 1);
+      cp_wait<1>();
+    } else {
+      cp_wait<0>();
+    }
+    __syncwarp();
+    const int n = (int)(item / nh), h = (int)(item - (long)n * nh);
+    const float* Qs = base_s + buf * 3 * MAT;
+    const float* Ks = Qs + MAT;
+    const float* Vs = Ks + MAT;
+    float acc[2][4][4];
+    gemm_xyT<DH>(acc, Qs, Ks, g, t);
+    softmax_rows(acc, inv, L, t);
+    store_frag(Ps, acc, g, t);
+    __syncwarp();
+    float o[2][Cfg<DH>::NT][4];
+    gemm_smemT<DH>(o, Ps, Vs, g, t);   // O[k, d] = sum_q P[q, k] V[q, d]
+    float* out = y + (long)n * L * D + h * DH;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < Cfg<DH>::NT; ++nt) {
+        const int col = nt * 8 + 2 * t;
+        if (col >= DH) continue;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int r = mt * 16 + g + hf * 8;
+          if (r >= L) continue;
+          float2 v = make_float2(o[mt][nt][hf * 2], o[mt][nt][hf * 2 + 1]);
+          if (drop.on()) {  // AttLayer2 only ever reads dropout(y): store it masked and scaled
+            const uint64_t idx = (uint64_t)((long)n * L + r) * (uint64_t)D + (uint64_t)(h * DH + col);
+            const float4 f = drop.factor4_group(idx >> 2);
+            v.x *= (idx & 2ull) ? f.z : f.x;
+            v.y *= (idx & 2ull) ? f.w : f.y;
+          }
+          *reinterpret_cast<uint2*>(out + (long)r * D + col) = make_uint2(ur(v.x), ur(v.y));
+        }
+      }
+    __syncwarp();  // everyone is done with this buffer and with Ps before they are overwritten
+    buf ^= 1;
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(WARPS * 32) attn_bwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
+                                                                  const float* __restrict__ dy, float* __restrict__ dqkv) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int MAT = Cfg<DH>::MAT;
+  constexpr int PER_WARP = 2 * 4 * MAT + LP * PS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float* base_s = smem + warp * PER_WARP;
+  float* Ds = base_s + 2 * 4 * MAT;
+  for (int i = lane; i < 2 * 4 * MAT; i += 32) base_s[i] = 0.0f;
+  __syncwarp();
+  const int D = nh * DH;
+  const float inv = rsqrtf((float)DH);
+  const long total = (long)n_seq * nh;
+  const long stride = (long)gridDim.x * WARPS;
+  long item = (long)blockIdx.x * WARPS + warp;
+  auto issue = [&](long it, int buf) {
+    const int n = (int)(it / nh), h = (int)(it - (long)n * nh);
+    const float* b = qkv + (long)n * L * 3 * D + h * DH;
+    const float* const src[4] = {b, b + D, b + 2 * D, dy + (long)n * L * D + h * DH};
+    const long ld[4] = {3L * D, 3L * D, 3L * D, (long)D};
+    stage_async<DH, 4>(base_s + buf * 4 * MAT, src, ld, L, lane);
+    cp_commit();
+  };
+  int buf = 0;
+  if (item < total) issue(item, 0);
+  for (; item < total; item += stride) {
+    const long next = item + stride;
+    if (next < total) {
+      issue(next, buf ^ 1);
+      cp_wait<1>();
+    } else {
+      cp_wait<0>();
+    }
+    __syncwarp();
+    const int n = (int)(item / nh), h = (int)(item - (long)n * nh);
+    const long row0 = (long)n * L;
+    const float* Qs = base_s + buf * 4 * MAT;
+    const float* Ks = Qs + MAT;
+    const float* Vs = Ks + MAT;
+    const float* Gs = Vs + MAT;  // dO
+    float a_acc[2][4][4], d_acc[2][4][4];
+    gemm_xyT<DH>(a_acc, Qs, Ks, g, t);   // A = softmax(Q K^T / sqrt(dh))
+    softmax_rows(a_acc, inv, L, t);
+    gemm_xyT<DH>(d_acc, Vs, Gs, g, t);   // dA = V dO^T
+    // dS = A o (dA - rowsum(dA o A))
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float dot = 0.0f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) dot = fmaf(d_acc[mt][nt][hf * 2 + e], a_acc[mt][nt][hf * 2 + e], dot);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            d_acc[mt][nt][hf * 2 + e] = a_acc[mt][nt][hf * 2 + e] * (d_acc[mt][nt][hf * 2 + e] - dot);
+      }
+    store_frag(Ds, d_acc, g, t);  // only the transposed use (dK) needs dS in shared memory
+    float o[2][Cfg<DH>::NT][4];
+    gemm_regP<DH>(o, a_acc, Gs, g, t);   // dV[q, d] = sum_k A[q, k] dO[k, d]
+    store_rows<DH>(o, 1.0f, dqkv, row0, 3 * D, 2 * D + h * DH, L, g, t);
+    gemm_regP<DH>(o, d_acc, Ks, g, t);   // dQ[q, d] = sum_k dS[q, k] K[k, d] / sqrt(dh)
+    store_rows<DH>(o, inv, dqkv, row0, 3 * D, h * DH, L, g, t);
+    __syncwarp();
+    gemm_smemT<DH>(o, Ds, Qs, g, t);     // dK[k, d] = sum_q dS[q, k] Q[q, d] / sqrt(dh)
+    store_rows<DH>(o, inv, dqkv, row0, 3 * D, D + h * DH, L, g, t);
+    __syncwarp();
+    buf ^= 1;
+  }
+}
+
+template <typename Kern>
+int cfg(Kern kern, size_t smem, long total, int* grid) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("attention_pre: smem %zu: %s", smem, cudaGetErrorString(e));
+    return EBK_ERR_CUDA;
+  }
+  const long blocks = (total + WARPS - 1) / WARPS;
+  const long cap = 148L * 2;  // persistent: two CTAs per SM, every warp walks its items with a prefetch in flight
+  *grid = (int)(blocks < cap ? blocks : cap);
+  return EBK_OK;
+}
+
+}  // namespace
+
+bool attention_pre_supported(int L, int dh, const void* p0, const void* p1, const void* p2) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return L >= 1 && L <= 32 && (dh == 16 || dh == 20 || dh == 24 || dh == 32) && al(p0) && al(p1) && al(p2);
+}
+
+#define EBK_ATT_DISPATCH(RUN) \
+  if (dh == 16) RUN(16) else if (dh == 20) RUN(20) else if (dh == 24) RUN(24) else RUN(32)
+
+int attention_core_fwd_pre(int n_seq, int L, int nh, int dh, const float* qkv, float* y, Dropout drop_out, cudaStream_t st) {
+  if (n_seq <= 0) return EBK_OK;
+  EBK_CHECK_ARG(attention_pre_supported(L, dh, qkv, y, qkv), "attention_pre: unsupported shape L=%d dh=%d", L, dh);
+  const long total = (long)n_seq * nh;
+  int grid;
+#define RUN(DH_)                                                                                  \
+  {                                                                                               \
+    const size_t smem = (size_t)WARPS * (2 * 3 * Cfg<DH_>::MAT + LP * PS) * sizeof(float);        \
+    EBK_TRY(cfg(attn_fwd_pre_kernel<DH_>, smem, total, &grid));                                   \
+    attn_fwd_pre_kernel<DH_><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, qkv, y, drop_out);     \
+  }
+  EBK_ATT_DISPATCH(RUN)
+#undef RUN
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+int attention_core_bwd_pre(int n_seq, int L, int nh, int dh, const float* qkv, const float* dy, float* dqkv,
+                           cudaStream_t st) {
+  if (n_seq <= 0) return EBK_OK;
+  EBK_CHECK_ARG(attention_pre_supported(L, dh, qkv, dy, dqkv), "attention_pre: unsupported shape L=%d dh=%d", L, dh);
+  const long total = (long)n_seq * nh;
+  int grid;
+#define RUN(DH_)                                                                                  \
+  {                                                                                               \
+    const size_t smem = (size_t)WARPS * (2 * 4 * Cfg<DH_>::MAT + LP * PS) * sizeof(float);        \
+    EBK_TRY(cfg(attn_bwd_pre_kernel<DH_>, smem, total, &grid));                                   \
+    attn_bwd_pre_kernel<DH_><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, qkv, dy, dqkv);        \
+  }
+  EBK_ATT_DISPATCH(RUN)
+#undef RUN
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+}  // namespace ebk

@@ -111,6 +111,60 @@ __global__ void __launch_bounds__(PT) attpool_bwd_kernel(int L, int D, int att, 
   }
 }
 
+// TMA-path AttLayer2 backward tail: one CTA per sequence.
+//   dw_t = X_t . g;  da_t = w_t (dw_t - sum_j w_j dw_j);  dpre[t, j] = tf32(da_t q_j (1 - h_tj^2))
+//   colpart[n, j] = sum_t dpre[t, j];  colpart[n, att + j] = sum_t h_tj da_t     (deterministic partials)
+__global__ void __launch_bounds__(PT) attpool_bwd_fused_kernel(int L, int D, int att, const float* __restrict__ y0,
+                                                                const float* __restrict__ hbuf,
+                                                                const float* __restrict__ attq,
+                                                                const float* __restrict__ w,
+                                                                const float* __restrict__ d_out,
+                                                                float* __restrict__ da, float* __restrict__ dpre,
+                                                                float* __restrict__ colpart) {
+  __shared__ float dw_s[64];
+  __shared__ float da_s[64];
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = PT / 32;
+  const float4* g4 = reinterpret_cast<const float4*>(d_out + (long)n * D);
+  const int D4 = D >> 2;
+  for (int t = warp; t < L; t += nwarp) {
+    const float4* x4 = reinterpret_cast<const float4*>(y0 + ((long)n * L + t) * D);
+    float acc = 0.0f;
+    for (int d = lane; d < D4; d += 32) {
+      const float4 x = __ldg(x4 + d), gd = __ldg(g4 + d);
+      acc = fmaf(x.x, gd.x, fmaf(x.y, gd.y, fmaf(x.z, gd.z, fmaf(x.w, gd.w, acc))));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) dw_s[t] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float s = 0.0f;
+    for (int t = lane; t < L; t += 32) s = fmaf(w[(long)n * L + t], dw_s[t], s);
+    s = warp_sum(s);
+    for (int t = lane; t < L; t += 32) {
+      const float v = w[(long)n * L + t] * (dw_s[t] - s);
+      da_s[t] = v;
+      da[(long)n * L + t] = v;
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < att; j += PT) {
+    const float qj = attq[j];
+    float sb = 0.0f, sq = 0.0f;
+    for (int t = 0; t < L; ++t) {
+      const long r = (long)n * L + t;
+      const float h = hbuf[r * att + j];
+      const float v = round_tf32_bits(da_s[t] * qj * (1.0f - h * h));
+      dpre[r * att + j] = v;
+      sb += v;
+      sq = fmaf(h, da_s[t], sq);
+    }
+    colpart[(long)n * 2 * att + j] = sb;
+    colpart[(long)n * 2 * att + att + j] = sq;
+  }
+}
+
 // Two-stage deterministic column reduction: partial[blk, j] then out[j] += sum_blk.
 constexpr int CS_ROWS = 256;
 __global__ void colsum_partial_kernel(int R, int Ncols, const float* __restrict__ X, int ldx,
@@ -216,6 +270,15 @@ int attpool_bwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop,
   EBK_CHECK_ARG(L <= 64, "attpool: L=%d > 64", L);
   attpool_bwd_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, drop, hbuf, attq, w, d_out, dout_ld > 0 ? dout_ld : D, da, dpre, dy,
                                            round_dpre);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+int attpool_bwd_fused(int n_seq, int L, int D, int att, const float* y0, const float* hbuf, const float* attq,
+                      const float* w, const float* d_out, float* da, float* dpre, float* colpart, cudaStream_t st) {
+  if (n_seq <= 0) return EBK_OK;
+  EBK_CHECK_ARG(L <= 64 && D % 4 == 0, "attpool: L=%d > 64 or D=%d not a multiple of 4", L, D);
+  attpool_bwd_fused_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, hbuf, attq, w, d_out, da, dpre, colpart);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

@@ -184,9 +184,18 @@ int gemm_dispatch(int math, const GemmOperandA& A, const float* B, int ldb, bool
                   const float* B_lo = nullptr);
 // All-TMA tcgen05 GEMM on dense operands that already hold tf32-representable values (gemm_tma_sm100.cu):
 // C (+)= alpha * opA(A) . opB(B); beta in {0,1}; tall: 256-row tiles (halves the L2 traffic of B)
+// Optional fused epilogue (beta == 0 only), applied in this order to v = alpha * acc:
+//   v += rowscale[row] * rowvec[(row / L) * rowvec_ld + col]   (if rowscale)
+//   v *= dropout factor of element row * drop_ld + col            (if drop.on())
+//   v  = tf32(v)                                                   (if round_out: C feeds another tensor-core op)
+struct GemmEpilogue {
+  const float* rowscale; const float* rowvec; int rowvec_ld; int L;
+  Dropout drop; int drop_ld;
+  bool round_out;
+};
 bool gemm_tma_eligible(const float* A, int lda, const float* B, int ldb, int M, int N, int K);
 int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool transB, float* C, int ldc, int M,
-             int N, int K, float beta, float alpha, cudaStream_t st, int tall = 0);
+             int N, int K, float beta, float alpha, cudaStream_t st, int tall = 0, const GemmEpilogue* epi = nullptr);
 // hi[i] = tf32(src[i]) (round to nearest), lo[i] = src[i] - hi[i]
 int split_tf32_copy(float* hi, float* lo, const float* src, size_t n, cudaStream_t st);
 // dst[i] = round-to-nearest-tf32(src[i])  (so that the tensor core's truncation is exact)
@@ -209,6 +218,13 @@ int attention_core_bwd_mma(int n_seq, int L, int nh, int dh, const float* qkv, c
                            float* dqkv, bool round_out, cudaStream_t st, float* dqkv_packed = nullptr,
                            int packed_bn = 0);
 
+// TMA-path attention (attention_pre.cu): qkv / dy already hold tf32 values (dy already dropout-masked);
+// cp.async double-buffered staging, register-resident A / dS.  fwd stores tf32(dropout(y)); bwd stores tf32(dqkv).
+bool attention_pre_supported(int L, int dh, const void* p0, const void* p1, const void* p2);
+int attention_core_fwd_pre(int n_seq, int L, int nh, int dh, const float* qkv, float* y, Dropout drop_out, cudaStream_t st);
+int attention_core_bwd_pre(int n_seq, int L, int nh, int dh, const float* qkv, const float* dy, float* dqkv,
+                           cudaStream_t st);
+
 // AttLayer2 pieces
 int attpool_fwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, float* hbuf /*[R,att] in: pre-act, out: tanh*/,
                 const float* attb, const float* attq, float* w /*[R]*/, float* out /*[n_seq,out_ld]*/, cudaStream_t st,
@@ -217,6 +233,10 @@ int attpool_bwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop,
                 const float* attq, const float* w, const float* d_out, float* da /*[R]*/,
                 float* dpre /*[R,att]*/, float* dy /*[R,D] = w_t*d_out*/, bool round_dpre, cudaStream_t st,
                 int dout_ld = 0 /*0 => D*/);
+// TMA-path variant: y0 is already dropout(Y0); dy is NOT written (the dpre.W^T GEMM adds w_t*d_out in its
+// epilogue); per-sequence column sums of dpre and of h*da go to colpart [n_seq, 2*att] (dattb | dattq partials)
+int attpool_bwd_fused(int n_seq, int L, int D, int att, const float* y0, const float* hbuf, const float* attq,
+                      const float* w, const float* d_out, float* da, float* dpre, float* colpart, cudaStream_t st);
 // column sums: out[j] += sum_r coef[r] * X[r,j]   (coef may be NULL => 1); deterministic
 // two-stage reduction through `partial` (colsum_partial_floats(R, Ncols) floats of scratch)
 int colsum_accum_ws(int R, int Ncols, const float* X, int ldx, const float* coef, float* out, float* partial,

@@ -52,6 +52,7 @@ struct TParams {
   int ksteps_total, ksteps_per_split;
   int out_mode;        // 0 store, 1 load-add-store (beta = 1), 2 red.add (split-K)
   float alpha;
+  GemmEpilogue epi;    // optional fused epilogue (out_mode 0 only)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -335,6 +336,27 @@ __global__ void __launch_bounds__(THREADS, 1)
           if (row < p.M) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] *= alpha;
+            if (p.epi.rowscale != nullptr) {
+              // + rowscale[row] * rowvec[row / L, col]   (AttLayer2 backward: w_t * d_out[n, :])
+              const float rs = __ldg(p.epi.rowscale + row);
+              const float* vec = p.epi.rowvec + (long)(row / p.epi.L) * p.epi.rowvec_ld + n0 + c0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (n0 + c0 + i < p.N) v[i] = fmaf(rs, __ldg(vec + i), v[i]);
+            }
+            if (p.epi.drop.on()) {
+              // inverted-dropout mask and scale of element (row, col): index row * drop_ld + col
+              const uint64_t g0 = ((uint64_t)row * (uint64_t)p.epi.drop_ld + (uint64_t)(n0 + c0)) >> 2;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 f = p.epi.drop.factor4_group(g0 + q);
+                v[q * 4] *= f.x; v[q * 4 + 1] *= f.y; v[q * 4 + 2] *= f.z; v[q * 4 + 3] *= f.w;
+              }
+            }
+            if (p.epi.round_out) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = round_tf32_bits(v[i]);
+            }
             if (vec8_ok && n0 + c0 + 15 < p.N) {
               asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + c0), "f"(v[0]), "f"(v[1]),
                            "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
@@ -476,7 +498,7 @@ bool gemm_tma_eligible(const float* A, int lda, const float* B, int ldb, int M, 
 // bits of whatever it is given).  transA: A is stored [K, M]; transB: B is stored [N, K].
 // tall: 1 selects 256-row tiles (MT = 2), 0 128-row tiles, -1 picks by problem size.
 int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool transB, float* C, int ldc, int M,
-             int N, int K, float beta, float alpha, cudaStream_t st, int tall) {
+             int N, int K, float beta, float alpha, cudaStream_t st, int tall, const GemmEpilogue* epi) {
   if (M <= 0 || N <= 0) return EBK_OK;
   EBK_CHECK_ARG(A && B && C && K >= 1, "gemm_tma: null operand or K < 1");
   EBK_CHECK_ARG(gemm_tma_eligible(A, lda, B, ldb, M, N, K), "gemm_tma: operands must be 16-byte aligned with ld %% 4 == 0");
@@ -497,6 +519,10 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   const int MT = tall ? 2 : 1;
   TParams p;
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.alpha = alpha;
+  p.epi = epi ? *epi : GemmEpilogue{nullptr, nullptr, 0, 1, Dropout{0, 0, 1.0f}, 0, false};
+  const bool has_epi = p.epi.rowscale != nullptr || p.epi.drop.on() || p.epi.round_out;
+  EBK_CHECK_ARG(!has_epi || beta == 0.0f, "gemm_tma: a fused epilogue needs beta == 0");
+  EBK_CHECK_ARG(!p.epi.drop.on() || p.epi.drop_ld % 4 == 0, "gemm_tma: dropout epilogue needs drop_ld %% 4 == 0");
   const int ntn = ceil_div(N, 256);
   p.BN = ceil_div(ceil_div(N, ntn), 16) * 16;
   p.tiles_n = ceil_div(N, p.BN);
@@ -510,7 +536,7 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   p.stages = stages;
   const long tiles = (long)p.tiles_m * p.tiles_n;
   int splitk = 1;
-  if (tiles < g_sms && p.ksteps_total >= 16) {
+  if (tiles < g_sms && p.ksteps_total >= 16 && !has_epi) {
     splitk = (int)(g_sms / tiles);  // fill the machine in ONE wave of equal items
     const int maxsplit = p.ksteps_total / 8;
     if (splitk > maxsplit) splitk = maxsplit;
