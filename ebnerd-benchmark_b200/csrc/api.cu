@@ -315,8 +315,9 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
     // dY0 = tf32(dropout2'(w_t d_out + dpre W^T)): pooling term, dropout backward and the rounding for the
     // attention kernel all happen in the GEMM epilogue
     const GemmEpilogue dy_epi{ws.w, d_out, D, d->L, drop2, D, true};
+    // (128-row tiles: this GEMM is epilogue-bound, so the double-buffered accumulator matters more than B traffic)
     EBK_PROF(T_ATT_DGRAD, gemm_tma(ws.dpre, d->att, false, ws.attw_r, d->att, true, ws.dy, D, R, D, d->att, 0.0f, 1.0f, st,
-                                   -1, &dy_epi));
+                                   0, &dy_epi));
     // SelfAttention core backward
     if (attention_pre_supported(d->L, d->dh, ws.qkv, ws.dy, ws.dqkv)) {
       EBK_PROF(T_ATTN_BWD, attention_core_bwd_pre(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, ws.dqkv, st));

@@ -2,8 +2,9 @@
 // operands that are ALREADY tf32 values: the QKV projection and the AttLayer2 dgrad GEMM round (and, for dY,
 // dropout-mask) their outputs in their epilogues, so this file only moves data and multiplies:
 //   * one warp per (sequence, head); Q, K, V (and dO) go global -> shared with 16-byte cp.async straight
-//     into the fragment-friendly layout, DOUBLE-BUFFERED: the loads of the warp's next item are in flight
-//     while the current one is computed (the previous kernels exposed one full memory round trip per item);
+//     into the fragment-friendly layout (zero-filled padding included, so the buffers can be re-used as
+//     scratch); STAGES = 2 keeps the loads of the warp's next item in flight while the current one is
+//     computed, STAGES = 1 spends the shared memory on more resident warps instead;
 //   * 32x32xDH products on mma.sync.m16n8k8 tf32; the softmax / dS algebra stays in the accumulator
 //     registers;
 //   * A and dS feed the next products (dV = A dO, dQ = dS K) DIRECTLY from the accumulator registers:
@@ -12,6 +13,8 @@
 //     through a 32x40 shared tile.
 // Shared-memory row stride ST: DH (=20) or DH+4, chosen so that the 8 rows x 4 columns touched by one
 // fragment load fall into 32 distinct banks.
+#include <stdlib.h>
+
 #include "ebk_common.cuh"
 
 namespace ebk {
@@ -37,21 +40,28 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 }
 __device__ __forceinline__ uint32_t u(float x) { return __float_as_uint(x); }
 __device__ __forceinline__ uint32_t ur(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }  // tf32 round
-__device__ __forceinline__ void cp16(float* dst, const float* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+// 16-byte async copy; bytes == 0 writes zeros (the source is not read)
+__device__ __forceinline__ void cp16(float* dst, const float* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(bytes)
                : "memory");
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// issue the cp.async copies of NM [L, DH] slices (global row strides ld[m]) into dst + m * MAT
+// issue the cp.async copies of NM [L, DH] slices (global row strides ld[m]) into dst + m * MAT; every
+// 16-byte chunk of the [32][ST] tiles is written (rows >= L and columns >= DH with zeros)
 template <int DH, int NM>
 __device__ __forceinline__ void stage_async(float* dst, const float* const (&src)[NM], const long (&ld)[NM], int L, int lane) {
-  constexpr int CPR = DH / 4, ST = Cfg<DH>::ST, MAT = Cfg<DH>::MAT;
-  for (int i = lane; i < L * CPR; i += 32) {
-    const int t = i / CPR, j = i - t * CPR;
+  constexpr int ST = Cfg<DH>::ST, CPR = ST / 4, MAT = Cfg<DH>::MAT;
 #pragma unroll
-    for (int m = 0; m < NM; ++m) cp16(dst + m * MAT + t * ST + j * 4, src[m] + (long)t * ld[m] + j * 4);
+  for (int it = 0; it < LP * CPR / 32; ++it) {
+    const int i = lane + it * 32;
+    const int t = i / CPR, j = i - t * CPR;
+    const bool ok = t < L && j * 4 < DH;
+#pragma unroll
+    for (int m = 0; m < NM; ++m)
+      cp16(dst + m * MAT + t * ST + j * 4, ok ? src[m] + (long)t * ld[m] + j * 4 : src[m], ok ? 16u : 0u);
   }
 }
 
@@ -229,17 +239,15 @@ __device__ __forceinline__ void store_rows(const float (&acc)[2][Cfg<DH>::NT][4]
     }
 }
 
-template <int DH>
+template <int DH, int STAGES>
 __global__ void __launch_bounds__(WARPS * 32) attn_fwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
                                                                   float* __restrict__ y, Dropout drop) {
   extern __shared__ __align__(16) float smem[];
   constexpr int MAT = Cfg<DH>::MAT;
-  constexpr int PER_WARP = 2 * 3 * MAT + LP * PS;
+  constexpr int PER_WARP = STAGES * 3 * MAT;
+  static_assert(2 * MAT >= LP * PS, "the score tile overlays Q and K");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   float* base_s = smem + warp * PER_WARP;
-  float* Ps = base_s + 2 * 3 * MAT;
-  for (int i = lane; i < 2 * 3 * MAT; i += 32) base_s[i] = 0.0f;  // zero padding rows / columns once
-  __syncwarp();
   const int D = nh * DH;
   const float inv = rsqrtf((float)DH);
   const long total = (long)n_seq * nh;
@@ -254,23 +262,30 @@ __global__ void __launch_bounds__(WARPS * 32) attn_fwd_pre_kernel(int n_seq, int
     cp_commit();
   };
   int buf = 0;
-  if (item < total) issue(item, 0);
+  if (STAGES == 2 && item < total) issue(item, 0);
   for (; item < total; item += stride) {
-    const long next = item + stride;
-    if (next < total) {
-      issue(next, buf ^ 1);
-      cp_wait<1>();
+    if (STAGES == 2) {
+      const long next = item + stride;
+      if (next < total) {
+        issue(next, buf ^ 1);
+        cp_wait<1>();
+      } else {
+        cp_wait<0>();
+      }
     } else {
+      issue(item, 0);
       cp_wait<0>();
     }
     __syncwarp();
     const int n = (int)(item / nh), h = (int)(item - (long)n * nh);
-    const float* Qs = base_s + buf * 3 * MAT;
+    float* Qs = base_s + buf * 3 * MAT;
     const float* Ks = Qs + MAT;
     const float* Vs = Ks + MAT;
+    float* Ps = Qs;  // overlays Q and K once the scores are in registers
     float acc[2][4][4];
     gemm_xyT<DH>(acc, Qs, Ks, g, t);
     softmax_rows(acc, inv, L, t);
+    __syncwarp();  // everyone is done reading Q / K
     store_frag(Ps, acc, g, t);
     __syncwarp();
     float o[2][Cfg<DH>::NT][4];
@@ -296,22 +311,19 @@ __global__ void __launch_bounds__(WARPS * 32) attn_fwd_pre_kernel(int n_seq, int
           *reinterpret_cast<uint2*>(out + (long)r * D + col) = make_uint2(ur(v.x), ur(v.y));
         }
       }
-    __syncwarp();  // everyone is done with this buffer and with Ps before they are overwritten
-    buf ^= 1;
+    __syncwarp();  // everyone is done with this buffer before it is overwritten
+    if (STAGES == 2) buf ^= 1;
   }
 }
 
-template <int DH>
+template <int DH, int STAGES>
 __global__ void __launch_bounds__(WARPS * 32) attn_bwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
                                                                   const float* __restrict__ dy, float* __restrict__ dqkv) {
   extern __shared__ __align__(16) float smem[];
   constexpr int MAT = Cfg<DH>::MAT;
-  constexpr int PER_WARP = 2 * 4 * MAT + LP * PS;
+  constexpr int PER_WARP = STAGES * 4 * MAT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   float* base_s = smem + warp * PER_WARP;
-  float* Ds = base_s + 2 * 4 * MAT;
-  for (int i = lane; i < 2 * 4 * MAT; i += 32) base_s[i] = 0.0f;
-  __syncwarp();
   const int D = nh * DH;
   const float inv = rsqrtf((float)DH);
   const long total = (long)n_seq * nh;
@@ -326,13 +338,18 @@ __global__ void __launch_bounds__(WARPS * 32) attn_bwd_pre_kernel(int n_seq, int
     cp_commit();
   };
   int buf = 0;
-  if (item < total) issue(item, 0);
+  if (STAGES == 2 && item < total) issue(item, 0);
   for (; item < total; item += stride) {
-    const long next = item + stride;
-    if (next < total) {
-      issue(next, buf ^ 1);
-      cp_wait<1>();
+    if (STAGES == 2) {
+      const long next = item + stride;
+      if (next < total) {
+        issue(next, buf ^ 1);
+        cp_wait<1>();
+      } else {
+        cp_wait<0>();
+      }
     } else {
+      issue(item, 0);
       cp_wait<0>();
     }
     __syncwarp();
@@ -340,8 +357,9 @@ __global__ void __launch_bounds__(WARPS * 32) attn_bwd_pre_kernel(int n_seq, int
     const long row0 = (long)n * L;
     const float* Qs = base_s + buf * 4 * MAT;
     const float* Ks = Qs + MAT;
-    const float* Vs = Ks + MAT;
+    float* Vs = base_s + buf * 4 * MAT + 2 * MAT;
     const float* Gs = Vs + MAT;  // dO
+    float* Ds = Vs;              // dS overlays V and dO once dV is done
     float a_acc[2][4][4], d_acc[2][4][4];
     gemm_xyT<DH>(a_acc, Qs, Ks, g, t);   // A = softmax(Q K^T / sqrt(dh))
     softmax_rows(a_acc, inv, L, t);
@@ -364,17 +382,18 @@ __global__ void __launch_bounds__(WARPS * 32) attn_bwd_pre_kernel(int n_seq, int
           for (int e = 0; e < 2; ++e)
             d_acc[mt][nt][hf * 2 + e] = a_acc[mt][nt][hf * 2 + e] * (d_acc[mt][nt][hf * 2 + e] - dot);
       }
-    store_frag(Ds, d_acc, g, t);  // only the transposed use (dK) needs dS in shared memory
     float o[2][Cfg<DH>::NT][4];
     gemm_regP<DH>(o, a_acc, Gs, g, t);   // dV[q, d] = sum_k A[q, k] dO[k, d]
     store_rows<DH>(o, 1.0f, dqkv, row0, 3 * D, 2 * D + h * DH, L, g, t);
+    __syncwarp();                        // everyone is done reading V and dO
+    store_frag(Ds, d_acc, g, t);         // only the transposed use (dK) needs dS in shared memory
     gemm_regP<DH>(o, d_acc, Ks, g, t);   // dQ[q, d] = sum_k dS[q, k] K[k, d] / sqrt(dh)
     store_rows<DH>(o, inv, dqkv, row0, 3 * D, h * DH, L, g, t);
     __syncwarp();
     gemm_smemT<DH>(o, Ds, Qs, g, t);     // dK[k, d] = sum_q dS[q, k] Q[q, d] / sqrt(dh)
     store_rows<DH>(o, inv, dqkv, row0, 3 * D, D + h * DH, L, g, t);
     __syncwarp();
-    buf ^= 1;
+    if (STAGES == 2) buf ^= 1;
   }
 }
 
@@ -385,10 +404,23 @@ int cfg(Kern kern, size_t smem, long total, int* grid) {
     set_error("attention_pre: smem %zu: %s", smem, cudaGetErrorString(e));
     return EBK_ERR_CUDA;
   }
+  int dev = 0, sms = 0, occ = 0;
+  EBK_CUDA(cudaGetDevice(&dev));
+  EBK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  EBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
   const long blocks = (total + WARPS - 1) / WARPS;
-  const long cap = 148L * 2;  // persistent: two CTAs per SM, every warp walks its items with a prefetch in flight
+  const long cap = (long)sms * (occ > 0 ? occ : 1);  // persistent: every resident warp walks its items
   *grid = (int)(blocks < cap ? blocks : cap);
   return EBK_OK;
+}
+
+int att_stages() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EBK_ATT_STAGES");
+    v = (e && e[0] == '2') ? 2 : 1;
+  }
+  return v;
 }
 
 }  // namespace
@@ -406,13 +438,15 @@ int attention_core_fwd_pre(int n_seq, int L, int nh, int dh, const float* qkv, f
   EBK_CHECK_ARG(attention_pre_supported(L, dh, qkv, y, qkv), "attention_pre: unsupported shape L=%d dh=%d", L, dh);
   const long total = (long)n_seq * nh;
   int grid;
-#define RUN(DH_)                                                                                  \
+#define RUN2(DH_, ST_)                                                                            \
   {                                                                                               \
-    const size_t smem = (size_t)WARPS * (2 * 3 * Cfg<DH_>::MAT + LP * PS) * sizeof(float);        \
-    EBK_TRY(cfg(attn_fwd_pre_kernel<DH_>, smem, total, &grid));                                   \
-    attn_fwd_pre_kernel<DH_><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, qkv, y, drop_out);     \
+    const size_t smem = (size_t)WARPS * (ST_ * 3 * Cfg<DH_>::MAT) * sizeof(float) + 64; /* n-tile overhang */ \
+    EBK_TRY(cfg(attn_fwd_pre_kernel<DH_, ST_>, smem, total, &grid));                              \
+    attn_fwd_pre_kernel<DH_, ST_><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, qkv, y, drop_out); \
   }
+#define RUN(DH_) { if (att_stages() == 2) RUN2(DH_, 2) else RUN2(DH_, 1) }
   EBK_ATT_DISPATCH(RUN)
+#undef RUN2
 #undef RUN
   EBK_LAUNCH_CHECK();
   return EBK_OK;
@@ -424,13 +458,15 @@ int attention_core_bwd_pre(int n_seq, int L, int nh, int dh, const float* qkv, c
   EBK_CHECK_ARG(attention_pre_supported(L, dh, qkv, dy, dqkv), "attention_pre: unsupported shape L=%d dh=%d", L, dh);
   const long total = (long)n_seq * nh;
   int grid;
-#define RUN(DH_)                                                                                  \
+#define RUN2(DH_, ST_)                                                                            \
   {                                                                                               \
-    const size_t smem = (size_t)WARPS * (2 * 4 * Cfg<DH_>::MAT + LP * PS) * sizeof(float);        \
-    EBK_TRY(cfg(attn_bwd_pre_kernel<DH_>, smem, total, &grid));                                   \
-    attn_bwd_pre_kernel<DH_><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, qkv, dy, dqkv);        \
+    const size_t smem = (size_t)WARPS * (ST_ * 4 * Cfg<DH_>::MAT) * sizeof(float) + 64; /* n-tile overhang */ \
+    EBK_TRY(cfg(attn_bwd_pre_kernel<DH_, ST_>, smem, total, &grid));                              \
+    attn_bwd_pre_kernel<DH_, ST_><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, qkv, dy, dqkv);   \
   }
+#define RUN(DH_) { if (att_stages() == 2) RUN2(DH_, 2) else RUN2(DH_, 1) }
   EBK_ATT_DISPATCH(RUN)
+#undef RUN2
 #undef RUN
   EBK_LAUNCH_CHECK();
   return EBK_OK;

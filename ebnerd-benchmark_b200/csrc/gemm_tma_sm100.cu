@@ -53,7 +53,10 @@ struct TParams {
   int out_mode;        // 0 store, 1 load-add-store (beta = 1), 2 red.add (split-K)
   float alpha;
   GemmEpilogue epi;    // optional fused epilogue (out_mode 0 only)
+  int rv_smem;         // 1: the rowvec rows of each epilogue warp are staged in shared memory (L >= 16)
 };
+constexpr int RV_ART = 4;                   // articles a warp's 32 rows can span when L >= 16
+constexpr int RV_WARP_FLOATS = RV_ART * 256; // per warp, per m-subtile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -317,9 +320,36 @@ __global__ void __launch_bounds__(THREADS, 1)
     const float alpha = p.alpha;
     const bool vec_base = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     const bool vec8_base = vec_base && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 31) == 0) && p.out_mode == 0;
+    // rowvec slab of this warp: [MT][RV_ART][BN] floats behind the stage ring
+    float* rv_s = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)S * stage_bytes) +
+                  (size_t)(warp - 2) * MT * RV_WARP_FLOATS;
     while (cu.valid(n_items)) {
       const int buf = NBUF == 2 ? (t & 1) : 0, use = NBUF == 2 ? (t >> 1) : t;
       const int n0 = cu.n0;
+      float rs_reg[MT];
+      int art0[MT];
+      if (p.epi.rowscale != nullptr) {
+        // operands of the fused epilogue that do not depend on the accumulator: fetched BEFORE waiting
+        // for the MMAs, so their latency hides behind the main loop
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int row_lo = cu.m0 + mt * BM + ew * 32, row = row_lo + lane;
+          rs_reg[mt] = row < p.M ? __ldg(p.epi.rowscale + row) : 0.0f;
+          art0[mt] = row_lo / p.epi.L;
+          if (p.rv_smem) {
+            const int art_last = (min(row_lo + 31, p.M - 1)) / p.epi.L;
+            for (int a = 0; a < RV_ART; ++a) {
+              const int art = art0[mt] + a;
+              for (int c = lane; c < BN; c += 32) {
+                float x = 0.0f;
+                if (art <= art_last && n0 + c < p.N) x = __ldg(p.epi.rowvec + (long)art * p.epi.rowvec_ld + n0 + c);
+                rv_s[(mt * RV_ART + a) * BN + c] = x;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
       mbar_wait_backoff(smem_u32(&tfull_bar[buf]), (uint32_t)(use & 1));
       tc_fence_after();
       const bool vec_ok = vec_base && ((n0 & 3) == 0);
@@ -338,11 +368,22 @@ __global__ void __launch_bounds__(THREADS, 1)
             for (int i = 0; i < 16; ++i) v[i] *= alpha;
             if (p.epi.rowscale != nullptr) {
               // + rowscale[row] * rowvec[row / L, col]   (AttLayer2 backward: w_t * d_out[n, :])
-              const float rs = __ldg(p.epi.rowscale + row);
-              const float* vec = p.epi.rowvec + (long)(row / p.epi.L) * p.epi.rowvec_ld + n0 + c0;
+              const float rs = rs_reg[mt];
+              if (p.rv_smem) {
+                const float4* vec = reinterpret_cast<const float4*>(
+                    rv_s + (mt * RV_ART + (row / p.epi.L - art0[mt])) * BN + c0);
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (n0 + c0 + i < p.N) v[i] = fmaf(rs, __ldg(vec + i), v[i]);
+                for (int q = 0; q < 4; ++q) {
+                  const float4 x = vec[q];
+                  v[q * 4] = fmaf(rs, x.x, v[q * 4]); v[q * 4 + 1] = fmaf(rs, x.y, v[q * 4 + 1]);
+                  v[q * 4 + 2] = fmaf(rs, x.z, v[q * 4 + 2]); v[q * 4 + 3] = fmaf(rs, x.w, v[q * 4 + 3]);
+                }
+              } else {
+                const float* vec = p.epi.rowvec + (long)(row / p.epi.L) * p.epi.rowvec_ld + n0 + c0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (n0 + c0 + i < p.N) v[i] = fmaf(rs, __ldg(vec + i), v[i]);
+              }
             }
             if (p.epi.drop.on()) {
               // inverted-dropout mask and scale of element (row, col): index row * drop_ld + col
@@ -400,6 +441,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&tempty_bar[buf]));  // buffer may be overwritten by the MMA warp
+      __syncwarp();                             // all lanes are done with the rowvec slab
       cu.next_item(p, n_items, gridDim.x);
       ++t;
     }
@@ -530,7 +572,9 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   p.tiles_m = ceil_div(M, BM * MT);
   p.ksteps_total = ceil_div(K, BK);
   const size_t stage_bytes = (size_t)MT * BM * BK * 4 + (size_t)p.b_rows * BK * 4;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  p.rv_smem = (p.epi.rowscale != nullptr && p.epi.L >= 16) ? 1 : 0;
+  const size_t rv_bytes = p.rv_smem ? (size_t)4 * MT * RV_WARP_FLOATS * sizeof(float) : 0;
+  int stages = (int)((200 * 1024 - rv_bytes) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) stages = 2;
   p.stages = stages;
@@ -558,7 +602,7 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   else       EBK_TRY(get_map(B, N, K, ldb, 32, true, &tmB));         // storage [K, N]
   const long n_items = tiles * splitk;
   const int grid = (int)(n_items < g_sms ? n_items : g_sms);
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + rv_bytes;
 #define LAUNCH3(AMN_, BMN_, MT_)                                                                               \
   {                                                                                                            \
     EBK_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<AMN_, BMN_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
