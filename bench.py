@@ -75,6 +75,55 @@ def flops_per_impression_fwd(w):
             + H * 6 * D * D + nh * 4 * H * H * dh + H * (2 * D * att + 2 * att) + 2 * C * D)
 
 
+def kernel_models(w, B, nparam):
+    """Algorithmic work of ONE launch of each kernel group at this workload:
+    ("tensor", flops) for the tensor-pipe-bound projections, ("hbm", bytes) for everything else."""
+    R = B * (w["H"] + w["C"]) * w["T"]
+    D, E, att = w["nh"] * w["dh"], w["E"], w["att"]
+    f = 4  # bytes per fp32
+    return {
+        "news.qkv_gemm_fwd": ("tensor", 2.0 * R * E * 3 * D),
+        "news.qkv_dgrad_gemm": ("tensor", 2.0 * R * E * 3 * D),
+        "news.qkv_wgrad_gemm": ("tensor", 2.0 * R * E * 3 * D),
+        # theta, g, m, v read; theta, m, v written, g cleared
+        "news.adam": ("hbm", 8.0 * f * nparam),
+        "news.attn_core_fwd": ("hbm", f * R * (3 * D + D)),
+        "news.attn_core_bwd": ("hbm", f * R * (3 * D + D + 3 * D)),
+        "news.embed_gather": ("hbm", f * R * 2 * E + 4 * R),
+        "news.embed_scatter": ("hbm", f * R * 3 * E + 4 * R),
+        "news.att_gemm_fwd": ("hbm", f * R * (D + att)),
+        "news.att_dgrad_gemm": ("hbm", f * R * (att + D)),
+        "news.att_wgrad_gemm": ("hbm", f * R * (D + att)),
+        "news.attpool_fwd": ("hbm", f * R * (2 * att + D)),
+        "news.attpool_bwd": ("hbm", f * R * (D + 2 * att)),
+    }
+
+
+def kernel_roofline(dom, prof, w, B, nparam, pk, step_prof_ms):
+    """`roofline` object of the dominant kernel group: achieved = algorithmic bytes|flops per launch / the
+    CUDA-event duration measured live by the library profiler; traffic = dram bytes per launch from the
+    committed ncu --set full capture (profiles/r01_traffic.json), or null."""
+    model = kernel_models(w, B, nparam).get(dom)
+    if model is None:
+        return None
+    bound, amount = model
+    ms = prof[dom][0] / max(1, prof[dom][1])
+    traffic = None
+    tf = ROOT / "profiles" / "r01_traffic.json"
+    if tf.exists():
+        traffic = json.loads(tf.read_text()).get(dom)
+    if bound == "tensor":
+        ach = amount / (ms * 1e-3) / 1e12
+        return {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": ach / pk["tensor"], "traffic": traffic, "algorithmic_flops": amount,
+                "peak_source": f"{pk['src']} bf16 sustained (the kernel computes in tf32, nominally half the bf16 rate)",
+                "share_of_step": prof[dom][0] / step_prof_ms, "ms_per_launch": ms}
+    ach = amount / (ms * 1e-3) / 1e9
+    return {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+            "traffic": traffic, "algorithmic_bytes": amount, "peak_source": pk["src"],
+            "share_of_step": prof[dom][0] / step_prof_ms, "ms_per_launch": ms}
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled through NVML DURING the timed region (B200_PROFILING.md)."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
@@ -269,7 +318,7 @@ def run_ours(args, w, wname):
         eng.train_step_dev(dev[i % n_pool][0], dev[i % n_pool][1], B, C_)
     torch.cuda.synchronize()
     if rank == 0:
-        prof = {k: (ms_ / psteps, c // psteps) for k, (ms_, c) in _ebk.prof_collect().items()}
+        prof = {k: (ms_ / psteps, max(1, c // psteps)) for k, (ms_, c) in _ebk.prof_collect().items()}
         lib.ebk_prof_enable(0)
     sync_all()
 
@@ -283,27 +332,9 @@ def run_ours(args, w, wname):
         ms_step = ms_total / args.steps
         value = B * world * args.steps / (ms_total / 1e3)
         e2e_value = B * world * args.steps / (e2e_ms / 1e3)
-        R = B * (w["H"] + w["C"]) * w["T"]
-        D = w["nh"] * w["dh"]
-        gemm_flops = {"news.qkv_gemm_fwd": 2.0 * R * w["E"] * 3 * D, "news.qkv_dgrad_gemm": 2.0 * R * w["E"] * 3 * D,
-                      "news.qkv_wgrad_gemm": 2.0 * R * w["E"] * 3 * D}
         step_prof_ms = sum(v[0] for v in prof.values()) or 1.0
         dom = max(prof, key=lambda k: prof[k][0]) if prof else None
-        roof = None
-        if dom in gemm_flops:
-            ach = gemm_flops[dom] / (prof[dom][0] * 1e-3) / 1e12
-            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tensor"], "traffic": None,
-                    "peak_source": f"{pk['src']} bf16 sustained (kernel computes in tf32, nominal half-rate of bf16)",
-                    "share_of_step": prof[dom][0] / step_prof_ms, "ms_per_launch": prof[dom][0]}
-        elif dom is not None:
-            nparam = eng.params.n
-            byts = {"news.adam": 7.0 * 4 * nparam, "user.adam": 7.0 * 4 * nparam}.get(dom)
-            if byts:
-                ach = byts / (prof[dom][0] * 1e-3) / 1e9
-                roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
-                        "share_of_step": prof[dom][0] / step_prof_ms, "ms_per_launch": prof[dom][0]}
+        roof = kernel_roofline(dom, prof, w, B, eng.params.n, pk, step_prof_ms)
         bpi = bytes_per_impression(w)
         line = {
             "metric": "train_impressions_per_sec", "value": value, "unit": "impressions/s", "n_gpus": world,
@@ -326,6 +357,8 @@ def run_ours(args, w, wname):
                                      "peak": pk["tensor"], "unit": "TFLOP/s",
                                      "frac": value / world * 3 * flops_per_impression_fwd(w) / 1e12 / pk["tensor"]},
             "kernel_ms_per_step": {k: round(v[0], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+            "kernel_roofline_frac": {k: round(kernel_roofline(k, prof, w, B, eng.params.n, pk, step_prof_ms)["frac"], 3)
+                                     for k in prof if k in kernel_models(w, B, eng.params.n)},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -54,7 +54,9 @@ struct TParams {
   float alpha;
   GemmEpilogue epi;    // optional fused epilogue (out_mode 0 only)
   int rv_smem;         // 1: the rowvec rows of each epilogue warp are staged in shared memory (L >= 16)
+  int c_tma;           // 1: C has a tensor map -> the epilogue stores through shared memory + TMA
 };
+constexpr uint32_t STG_BYTES = 4u * 2u * 4096u;  // store staging: 4 epilogue warps x 2 x [32][128 B]
 constexpr int RV_ART = 4;                   // articles a warp's 32 rows can span when L >= 16
 constexpr int RV_WARP_FLOATS = RV_ART * 256; // per warp, per m-subtile
 
@@ -188,9 +190,93 @@ struct Cursor {
   }
 };
 
+// Per-row operands of the fused epilogue, fetched before the accumulator is ready.
+struct EpiRow {
+  float rs;          // rowscale[row]
+  const float* rv;   // rowvec row of this thread (shared-memory slab or global), indexed by tile column
+};
+
+// fused epilogue on 16 consecutive columns [n0 + c0, n0 + c0 + 16) of one row (see GemmEpilogue)
+__device__ __forceinline__ void epi_apply16(const TParams& p, const EpiRow& er, float* v, int row, int n0, int c0) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
+  if (p.epi.rowscale != nullptr && er.rv != nullptr) {
+    // + rowscale[row] * rowvec[row / L, col]   (AttLayer2 backward: w_t * d_out[n, :])
+    if (p.rv_smem) {
+      const float4* vec = reinterpret_cast<const float4*>(er.rv + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 x = vec[q];
+        v[q * 4] = fmaf(er.rs, x.x, v[q * 4]); v[q * 4 + 1] = fmaf(er.rs, x.y, v[q * 4 + 1]);
+        v[q * 4 + 2] = fmaf(er.rs, x.z, v[q * 4 + 2]); v[q * 4 + 3] = fmaf(er.rs, x.w, v[q * 4 + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (n0 + c0 + i < p.N) v[i] = fmaf(er.rs, __ldg(er.rv + c0 + i), v[i]);
+    }
+  }
+  if (p.epi.drop.on()) {
+    // inverted-dropout mask and scale of element (row, col): index row * drop_ld + col
+    const uint64_t g0 = ((uint64_t)row * (uint64_t)p.epi.drop_ld + (uint64_t)(n0 + c0)) >> 2;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 f = p.epi.drop.factor4_group(g0 + q);
+      v[q * 4] *= f.x; v[q * 4 + 1] *= f.y; v[q * 4 + 2] *= f.z; v[q * 4 + 3] *= f.w;
+    }
+  }
+  if (p.epi.round_out) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = round_tf32_bits(v[i]);
+  }
+}
+
+// row-per-thread global stores of 16 columns (no tensor map for C, or the 16-column tail of a tile)
+__device__ __forceinline__ void store16_direct(const TParams& p, float* crow, const float* v, int n0, int c0, bool vec_ok,
+                                               bool vec8_ok) {
+  if (vec8_ok && n0 + c0 + 15 < p.N) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + c0), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + c0 + 8), "f"(v[8]), "f"(v[9]),
+                 "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+                 : "memory");
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int col = c0 + q * 4;
+    if (n0 + col >= p.N) break;
+    float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    if (vec_ok && n0 + col + 3 < p.N) {
+      float4* dst = reinterpret_cast<float4*>(crow + col);
+      if (p.out_mode == 0) {
+        *dst = o;
+      } else if (p.out_mode == 1) {
+        float4 c = *dst;
+        c.x += o.x; c.y += o.y; c.z += o.z; c.w += o.w;
+        *dst = c;
+      } else {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                     : "memory");
+      }
+    } else {
+      const float oe[4] = {o.x, o.y, o.z, o.w};
+      for (int e = 0; e < 4; ++e) {
+        if (n0 + col + e >= p.N) break;
+        float* dst = crow + col + e;
+        if (p.out_mode == 0) *dst = oe[e];
+        else if (p.out_mode == 1) *dst += oe[e];
+        else atomicAdd(dst, oe[e]);
+      }
+    }
+  }
+}
+
 template <bool A_MN, bool B_MN, int MT>
 __global__ void __launch_bounds__(THREADS, 1)
-    gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TParams p) {
+    gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const TParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -220,6 +306,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (p.c_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
@@ -313,39 +400,53 @@ __global__ void __launch_bounds__(THREADS, 1)
     __syncwarp();
   } else {
     // ===================== epilogue (warps 2-5; TMEM lane quarter = warp & 3) =====================
+    // TMEM -> registers -> (fused ops) -> 32x32 swizzled staging tile in shared memory -> TMA store
+    // (cp.async.bulk.tensor, or its .add reduction for beta = 1 / split-K).  A thread owns one accumulator
+    // ROW, so direct global stores touch 32 different cache lines per instruction -- measured, they kept the
+    // LSU busy ~8k cycles per 256x240 tile with the tensor pipe idle; the TMA store writes whole 128-byte
+    // lines and clips at the matrix edge by itself.
     const int ew = warp & 3;
     Cursor<MT> cu;
     cu.init(p, blockIdx.x, n_items);
     int t = 0;
-    const float alpha = p.alpha;
     const bool vec_base = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     const bool vec8_base = vec_base && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 31) == 0) && p.out_mode == 0;
-    // rowvec slab of this warp: [MT][RV_ART][BN] floats behind the stage ring
-    float* rv_s = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)S * stage_bytes) +
-                  (size_t)(warp - 2) * MT * RV_WARP_FLOATS;
+    uint8_t* tail = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)S * stage_bytes;   // behind the stage ring
+    // rowvec slab of this warp: [MT][RV_ART][BN] floats
+    float* rv_s = reinterpret_cast<float*>(tail + STG_BYTES) + (size_t)(warp - 2) * MT * RV_WARP_FLOATS;
+    // store staging of this warp: 2 x [32 rows][128 B], SWIZZLE_128B
+    const uint32_t stg = smem_base + (uint32_t)S * stage_bytes + (uint32_t)(warp - 2) * 2u * 4096u;
+    int nstore = 0;  // TMA stores issued by this warp (lane 0 tracks the bulk groups)
     while (cu.valid(n_items)) {
       const int buf = NBUF == 2 ? (t & 1) : 0, use = NBUF == 2 ? (t >> 1) : t;
       const int n0 = cu.n0;
-      float rs_reg[MT];
-      int art0[MT];
+      EpiRow er[MT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        er[mt].rs = 0.0f;
+        er[mt].rv = nullptr;
+      }
       if (p.epi.rowscale != nullptr) {
         // operands of the fused epilogue that do not depend on the accumulator: fetched BEFORE waiting
         // for the MMAs, so their latency hides behind the main loop
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const int row_lo = cu.m0 + mt * BM + ew * 32, row = row_lo + lane;
-          rs_reg[mt] = row < p.M ? __ldg(p.epi.rowscale + row) : 0.0f;
-          art0[mt] = row_lo / p.epi.L;
+          er[mt].rs = row < p.M ? __ldg(p.epi.rowscale + row) : 0.0f;
+          const int art0 = row_lo / p.epi.L;
           if (p.rv_smem) {
             const int art_last = (min(row_lo + 31, p.M - 1)) / p.epi.L;
             for (int a = 0; a < RV_ART; ++a) {
-              const int art = art0[mt] + a;
+              const int art = art0 + a;
               for (int c = lane; c < BN; c += 32) {
                 float x = 0.0f;
                 if (art <= art_last && n0 + c < p.N) x = __ldg(p.epi.rowvec + (long)art * p.epi.rowvec_ld + n0 + c);
                 rv_s[(mt * RV_ART + a) * BN + c] = x;
               }
             }
+            er[mt].rv = rv_s + (mt * RV_ART + (min(row, p.M - 1) / p.epi.L - art0)) * BN;
+          } else if (row < p.M) {
+            er[mt].rv = p.epi.rowvec + (long)(row / p.epi.L) * p.epi.rowvec_ld + n0;
           }
         }
         __syncwarp();
@@ -356,86 +457,53 @@ __global__ void __launch_bounds__(THREADS, 1)
       const bool vec8_ok = vec8_base && ((n0 & 7) == 0);
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const int row = cu.m0 + mt * BM + ew * 32 + lane;
+        const int row_lo = cu.m0 + mt * BM + ew * 32, row = row_lo + lane;
         const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (NBUF == 2 ? (uint32_t)buf * 256u : (uint32_t)mt * 256u);
+        int c0 = 0;
+        if (p.c_tma) {
+          for (; c0 + 32 <= BN && n0 + c0 < p.N; c0 += 32) {
+            float v[32];
+            tmem_ld16(tbase + (uint32_t)c0, v);
+            tmem_ld16(tbase + (uint32_t)c0 + 16u, v + 16);
+            epi_apply16(p, er[mt], v, row, n0, c0);
+            epi_apply16(p, er[mt], v + 16, row, n0, c0 + 16);
+            const uint32_t sb = stg + (uint32_t)(nstore & 1) * 4096u;
+            if (nstore >= 2) {  // the store that used this staging tile two chunks ago must have read it
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t dst = sb + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                           "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                           : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              if (p.out_mode == 0)
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&tmC),
+                             "r"(n0 + c0), "r"(row_lo), "r"(sb)
+                             : "memory");
+              else
+                asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&tmC),
+                             "r"(n0 + c0), "r"(row_lo), "r"(sb)
+                             : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++nstore;
+          }
+        }
+        // direct path: everything when C has no tensor map, else the 16-column tail of a tile
         float* crow = p.C + (long)row * p.ldc + n0;
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (; c0 < BN; c0 += 16) {
           if (n0 + c0 >= p.N) break;  // warp-uniform
           float v[16];
           tmem_ld16(tbase + (uint32_t)c0, v);  // warp-collective
           if (row < p.M) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= alpha;
-            if (p.epi.rowscale != nullptr) {
-              // + rowscale[row] * rowvec[row / L, col]   (AttLayer2 backward: w_t * d_out[n, :])
-              const float rs = rs_reg[mt];
-              if (p.rv_smem) {
-                const float4* vec = reinterpret_cast<const float4*>(
-                    rv_s + (mt * RV_ART + (row / p.epi.L - art0[mt])) * BN + c0);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float4 x = vec[q];
-                  v[q * 4] = fmaf(rs, x.x, v[q * 4]); v[q * 4 + 1] = fmaf(rs, x.y, v[q * 4 + 1]);
-                  v[q * 4 + 2] = fmaf(rs, x.z, v[q * 4 + 2]); v[q * 4 + 3] = fmaf(rs, x.w, v[q * 4 + 3]);
-                }
-              } else {
-                const float* vec = p.epi.rowvec + (long)(row / p.epi.L) * p.epi.rowvec_ld + n0 + c0;
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (n0 + c0 + i < p.N) v[i] = fmaf(rs, __ldg(vec + i), v[i]);
-              }
-            }
-            if (p.epi.drop.on()) {
-              // inverted-dropout mask and scale of element (row, col): index row * drop_ld + col
-              const uint64_t g0 = ((uint64_t)row * (uint64_t)p.epi.drop_ld + (uint64_t)(n0 + c0)) >> 2;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 f = p.epi.drop.factor4_group(g0 + q);
-                v[q * 4] *= f.x; v[q * 4 + 1] *= f.y; v[q * 4 + 2] *= f.z; v[q * 4 + 3] *= f.w;
-              }
-            }
-            if (p.epi.round_out) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = round_tf32_bits(v[i]);
-            }
-            if (vec8_ok && n0 + c0 + 15 < p.N) {
-              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + c0), "f"(v[0]), "f"(v[1]),
-                           "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-                           : "memory");
-              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + c0 + 8), "f"(v[8]),
-                           "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
-                           : "memory");
-              continue;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int col = c0 + q * 4;
-              if (n0 + col >= p.N) break;
-              float4 o = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-              if (vec_ok && n0 + col + 3 < p.N) {
-                float4* dst = reinterpret_cast<float4*>(crow + col);
-                if (p.out_mode == 0) {
-                  *dst = o;
-                } else if (p.out_mode == 1) {
-                  float4 c = *dst;
-                  c.x += o.x; c.y += o.y; c.z += o.z; c.w += o.w;
-                  *dst = c;
-                } else {
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y),
-                               "f"(o.z), "f"(o.w)
-                               : "memory");
-                }
-              } else {
-                const float oe[4] = {o.x, o.y, o.z, o.w};
-                for (int e = 0; e < 4; ++e) {
-                  if (n0 + col + e >= p.N) break;
-                  float* dst = crow + col + e;
-                  if (p.out_mode == 0) *dst = oe[e];
-                  else if (p.out_mode == 1) *dst += oe[e];
-                  else atomicAdd(dst, oe[e]);
-                }
-              }
-            }
+            epi_apply16(p, er[mt], v, row, n0, c0);
+            store16_direct(p, crow, v, n0, c0, vec_ok, vec8_ok);
           }
         }
       }
@@ -445,6 +513,8 @@ __global__ void __launch_bounds__(THREADS, 1)
       cu.next_item(p, n_items, gridDim.x);
       ++t;
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging must outlive its readers
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -574,7 +644,9 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   const size_t stage_bytes = (size_t)MT * BM * BK * 4 + (size_t)p.b_rows * BK * 4;
   p.rv_smem = (p.epi.rowscale != nullptr && p.epi.L >= 16) ? 1 : 0;
   const size_t rv_bytes = p.rv_smem ? (size_t)4 * MT * RV_WARP_FLOATS * sizeof(float) : 0;
-  int stages = (int)((200 * 1024 - rv_bytes) / stage_bytes);
+  p.c_tma = (ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
+  const size_t budget = 226 * 1024 - 1024 - STG_BYTES - rv_bytes;   // 227 KB per CTA minus barriers / alignment slack
+  int stages = (int)(budget / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) stages = 2;
   p.stages = stages;
@@ -602,12 +674,14 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   else       EBK_TRY(get_map(B, N, K, ldb, 32, true, &tmB));         // storage [K, N]
   const long n_items = tiles * splitk;
   const int grid = (int)(n_items < g_sms ? n_items : g_sms);
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + rv_bytes;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + STG_BYTES + rv_bytes;
+  CUtensorMap tmC = tmA;
+  if (p.c_tma) EBK_TRY(get_map(C, N, M, ldc, 32, false, &tmC));      // box {32 cols, 32 rows}, SWIZZLE_128B
 #define LAUNCH3(AMN_, BMN_, MT_)                                                                               \
   {                                                                                                            \
     EBK_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<AMN_, BMN_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)smem));                                                                 \
-    gemm_tma_kernel<AMN_, BMN_, MT_><<<grid, THREADS, smem, st>>>(tmA, tmB, p);                                \
+    gemm_tma_kernel<AMN_, BMN_, MT_><<<grid, THREADS, smem, st>>>(tmA, tmB, tmC, p);                                \
   }
 #define LAUNCH2(AMN_, BMN_)                  \
   {                                          \
