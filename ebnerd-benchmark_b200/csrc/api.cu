@@ -400,7 +400,10 @@ extern "C" int ebk_gemm_tma(int32_t transA, int32_t transB, int32_t tall, int32_
                             const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,
                             float beta, float alpha, void* stream) {
   EBK_CHECK_ARG(M >= 0 && N >= 0 && K >= 1 && A && B && C, "gemm_tma: bad argument");
-  return gemm_tma(A, lda, transA != 0, B, ldb, transB != 0, C, ldc, M, N, K, beta, alpha, (cudaStream_t)stream, tall);
+  // tall: bits 0-3 = tile mode (0 / 1 / 15 = auto), bits 4-7 = cluster mode (0 / 1 / 2 / 15 = auto)
+  const int tile = (tall & 15) == 15 ? -1 : (tall & 15), cl = ((tall >> 4) & 15) == 15 ? -1 : ((tall >> 4) & 15);
+  return gemm_tma(A, lda, transA != 0, B, ldb, transB != 0, C, ldc, M, N, K, beta, alpha, (cudaStream_t)stream, tile,
+                  nullptr, cl);
 }
 
 extern "C" int ebk_attention_core_fwd(int32_t n_seq, int32_t L, int32_t nh, int32_t dh, const float* qkv,

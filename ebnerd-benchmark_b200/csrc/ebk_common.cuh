@@ -195,7 +195,8 @@ struct GemmEpilogue {
 };
 bool gemm_tma_eligible(const float* A, int lda, const float* B, int ldb, int M, int N, int K);
 int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool transB, float* C, int ldc, int M,
-             int N, int K, float beta, float alpha, cudaStream_t st, int tall = 0, const GemmEpilogue* epi = nullptr);
+             int N, int K, float beta, float alpha, cudaStream_t st, int tall = 0, const GemmEpilogue* epi = nullptr,
+             int cluster = 0);
 // hi[i] = tf32(src[i]) (round to nearest), lo[i] = src[i] - hi[i]
 int split_tf32_copy(float* hi, float* lo, const float* src, size_t n, cudaStream_t st);
 // dst[i] = round-to-nearest-tf32(src[i])  (so that the tensor core's truncation is exact)

@@ -20,11 +20,24 @@
 //            blocks of consecutive mn groups follow each other: LBO = 4096, SBO = 512, k-advance = +1024 B.
 //   Out-of-range box elements are zero-filled by the TMA unit, so no tail code exists for M, N or K.
 //
+// PAIR (cta_group::2): measured, the 1-CTA kernel tops out near 62 % tensor-pipe activity because every byte
+// of A and B is written to AND read from the SM's shared memory once per MMA (154 KB per k-step of a
+// 256 x 240 tile against ~128 B/clk).  In PAIR mode two CTAs of a cluster (one TPC) form one 512-row
+// (MT = 2) tile: each stages its own A rows and only HALF of the B tile, and the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256) that feeds both tensor cores from both shared memories.  The peer's
+// TMA loads complete on the LEADER's full barrier (cp.async.bulk.tensor ... .cta_group::2), the leader's
+// tcgen05.commit multicasts to both CTAs' empty / accumulator-full barriers, both epilogues release the
+// accumulator on the leader's barrier.  (Plain operand MULTICAST between 1-CTA tiles was tried first: it
+// cuts L2 traffic but not shared-memory traffic and measured no gain, so it is not kept.)
+//
 // MT = 1: 128 x BN tiles, double-buffered accumulator (2 x 256 TMEM columns): the epilogue of tile i
 //         overlaps the main loop of tile i+1.
 // MT = 2: 256 x BN tiles (two M=128 MMAs per k-step sharing the B tile, 2 x 256 TMEM columns, single
 //         buffered): halves the L2->SM traffic of the B operand; used where B is the re-read operand.
 #include <cuda.h>  // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
+
+#include <stdlib.h>
+#include <string.h>
 
 #include <unordered_map>
 
@@ -106,6 +119,51 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// PAIR mode: the copy lands in THIS CTA's shared memory, its completion is counted on `bar`, a
+// shared::cluster address that may belong to the peer (leader) CTA
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// cta_group::2 commit: arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
@@ -134,7 +192,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A,B=tf32 [7,10)=[10,13)=2,
 // a_major bit15, b_major bit16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29).
-__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn, int n) {
+__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn, int n, int m = BM) {
   uint32_t d = 0;
   d |= 1u << 4;
   d |= 2u << 7;
@@ -142,7 +200,7 @@ __device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn, int n) {
   d |= (a_mn ? 1u : 0u) << 15;
   d |= (b_mn ? 1u : 0u) << 16;
   d |= (uint32_t)(n >> 3) << 17;
-  d |= (uint32_t)(BM >> 4) << 24;
+  d |= (uint32_t)(m >> 4) << 24;
   return d;
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
@@ -160,20 +218,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 // Walks this CTA's work items (m-tile, n-tile, k-split; n fastest so the CTAs that run at the same
 // time share the A rows in L2) k-step by k-step.
-template <int MT>
+template <int MT, bool PAIR>
 struct Cursor {
   int item, ks, ks_end, m0, n0;
+  int rm;  // rank of this CTA inside its pair (PAIR: an item is a tile of 2 x MT x 128 rows)
   __device__ __forceinline__ void load(const TParams& p) {
     const int per_m = p.tiles_n * p.splitk;
     const int tm = item / per_m, rem = item - tm * per_m;
     const int tn = rem / p.splitk, sp = rem - tn * p.splitk;
-    m0 = tm * BM * MT;
+    m0 = (tm * (PAIR ? 2 : 1) + rm) * BM * MT;
     n0 = tn * p.BN;
     ks = sp * p.ksteps_per_split;
     ks_end = min(p.ksteps_total, ks + p.ksteps_per_split);
   }
-  __device__ __forceinline__ void init(const TParams& p, int first, int n_items) {
+  __device__ __forceinline__ void init(const TParams& p, int first, int n_items, int rm_) {
     item = first;
+    rm = rm_;
     ks = ks_end = m0 = n0 = 0;
     if (item < n_items) load(p);
   }
@@ -273,7 +333,7 @@ __device__ __forceinline__ void store16_direct(const TParams& p, float* crow, co
   }
 }
 
-template <bool A_MN, bool B_MN, int MT>
+template <bool A_MN, bool B_MN, int MT, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
     gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const TParams p) {
@@ -293,6 +353,9 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int n_items = p.tiles_m * p.tiles_n * p.splitk;
+  constexpr int csize = PAIR ? 2 : 1;
+  const int rm = PAIR ? (int)cluster_ctarank() : 0;   // 0 = leader (issues the MMAs of the pair)
+  const int first_item = (int)blockIdx.x / csize, item_stride = (int)gridDim.x / csize;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
@@ -301,7 +364,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tfull_bar[b]), 1);
-      mbar_init(smem_u32(&tempty_bar[b]), EPI_THREADS);
+      mbar_init(smem_u32(&tempty_bar[b]), EPI_THREADS * csize);  // PAIR: both CTAs' epilogues release the leader
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -309,43 +372,71 @@ __global__ void __launch_bounds__(THREADS, 1)
     if (p.c_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
-                 "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                   "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                   "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // every barrier of the cluster exists before anyone signals a peer
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer (one thread) =====================
     if (lane == 0) {
-      Cursor<MT> cu;
-      cu.init(p, blockIdx.x, n_items);
+      Cursor<MT, PAIR> cu;
+      cu.init(p, first_item, n_items, rm);
       int s = 0;
       uint32_t ph = 0;
       while (cu.valid(n_items)) {
         const int k0 = cu.ks * BK;
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-        const uint32_t bar = smem_u32(&full_bar[s]);
-        mbar_expect_tx(bar, stage_bytes);
         const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
         const uint32_t sb = sa + a_bytes;
-        if (!A_MN) {
-          tma_load_2d(sa, &tmA, k0, cu.m0, bar);                       // box {32 k, 128*MT rows}
-        } else {
+        if (!PAIR) {
+          const uint32_t bar = smem_u32(&full_bar[s]);
+          mbar_expect_tx(bar, stage_bytes);
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, k0, cu.m0, bar);                       // box {32 k, 128*MT rows}
+          } else {
 #pragma unroll
-          for (int g = 0; g < 4 * MT; ++g) tma_load_2d(sa + (uint32_t)g * 4096u, &tmA, cu.m0 + 32 * g, k0, bar);
-        }
-        if (!B_MN) {
-          tma_load_2d(sb, &tmB, k0, cu.n0, bar);                       // box {32 k, b_rows rows}
+            for (int g = 0; g < 4 * MT; ++g) tma_load_2d(sa + (uint32_t)g * 4096u, &tmA, cu.m0 + 32 * g, k0, bar);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, k0, cu.n0, bar);                       // box {32 k, b_rows rows}
+          } else {
+            const int groups = p.b_rows >> 5;
+            for (int g = 0; g < groups; ++g) tma_load_2d(sb + (uint32_t)g * 4096u, &tmB, cu.n0 + 32 * g, k0, bar);
+          }
         } else {
-          const int groups = p.b_rows >> 5;
-          for (int g = 0; g < groups; ++g) tma_load_2d(sb + (uint32_t)g * 4096u, &tmB, cu.n0 + 32 * g, k0, bar);
+          // both CTAs' bytes are counted on the LEADER's barrier; this CTA stages its own A rows and its
+          // half of the B tile (columns n0 + rm * BN/2 ...) in its own shared memory
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+          if (rm == 0) mbar_expect_tx(smem_u32(&full_bar[s]), 2u * stage_bytes);
+          const int nb0 = cu.n0 + rm * (BN >> 1);
+          if (!A_MN) {
+            tma_load_2d_2sm(sa, &tmA, k0, cu.m0, bar);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4 * MT; ++g) tma_load_2d_2sm(sa + (uint32_t)g * 4096u, &tmA, cu.m0 + 32 * g, k0, bar);
+          }
+          if (!B_MN) {
+            tma_load_2d_2sm(sb, &tmB, k0, nb0, bar);                     // box {32 k, b_rows = BN/2 rows}
+          } else {
+            const int groups = p.b_rows >> 5;
+            for (int g = 0; g < groups; ++g) tma_load_2d_2sm(sb + (uint32_t)g * 4096u, &tmB, nb0 + 32 * g, k0, bar);
+          }
         }
-        cu.advance(p, n_items, gridDim.x);
+        cu.advance(p, n_items, item_stride);
         if (++s == S) {
           s = 0;
           ph ^= 1u;
@@ -355,13 +446,13 @@ __global__ void __launch_bounds__(THREADS, 1)
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(A_MN, B_MN, BN);
+    if (lane == 0 && rm == 0) {   // PAIR: only the leader CTA issues
+      const uint32_t idesc = make_idesc(A_MN, B_MN, BN, PAIR ? 2 * BM : BM);
       constexpr uint32_t a_lbo = A_MN ? 4096u : 16u, a_sbo = A_MN ? 512u : 1024u, a_lt = A_MN ? 1u : 2u;
       constexpr uint32_t b_lbo = B_MN ? 4096u : 16u, b_sbo = B_MN ? 512u : 1024u, b_lt = B_MN ? 1u : 2u;
       constexpr uint32_t a_kadv = A_MN ? 1024u : 32u, b_kadv = B_MN ? 1024u : 32u;  // bytes per UMMA_K
-      Cursor<MT> cu;
-      cu.init(p, blockIdx.x, n_items);
+      Cursor<MT, PAIR> cu;
+      cu.init(p, first_item, n_items, rm);
       int t = 0, s = 0;
       uint32_t ph = 0;
       while (cu.valid(n_items)) {
@@ -382,18 +473,23 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
               const uint32_t a_addr = sa + (uint32_t)mt * (uint32_t)(BM * BK * 4) + (uint32_t)k * a_kadv;
-              umma_tf32(tacc + (uint32_t)mt * 256u, make_desc(a_addr, a_lbo, a_sbo, a_lt), db, idesc, acc);
+              if (PAIR) umma_tf32_2sm(tacc + (uint32_t)mt * 256u, make_desc(a_addr, a_lbo, a_sbo, a_lt), db, idesc, acc);
+              else umma_tf32(tacc + (uint32_t)mt * 256u, make_desc(a_addr, a_lbo, a_sbo, a_lt), db, idesc, acc);
             }
           }
-          umma_commit(smem_u32(&empty_bar[s]));  // frees the stage when these MMAs retire
+          // frees the stage when these MMAs retire (PAIR: in both CTAs)
+          if (PAIR) umma_commit_2sm(smem_u32(&empty_bar[s]));
+          else umma_commit(smem_u32(&empty_bar[s]));
           first = false;
-          last = cu.advance(p, n_items, gridDim.x);
+          last = cu.advance(p, n_items, item_stride);
           if (++s == S) {
             s = 0;
             ph ^= 1u;
           }
         }
-        umma_commit(smem_u32(&tfull_bar[buf]));  // accumulator(s) of this item complete
+        // accumulator(s) of this item complete (PAIR: each CTA's epilogue drains its own 128 x MT rows)
+        if (PAIR) umma_commit_2sm(smem_u32(&tfull_bar[buf]));
+        else umma_commit(smem_u32(&tfull_bar[buf]));
         ++t;
       }
     }
@@ -406,8 +502,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     // LSU busy ~8k cycles per 256x240 tile with the tensor pipe idle; the TMA store writes whole 128-byte
     // lines and clips at the matrix edge by itself.
     const int ew = warp & 3;
-    Cursor<MT> cu;
-    cu.init(p, blockIdx.x, n_items);
+    Cursor<MT, PAIR> cu;
+    cu.init(p, first_item, n_items, rm);
     int t = 0;
     const bool vec_base = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     const bool vec8_base = vec_base && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 31) == 0) && p.out_mode == 0;
@@ -508,9 +604,11 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
       }
       tc_fence_before();
-      mbar_arrive(smem_u32(&tempty_bar[buf]));  // buffer may be overwritten by the MMA warp
+      // buffer may be overwritten by the MMA warp (PAIR: the leader's, which waits for both epilogues)
+      if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+      else mbar_arrive(smem_u32(&tempty_bar[buf]));
       __syncwarp();                             // all lanes are done with the rowvec slab
-      cu.next_item(p, n_items, gridDim.x);
+      cu.next_item(p, n_items, item_stride);
       ++t;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging must outlive its readers
@@ -518,9 +616,11 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers or read its operands
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -609,8 +709,9 @@ bool gemm_tma_eligible(const float* A, int lda, const float* B, int ldb, int M, 
 // Operands must already hold tf32-representable values (the tensor core truncates the low 13 mantissa
 // bits of whatever it is given).  transA: A is stored [K, M]; transB: B is stored [N, K].
 // tall: 1 selects 256-row tiles (MT = 2), 0 128-row tiles, -1 picks by problem size.
+// cluster: 0 one CTA per tile, 1 CTA pairs (cta_group::2 MMA, each CTA stages half of B), -1 picks by problem size.
 int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool transB, float* C, int ldc, int M,
-             int N, int K, float beta, float alpha, cudaStream_t st, int tall, const GemmEpilogue* epi) {
+             int N, int K, float beta, float alpha, cudaStream_t st, int tall, const GemmEpilogue* epi, int cluster) {
   if (M <= 0 || N <= 0) return EBK_OK;
   EBK_CHECK_ARG(A && B && C && K >= 1, "gemm_tma: null operand or K < 1");
   EBK_CHECK_ARG(gemm_tma_eligible(A, lda, B, ldb, M, N, K), "gemm_tma: operands must be 16-byte aligned with ld %% 4 == 0");
@@ -621,6 +722,8 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
     EBK_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const bool a_mn = transA, b_mn = !transB;
+  static const int env_cluster = getenv("EBK_GEMM_CLUSTER") ? atoi(getenv("EBK_GEMM_CLUSTER")) : -2;  // experiments
+  if (env_cluster >= -1) cluster = env_cluster;
   if (tall < 0) {
     // auto: 256-row tiles halve the L2 traffic of B; use them when they still fill the machine, or when
     // split-K fills it anyway
@@ -629,6 +732,13 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
     tall = (t2 >= 2L * g_sms || t1 < g_sms) ? 1 : 0;
   }
   const int MT = tall ? 2 : 1;
+  // cluster: 0 = one CTA per tile, 1 = CTA pairs (cta_group::2), -1 auto.  Measured on B200 (tools/bench_gemm_tma.py):
+  // pairs lift 128-row tiles to the speed of 256-row tiles (both halve the B traffic through shared memory) but
+  // add nothing on top of them -- 620-660 TFLOP/s tf32 either way, ~90 % of half the sustained cuBLAS bf16 rate --
+  // so auto only pairs up 128-row tiles of problems large enough to keep every pair busy.
+  if (cluster < 0) cluster = (MT == 1 && (long)ceil_div(M, 2 * BM) * ceil_div(N, 256) >= 2L * (g_sms / 2)) ? 1 : 0;
+  const bool pair = cluster >= 1;
+  const int cm = pair ? 2 : 1;
   TParams p;
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.alpha = alpha;
   p.epi = epi ? *epi : GemmEpilogue{nullptr, nullptr, 0, 1, Dropout{0, 0, 1.0f}, 0, false};
@@ -638,8 +748,9 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   const int ntn = ceil_div(N, 256);
   p.BN = ceil_div(ceil_div(N, ntn), 16) * 16;
   p.tiles_n = ceil_div(N, p.BN);
-  p.b_rows = b_mn ? ((p.BN + 31) & ~31) : p.BN;
-  p.tiles_m = ceil_div(M, BM * MT);
+  const int bn_cta = pair ? p.BN / 2 : p.BN;                       // B columns staged by one CTA
+  p.b_rows = b_mn ? ((bn_cta + 31) & ~31) : bn_cta;
+  p.tiles_m = ceil_div(M, BM * MT * cm);
   p.ksteps_total = ceil_div(K, BK);
   const size_t stage_bytes = (size_t)MT * BM * BK * 4 + (size_t)p.b_rows * BK * 4;
   p.rv_smem = (p.epi.rowscale != nullptr && p.epi.L >= 16) ? 1 : 0;
@@ -650,10 +761,12 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const long tiles = (long)p.tiles_m * p.tiles_n;
+  const int csize = cm;
+  const int max_clusters = g_sms / csize;
+  const long tiles = (long)p.tiles_m * p.tiles_n;         // work items (of a CTA or of a CTA pair)
   int splitk = 1;
-  if (tiles < g_sms && p.ksteps_total >= 16 && !has_epi) {
-    splitk = (int)(g_sms / tiles);  // fill the machine in ONE wave of equal items
+  if (tiles < max_clusters && p.ksteps_total >= 16 && !has_epi) {
+    splitk = (int)(max_clusters / tiles);  // fill the machine in ONE wave of equal items
     const int maxsplit = p.ksteps_total / 8;
     if (splitk > maxsplit) splitk = maxsplit;
     if (splitk < 1) splitk = 1;
@@ -670,18 +783,37 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   CUtensorMap tmA, tmB;
   if (!a_mn) EBK_TRY(get_map(A, K, M, lda, BM * MT, false, &tmA));   // storage [M, K]
   else       EBK_TRY(get_map(A, M, K, lda, 32, true, &tmA));         // storage [K, M]
-  if (!b_mn) EBK_TRY(get_map(B, K, N, ldb, p.b_rows, false, &tmB));  // storage [N, K]
+  if (!b_mn) EBK_TRY(get_map(B, K, N, ldb, p.b_rows, false, &tmB));  // storage [N, K]; PAIR: half of the tile's rows
   else       EBK_TRY(get_map(B, N, K, ldb, 32, true, &tmB));         // storage [K, N]
   const long n_items = tiles * splitk;
-  const int grid = (int)(n_items < g_sms ? n_items : g_sms);
+  const int n_clusters = (int)(n_items < max_clusters ? n_items : max_clusters);
+  const int grid = n_clusters * csize;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + STG_BYTES + rv_bytes;
   CUtensorMap tmC = tmA;
   if (p.c_tma) EBK_TRY(get_map(C, N, M, ldc, 32, false, &tmC));      // box {32 cols, 32 rows}, SWIZZLE_128B
-#define LAUNCH3(AMN_, BMN_, MT_)                                                                               \
-  {                                                                                                            \
-    EBK_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<AMN_, BMN_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  (int)smem));                                                                 \
-    gemm_tma_kernel<AMN_, BMN_, MT_><<<grid, THREADS, smem, st>>>(tmA, tmB, tmC, p);                                \
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = csize > 1 ? 1 : 0;
+#define LAUNCH4(AMN_, BMN_, MT_, PAIR_)                                                                          \
+  {                                                                                                                \
+    EBK_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<AMN_, BMN_, MT_, PAIR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smem));                                                                     \
+    EBK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tma_kernel<AMN_, BMN_, MT_, PAIR_>, tmA, tmB, tmC, p));                  \
+  }
+#define LAUNCH3(AMN_, BMN_, MT_)                   \
+  {                                                \
+    if (pair) LAUNCH4(AMN_, BMN_, MT_, true)       \
+    else LAUNCH4(AMN_, BMN_, MT_, false)           \
   }
 #define LAUNCH2(AMN_, BMN_)                  \
   {                                          \
@@ -694,6 +826,7 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   else LAUNCH2(true, true)
 #undef LAUNCH2
 #undef LAUNCH3
+#undef LAUNCH4
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

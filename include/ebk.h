@@ -244,7 +244,8 @@ int ebk_gemm(int32_t math, int32_t transA, int32_t transB, int32_t M, int32_t N,
 
 /* The training-path GEMM on its own: all-TMA tcgen05 kind::tf32, C (+)= alpha * op(A) . op(B), beta in {0,1}.
  * A and B must hold tf32-representable values (the tensor core truncates); transA: A stored [K, M];
- * transB: B stored [N, K]; tall != 0: 256-row tiles.  Replaces the K.dot / tf.matmul contractions of
+ * transB: B stored [N, K]; tall bits 0-3: 0 = 128-row tiles, 1 = 256-row tiles, 15 = auto; bits 4-7: thread-block
+ * CTA pairs (tcgen05 cta_group::2, each CTA stages half of B), 0 = off, 1 = on, 15 = auto.  Replaces the K.dot / tf.matmul contractions of
  * layers.py:65, 214-230 and their autodiff transposes. */
 int ebk_gemm_tma(int32_t transA, int32_t transB, int32_t tall, int32_t M, int32_t N, int32_t K,
                  const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc,

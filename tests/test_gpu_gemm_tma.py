@@ -28,7 +28,8 @@ SHAPES = [(1, 1, 1), (37, 53, 29), (128, 256, 64), (300, 1200, 768), (130, 200, 
           (3840, 1200, 100), (768, 1200, 3841), (400, 200, 6000), (640, 400, 200), (513, 768, 1200)]
 
 
-@pytest.mark.parametrize("tall", [0, 1])
+# tile/pair mode: bits 0-3 tile rows (0 = 128, 1 = 256, 15 = auto), bits 4-7 CTA pairs / cta_group::2 (0, 1, 15 = auto)
+@pytest.mark.parametrize("tall", [0, 1, 0 | (1 << 4), 1 | (1 << 4), 15 | (15 << 4)])
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_gemm_tma(ebk, tall, tA, tB, M, N, K):

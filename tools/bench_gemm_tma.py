@@ -46,14 +46,9 @@ for name, tA, tB, M, N, K, sa, sb in cases:
     C = torch.zeros(M, N, device="cuda")
     fl = 2.0 * M * N * K
     line = f"{name:28s}"
-    for tall in (0, 1):
+    for tall in (0, 1, 0 | (1 << 4), 1 | (1 << 4)):
         f = lambda: _ebk.check(lib.ebk_gemm_tma(tA, tB, tall, M, N, K, _ebk.ptr(A), sa[1], _ebk.ptr(B), sb[1],
                                                 _ebk.ptr(C), N, 0.0, 1.0, _ebk.stream()))
         ms = timeit(f)
-        line += f"  tma(tall={tall}) {ms:7.3f} ms {fl / ms / 1e9:7.1f} TF/s"
-    f = lambda: _ebk.check(lib.ebk_gemm(1, tA, tB, M, N, K, _ebk.ptr(A), sa[1], _ebk.ptr(B), sb[1], _ebk.ptr(C), N, 0.0,
-                                        _ebk.stream()))
-    ms = timeit(f)
-    line += f"  regpath {ms:7.3f} ms {fl / ms / 1e9:7.1f} TF/s"
-    ref = (A.t() if tA else A)[:2048].double() if not tA else None
+        line += f"  t{tall & 15}c{tall >> 4} {ms:6.3f}ms {fl / ms / 1e9:5.0f}TF"
     print(line, flush=True)
