@@ -287,7 +287,8 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   (void)attb;
   EBK_CHECK_ARG(table_or_x && Wqkv && attW && attq && d_out && workspace, "seqenc_bwd: null pointer");
   EBK_CHECK_ARG(dWqkv && dattW && dattb && dattq, "seqenc_bwd: null parameter-gradient pointer");
-  EBK_CHECK_ARG(tok == nullptr || d_x == nullptr, "seqenc_bwd: d_x must be NULL when tokens are gathered");
+  EBK_CHECK_ARG(tok == nullptr || d_x == nullptr || d_table == nullptr,
+                "seqenc_bwd: with token ids give d_table (scatter here) OR d_x (rows for ebk_embed_adam_step), not both");
   EBK_CHECK_ARG(tok != nullptr || d_table == nullptr, "seqenc_bwd: d_table needs token ids");
   EBK_CHECK_ARG(tok != nullptr || !(training && d->dropout > 0.0f), "seqenc_bwd: dropout on a dense input is not supported");
   SeqWs ws = seq_layout(*d, workspace);
@@ -330,11 +331,11 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
     EBK_PROF(T_QKV_WGRAD, gemm_tma(ws.xd, d->Din, true, ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din, 3 * D, R, 1.0f, 1.0f,
                                    st, -1));
     // dX = dQKV Wqkv^T
-    if (tok != nullptr ? (d_table != nullptr) : (d_x != nullptr)) {
-      float* dx = tok ? ws.dx : d_x;
+    if (d_table != nullptr || d_x != nullptr) {
+      float* dx = d_x ? d_x : ws.dx;
       EBK_PROF(T_QKV_DGRAD, gemm_tma(ws.dqkv, 3 * D, false, ws.wqkv_r, 3 * D, true, dx, d->Din, R, d->Din, 3 * D, 0.0f, 1.0f,
                                      st, -1));
-      if (tok) EBK_PROF(T_SCATTER, scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
+      if (tok && d_table) EBK_PROF(T_SCATTER, scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
     }
     return EBK_OK;
   }
@@ -379,11 +380,11 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
                                       3 * D, R, 1.0f, st,
                                       pk_dq ? GEMM_B_PACKED : (rnd ? GEMM_B_ROUNDED : GEMM_B_RAW)));
   // dX = dQKV Wqkv^T
-  if (tok != nullptr ? (d_table != nullptr) : (d_x != nullptr)) {
-    float* dx = tok ? ws.dx : d_x;
+  if (d_table != nullptr || d_x != nullptr) {
+    float* dx = d_x ? d_x : ws.dx;
     EBK_PROF(T_QKV_DGRAD, gemm_dispatch(d->math, adq, pk_qkv ? ws.wqkv_d : Wqkv, 3 * D, true, dx, d->Din, R, d->Din,
                                         3 * D, 0.0f, st, pk_qkv ? GEMM_B_PACKED : GEMM_B_RAW));
-    if (tok) EBK_PROF(T_SCATTER, scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
+    if (tok && d_table) EBK_PROF(T_SCATTER, scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
   }
   return EBK_OK;
 }

@@ -24,6 +24,7 @@ SYMBOLS = [
     "ebk_last_error", "ebk_version", "ebk_device_ok",
     "ebk_seqenc_workspace_bytes", "ebk_seqenc_fwd", "ebk_seqenc_bwd",
     "ebk_score_softmax_ce", "ebk_score_sigmoid", "ebk_adam_keras_step",
+    "ebk_embed_adam_workspace_bytes", "ebk_embed_adam_step",
     "ebk_dense_workspace_bytes", "ebk_dense_fwd", "ebk_dense_bwd", "ebk_sumsq_accum",
     "ebk_attlayer_workspace_bytes", "ebk_attlayer_fwd", "ebk_attlayer_bwd",
     "ebk_conv1d_workspace_bytes", "ebk_conv1d_fwd", "ebk_conv1d_bwd",
@@ -113,6 +114,9 @@ def lib() -> C.CDLL:
     l.ebk_score_softmax_ce.argtypes = [i32, i32, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp]
     l.ebk_score_sigmoid.argtypes = [i32, i32, i32, vp, vp, vp, vp]
     l.ebk_adam_keras_step.argtypes = [vp, vp, vp, vp, sz, f32, f64, f64, f32, C.c_int, vp]
+    l.ebk_embed_adam_workspace_bytes.restype = sz
+    l.ebk_embed_adam_workspace_bytes.argtypes = [i32, i32]
+    l.ebk_embed_adam_step.argtypes = [i32, i32, i32, vp, vp, f32, u64, vp, vp, vp, vp, f32, f64, f64, f32, vp, sz, vp]
     l.ebk_gemm.argtypes = [i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, f32, vp]
     l.ebk_gemm_tma.argtypes = [i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, f32, f32, vp]
     l.ebk_attention_core_fwd.argtypes = [i32, i32, i32, i32, vp, vp, vp]

@@ -98,6 +98,9 @@ class NRMSEngine:
             self.world = torch.distributed.get_world_size()
             self.rank = torch.distributed.get_rank()
         self.launches_per_step = 0
+        # single-GPU train_step_dev: fused IndexedSlices gradient + Adam (see there); EBK_SPARSE_ADAM=0 disables
+        import os
+        self.sparse_table_grad = type(self) is NRMSEngine and os.environ.get("EBK_SPARSE_ADAM", "1") != "0"
 
     # ------------------------------------------------------------------ weights
     def set_weights(self, weights: list[np.ndarray]) -> None:
@@ -244,8 +247,10 @@ class NRMSEngine:
         base = _mix(self.seed, self.step_count * self.world + self.rank)
         return _mix(base, 1), _mix(base, 2)
 
-    def loss_and_grads_dev(self, tok_all, labels, B, C_, training=True, seeds=None):
-        """Forward + backward; gradients ACCUMULATE into params.grad.  Returns (loss_sum, probs)."""
+    def loss_and_grads_dev(self, tok_all, labels, B, C_, training=True, seeds=None, sparse_table=False):
+        """Forward + backward; gradients ACCUMULATE into params.grad.  Returns (loss_sum, probs).
+        sparse_table: leave the table gradient as per-row gradients in the "dx" buffer (for apply_adam(sparse=...))
+        instead of scatter-adding it into params.grad."""
         lib, P = _ebk.lib(), self.params
         seeds = self.step_seeds() if seeds is None else seeds
         n_all, news_c, u, (dn, wn, du, wu) = self.forward_logits_parts(tok_all, B, C_, training, seeds)
@@ -272,11 +277,17 @@ class NRMSEngine:
                                       seeds[0], seeds[1], _ebk.ptr(wn), wn.numel(), _ebk.ptr(dn_all),
                                       _ebk.ptr(P.g("news_Wqkv")), _ebk.ptr(P.g("news_attW")),
                                       _ebk.ptr(P.g("news_attb")), _ebk.ptr(P.g("news_attq")),
-                                      _ebk.ptr(P.g("table")), None, _ebk.stream()))
+                                      None if sparse_table else _ebk.ptr(P.g("table")),
+                                      _ebk.ptr(self._buf("dx", (N * self.T, self.E))) if sparse_table else None,
+                                      _ebk.stream()))
         return loss, probs
 
-    def apply_adam(self) -> None:
+    def apply_adam(self, sparse=None) -> None:
         """One Keras-form Adam iteration over the whole flat buffer (clears grad in the same pass).
+
+        sparse = (tok_all, dropout seed of the embedded tokens): the table rows are updated by
+        ebk_embed_adam_step from the per-row gradients left in the "dx" buffer; the dense Adam then only
+        covers the remaining (small) parameters.
 
         Data parallel (world > 1): the gradient exchange is a reduce-scatter of the flat buffer (sum; the
         loss is pre-scaled by 1/world), each rank runs the dense Keras Adam on ITS 1/world slice of
@@ -286,6 +297,20 @@ class NRMSEngine:
         self.step_count += 1
         alpha = keras_adam_alpha(self.lr, self.step_count, self.beta1, self.beta2)
         lib = _ebk.lib()
+        if sparse is not None:
+            tok_all, seed1 = sparse
+            R = tok_all.numel()
+            need = lib.ebk_embed_adam_workspace_bytes(R, self.V)
+            ws = self._buf("embed_adam_ws", (need,), dtype=torch.uint8)
+            _ebk.check(lib.ebk_embed_adam_step(R, self.E, self.V, _ebk.ptr(tok_all), _ebk.ptr(self._buf("dx", (R, self.E))),
+                                               self.dropout, seed1, _ebk.ptr(P.theta), _ebk.ptr(P.grad), _ebk.ptr(P.m),
+                                               _ebk.ptr(P.v), alpha, self.beta1, self.beta2, self.eps, _ebk.ptr(ws),
+                                               ws.numel(), _ebk.stream()))
+            lo = P.offsets["news_Wqkv"]  # everything behind the table
+            th, g, m, v = P.theta[lo:], P.grad[lo:], P.m[lo:], P.v[lo:]
+            _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(th), _ebk.ptr(g), _ebk.ptr(m), _ebk.ptr(v), P.n - lo, alpha,
+                                               self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
+            return
         if self.world == 1:
             _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(P.theta), _ebk.ptr(P.grad), _ebk.ptr(P.m), _ebk.ptr(P.v),
                                                P.n, alpha, self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
@@ -302,8 +327,19 @@ class NRMSEngine:
         P.grad.zero_()
 
     def train_step_dev(self, tok_all, labels, B, C_):
-        loss, probs = self.loss_and_grads_dev(tok_all, labels, B, C_, training=True)
-        self.apply_adam()
+        """One optimizer iteration.  Single GPU: the Embedding's row-sparse gradient never becomes a dense
+        [V, E] buffer -- the backward leaves the per-row gradients dX and ebk_embed_adam_step sums them per
+        token inside the table's (dense, Keras-form) Adam pass.  Data parallel: dense gradient buffer +
+        reduce-scatter (see apply_adam)."""
+        # (subclasses with other graphs -- DocVec, NAML -- keep the dense path: they never set the flag)
+        sparse = getattr(self, "sparse_table_grad", False) and self.world == 1 and self.E <= 1024
+        if not sparse:
+            loss, probs = self.loss_and_grads_dev(tok_all, labels, B, C_, training=True)
+            self.apply_adam()
+            return loss, probs
+        seeds = self.step_seeds()
+        loss, probs = self.loss_and_grads_dev(tok_all, labels, B, C_, training=True, seeds=seeds, sparse_table=sparse)
+        self.apply_adam(sparse=(tok_all, seeds[0]) if sparse else None)
         return loss, probs
 
     # ------------------------------------------------------------------ host-array convenience

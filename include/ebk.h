@@ -84,7 +84,9 @@ int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, const float* ta
 /* Backward of ebk_seqenc_fwd (the reference gets it from TF autodiff).  Gradients are
  * ACCUMULATED (+=) into dWqkv/dattW/dattb/dattq.  Input gradient:
  *   tok != NULL: rows of dX are scatter-added into d_table [V, Din] (the Embedding's
- *                IndexedSlices gradient, nrms.py:125-134), d_x must be NULL;
+ *                IndexedSlices gradient, nrms.py:125-134) when d_table != NULL; or, when d_x != NULL
+ *                (d_table NULL), the UNMASKED per-row gradients dX [n_seq*L, Din] are written to d_x for
+ *                ebk_embed_adam_step, which applies the dropout mask and sums rows per token itself;
  *   tok == NULL: d_x [n_seq*L, Din] is overwritten (may be NULL to skip). */
 int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, const float* table_or_x,
                    const float* Wqkv, const float* attW, const float* attb, const float* attq,
@@ -220,6 +222,22 @@ int ebk_score_sigmoid(int32_t B, int32_t C, int32_t D, const float* news, const 
  * ---------------------------------------------------------------------------------- */
 int ebk_adam_keras_step(float* theta, float* g, float* m, float* v, size_t n, float alpha,
                         double beta1, double beta2, float eps, int zero_grad, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Embedding table: IndexedSlices gradient + the same Keras-form Adam, fused (single-GPU training path).
+ * Replaces the Embedding backward (nrms.py:125-134) and the table's share of Adam (nrms.py:76-77) without
+ * materialising a dense [V, E] gradient: g[v, :] = sum over rows r with tok[r] == v of
+ * dX[r, :] * dropout'(r, :) (mask of seed drop_seed, element index r*E + e, rate drop_p; 0 = off) is summed per
+ * table row (ascending r: bit-reproducible) inside the optimizer pass; EVERY row's m, v, theta are updated
+ * (non-lazy Adam, identical arithmetic to ebk_adam_keras_step).
+ *   tok [R] int32 (ids outside [0, V) ignored), dX [R, E] = ebk_seqenc_bwd's d_x output, theta/m/v [V, E],
+ *   d_table [V, E]: dense gradient buffer, must be all-zero on entry and is all-zero on exit (rows referenced
+ *   more than 32 times are pre-reduced into it).  E % 4 == 0, E <= 1024.
+ * ---------------------------------------------------------------------------------- */
+size_t ebk_embed_adam_workspace_bytes(int32_t R, int32_t V);
+int ebk_embed_adam_step(int32_t R, int32_t E, int32_t V, const int32_t* tok, const float* dX, float drop_p,
+                        uint64_t drop_seed, float* theta, float* d_table, float* m, float* v, float alpha,
+                        double beta1, double beta2, float eps, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): number of kernels this library has launched so far, and an
