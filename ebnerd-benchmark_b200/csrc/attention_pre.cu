@@ -240,7 +240,7 @@ __device__ __forceinline__ void store_rows(const float (&acc)[2][Cfg<DH>::NT][4]
 }
 
 template <int DH, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32) attn_fwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
+__global__ void __launch_bounds__(WARPS * 32, 5) attn_fwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
                                                                   float* __restrict__ y, Dropout drop) {
   extern __shared__ __align__(16) float smem[];
   constexpr int MAT = Cfg<DH>::MAT;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(WARPS * 32) attn_fwd_pre_kernel(int n_seq, int
 }
 
 template <int DH, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32) attn_bwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
+__global__ void __launch_bounds__(WARPS * 32, 4) attn_bwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
                                                                   const float* __restrict__ dy, float* __restrict__ dqkv) {
   extern __shared__ __align__(16) float smem[];
   constexpr int MAT = Cfg<DH>::MAT;
