@@ -92,7 +92,6 @@ def kernel_models(w, B, nparam):
         "news.attn_core_fwd": ("hbm", f * R * (3 * D + D)),
         "news.attn_core_bwd": ("hbm", f * R * (3 * D + D + 3 * D)),
         "news.embed_gather": ("hbm", f * R * 2 * E + 4 * R),
-        "news.embed_scatter": ("hbm", f * R * 3 * E + 4 * R),
         "news.att_gemm_fwd": ("hbm", f * R * (D + att)),
         "news.att_dgrad_gemm": ("hbm", f * R * (att + D)),
         "news.att_wgrad_gemm": ("hbm", f * R * (D + att)),

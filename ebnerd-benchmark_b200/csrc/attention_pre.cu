@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(WARPS * 32, 5) attn_fwd_pre_kernel(int n_seq, 
 }
 
 template <int DH, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32, 4) attn_bwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
+__global__ void __launch_bounds__(WARPS * 32, 3) attn_bwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
                                                                   const float* __restrict__ dy, float* __restrict__ dqkv) {
   extern __shared__ __align__(16) float smem[];
   constexpr int MAT = Cfg<DH>::MAT;
