@@ -213,6 +213,68 @@ class NRMSEngine:
                                                 0.0, _ebk.ptr(out), _ebk.ptr(loss), None, None, _ebk.stream()))
         return out
 
+    def predict_host_dedup(self, his: np.ndarray, pred: np.ndarray, head: str = "softmax") -> torch.Tensor:
+        """Inference with each DISTINCT article and each distinct history encoded once.
+
+        The reference's eval-mode loader repeats the whole history once per candidate
+        (dataloader.py:94-107, _python.py:370-388) and its scorer graph re-encodes it every time
+        (nrms.py:204-208).  Without dropout the encoders are pure functions of a token row / a history, so the
+        result is identical: unique token rows -> news encoder; unique tuples of article indices -> user
+        encoder; device-side index_select puts the vectors back in [B, C] order for the score kernel."""
+        lib = _ebk.lib()
+        his, pred = np.asarray(his), np.asarray(pred)
+        B, H, T = his.shape
+        C_ = pred.shape[1]
+        if H != self.H:
+            raise ValueError(f"history length {H} != hparams.history_size {self.H}")
+        rows = np.concatenate([his.reshape(B * H, T), pred.reshape(B * C_, T)]).astype(np.int32, copy=False)
+        uniq, inv = np.unique(rows, axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+        users, uinv = np.unique(inv[: B * H].reshape(B, H), axis=0, return_inverse=True)
+        uinv = uinv.reshape(-1)
+        dev = self.device
+        n_u = self.encode_news_dev(torch.from_numpy(np.ascontiguousarray(uniq)).to(dev))
+        hist = n_u.index_select(0, torch.from_numpy(users.reshape(-1).astype(np.int64)).to(dev)).contiguous()
+        u_u = self.encode_user_dev(hist, users.shape[0])
+        news_c = n_u.index_select(0, torch.from_numpy(inv[B * H:].astype(np.int64)).to(dev)).contiguous()
+        u = u_u.index_select(0, torch.from_numpy(uinv.astype(np.int64)).to(dev)).contiguous()
+        out = self._buf("probs", (B, C_))
+        if head == "sigmoid":
+            _ebk.check(lib.ebk_score_sigmoid(B, C_, self.D, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(out), _ebk.stream()))
+        else:
+            labels = self._buf("labels0", (B, C_))
+            labels.zero_()
+            loss = self._buf("loss", (1,))
+            loss.zero_()
+            _ebk.check(lib.ebk_score_softmax_ce(B, C_, self.D, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(labels),
+                                                0.0, _ebk.ptr(out), _ebk.ptr(loss), None, None, _ebk.stream()))
+        self.last_dedup = (int(rows.shape[0]), int(uniq.shape[0]), B, int(users.shape[0]))
+        return out
+
+    def encode_news_dev(self, tok: torch.Tensor) -> torch.Tensor:
+        """[N, T] int32 token rows (device) -> [N, D] news vectors, inference arithmetic."""
+        lib, P = _ebk.lib(), self.params
+        dn = self._desc("news", tok.shape[0])
+        wn = self._workspace("news", dn)
+        out = torch.empty((tok.shape[0], self.D), device=self.device)
+        _ebk.check(lib.ebk_seqenc_fwd(C.byref(dn), _ebk.ptr(tok), _ebk.ptr(P.p("table")),
+                                      _ebk.ptr(P.p("news_Wqkv")), _ebk.ptr(P.p("news_attW")),
+                                      _ebk.ptr(P.p("news_attb")), _ebk.ptr(P.p("news_attq")), 0, 0, 0,
+                                      _ebk.ptr(wn), wn.numel(), _ebk.ptr(out), _ebk.stream()))
+        return out
+
+    def encode_user_dev(self, hist: torch.Tensor, Bu: int) -> torch.Tensor:
+        """[Bu*H, D] history news vectors (device) -> [Bu, D] user vectors, inference arithmetic."""
+        lib, P = _ebk.lib(), self.params
+        du = self._desc("user", Bu)
+        wu = self._workspace("user", du)
+        u = torch.empty((Bu, self.D), device=self.device)
+        _ebk.check(lib.ebk_seqenc_fwd(C.byref(du), None, _ebk.ptr(hist), _ebk.ptr(P.p("user_Wqkv")),
+                                      _ebk.ptr(P.p("user_attW")), _ebk.ptr(P.p("user_attb")),
+                                      _ebk.ptr(P.p("user_attq")), 0, 0, 0, _ebk.ptr(wu), wu.numel(),
+                                      _ebk.ptr(u), _ebk.stream()))
+        return u
+
     def eval_loss_dev(self, tok_all, labels, B, C_):
         """Validation forward: dropout off, mean CE over the batch and the softmax probabilities."""
         lib = _ebk.lib()

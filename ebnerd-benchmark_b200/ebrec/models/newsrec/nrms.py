@@ -47,8 +47,11 @@ class _NRMSTrainModel(KerasLikeModel):
         return float(loss), probs.cpu().numpy(), B
 
     def _predict_batch(self, inputs):
-        tok, _, B, C_ = self._pack(inputs)
-        return self._engine.predict_dev(tok, B, C_, head=self._head).cpu().numpy()
+        # distinct articles / histories are encoded once (the eval-mode loader repeats the history per candidate)
+        his, pred = (np.asarray(a) for a in inputs)
+        if his.ndim != 3 or pred.ndim != 3:
+            raise ValueError(f"expected his [B,H,T] and pred [B,C,T], got {his.shape} and {pred.shape}")
+        return self._engine.predict_host_dedup(his, pred, head=self._head).cpu().numpy()
 
 
 class _EncoderView:

@@ -189,3 +189,25 @@ def test_fused_embedding_adam_matches_dense_path(V):
     for e in engs:
         assert float(e.params.grad.abs().max()) == 0.0
         assert float((e.params.m != 0).float().sum()) > 0
+
+
+def test_scorer_dedup_matches_plain_predict():
+    """Eval-mode batches repeat the history once per candidate (dataloader.py:94-107): the deduplicating
+    predict path (distinct articles and histories encoded once) must reproduce the plain path's scores."""
+    V, E, nh, dh, att, H, T = 300, 32, 4, 8, 24, 10, 12
+    rng = np.random.default_rng(21)
+    P, _, _, _ = make_case(rng, V, E, nh, dh, att, 2, H, 5, T)
+    eng = make_engine(P, V, E, T, H, nh, dh, att, 0.2, 1e-3, 1, seed=1)
+    pool = rng.integers(0, V, (40, T)).astype(np.int32)              # article pool: many repeats
+    n_inview = [3, 7, 1, 12, 5]
+    his = np.concatenate([np.repeat(pool[rng.integers(0, 40, H)][None], n, axis=0) for n in n_inview])   # [sumN, H, T]
+    pred = pool[rng.integers(0, 40, his.shape[0])][:, None, :]                                           # [sumN, 1, T]
+    B = his.shape[0]
+    tok, _ = eng.to_device_batch(his, pred)
+    plain = eng.predict_dev(tok, B, 1, head="sigmoid").cpu().numpy().copy()
+    dedup = eng.predict_host_dedup(his, pred, head="sigmoid").cpu().numpy()
+    rows, uniq, b, users = eng.last_dedup
+    assert uniq <= 40 and users == len(n_inview) and rows == B * (H + 1)
+    assert np.abs(plain - dedup).max() < 1e-6
+    want = O.nrms_score(his, pred, P, nh, dh)
+    assert float(np.abs(dedup - want).max() / np.abs(want).max()) < 1e-3     # and the fp32-oracle gate of the scorer
