@@ -83,7 +83,9 @@ struct SeqWs {
   size_t bytes;
 };
 
-SeqWs seq_layout(const ebk_seqenc_desc& d, void* base) {
+SeqWs seq_layout(const ebk_seqenc_desc& d0, void* base) {
+  ebk_seqenc_desc d = d0;
+  if (d.att <= 0) d.att = 4;   // attention-only mode: the AttLayer2 buffers are unused, keep their sizing well-defined
   const size_t R = (size_t)d.n_seq * d.L, D = (size_t)d.nh * d.dh;
   size_t off = 0;
   auto take = [&](size_t nfloat) {
@@ -121,8 +123,8 @@ SeqWs seq_layout(const ebk_seqenc_desc& d, void* base) {
 // The all-TMA GEMM path: tf32 tensor-core math, every row stride a multiple of 16 bytes.
 bool tma_path(const ebk_seqenc_desc& d, const SeqWs& ws) {
   const int D = d.nh * d.dh;
-  return d.math == EBK_MATH_TF32 && d.att % 4 == 0 &&
-         gemm_tma_eligible(ws.xd, d.Din, ws.wqkv_r, 3 * D, 1, 1, 1) && gemm_tma_eligible(ws.y0, D, ws.attw_r, d.att, 1, 1, 1);
+  return d.math == EBK_MATH_TF32 && d.att % 4 == 0 && gemm_tma_eligible(ws.xd, d.Din, ws.wqkv_r, 3 * D, 1, 1, 1) &&
+         (d.att == 0 || gemm_tma_eligible(ws.y0, D, ws.attw_r, d.att, 1, 1, 1));
 }
 
 int check_desc(const ebk_seqenc_desc* d) {
@@ -131,7 +133,7 @@ int check_desc(const ebk_seqenc_desc* d) {
   EBK_CHECK_ARG(d->Din >= 4 && d->Din % 4 == 0, "seqenc: Din=%d must be a positive multiple of 4", d->Din);
   EBK_CHECK_ARG(d->nh >= 1 && d->dh >= 1 && d->dh <= 32, "seqenc: need nh>=1, 1<=dh<=32 (nh=%d dh=%d)", d->nh, d->dh);
   EBK_CHECK_ARG((d->nh * d->dh) % 4 == 0, "seqenc: D=nh*dh=%d must be a multiple of 4", d->nh * d->dh);
-  EBK_CHECK_ARG(d->att >= 1, "seqenc: att=%d", d->att);
+  EBK_CHECK_ARG(d->att >= 0, "seqenc: att=%d", d->att);
   EBK_CHECK_ARG(d->dropout >= 0.0f && d->dropout < 1.0f, "seqenc: dropout=%f outside [0,1)", d->dropout);
   EBK_CHECK_ARG((long)d->n_seq * d->L < (1L << 31), "seqenc: n_seq*L overflows int32");
   return EBK_OK;
@@ -199,7 +201,8 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
                               size_t workspace_bytes, float* out, void* stream) {
   EBK_TRY(check_desc(d));
   if (d->n_seq == 0) return EBK_OK;
-  EBK_CHECK_ARG(table_or_x && Wqkv && attW && attb && attq && out && workspace, "seqenc_fwd: null pointer");
+  const bool pool = d->att > 0;   // att == 0: stop after the SelfAttention, out = [n_seq*L, D] (no dropout on it)
+  EBK_CHECK_ARG(table_or_x && Wqkv && out && workspace && (!pool || (attW && attb && attq)), "seqenc_fwd: null pointer");
   EBK_CHECK_ARG(tok == nullptr || d->V >= 1, "seqenc_fwd: V=%d with a token gather", d->V);
   EBK_CHECK_ARG(tok != nullptr || !(training && d->dropout > 0.0f), "seqenc_fwd: dropout on a dense input is not supported");
   SeqWs ws = seq_layout(*d, workspace);
@@ -218,22 +221,25 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
     // before it, so the tensor-core kernels spend no issue slots on operand preparation ----
     EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st));
     EBK_TRY(round_tf32_copy(ws.wqkv_r, Wqkv, (size_t)d->Din * 3 * D, st));
-    EBK_TRY(round_tf32_copy(ws.attw_r, attW, (size_t)D * d->att, st));
+    if (pool) EBK_TRY(round_tf32_copy(ws.attw_r, attW, (size_t)D * d->att, st));
     // (1) Q|K|V = dropout1(gather(table, tok)) . Wqkv        nrms.py:134-139, layers.py:214-230
     // (stored rounded to tf32: the attention kernels feed it to mma.sync without touching it again)
     const GemmEpilogue round_epi{nullptr, nullptr, 0, 1, none, 0, true};
     EBK_PROF(T_QKV_FWD, gemm_tma(ws.xd, d->Din, false, ws.wqkv_r, 3 * D, false, ws.qkv, 3 * D, R, 3 * D, d->Din, 0.0f,
                                  1.0f, st, -1, &round_epi));
     // (2) attention core; its output is stored as tf32(dropout2(Y0)) -- the only form AttLayer2 reads
-    if (attention_pre_supported(d->L, d->dh, ws.qkv, ws.y0, ws.qkv)) {
-      EBK_PROF(T_ATTN_FWD, attention_core_fwd_pre(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, drop2, st));
-    } else if (attention_mma_supported(d->L, d->dh, ws.qkv, ws.y0, ws.qkv)) {
-      EBK_PROF(T_ATTN_FWD, attention_core_fwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st, drop2, true));
+    float* y0 = pool ? ws.y0 : out;
+    const Dropout dropy = pool ? drop2 : none;
+    if (attention_pre_supported(d->L, d->dh, ws.qkv, y0, ws.qkv)) {
+      EBK_PROF(T_ATTN_FWD, attention_core_fwd_pre(d->n_seq, d->L, d->nh, d->dh, ws.qkv, y0, dropy, st));
+    } else if (attention_mma_supported(d->L, d->dh, ws.qkv, y0, ws.qkv)) {
+      EBK_PROF(T_ATTN_FWD, attention_core_fwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, y0, st, dropy, true));
     } else {
-      EBK_CHECK_ARG(!drop2.on(), "seqenc_fwd: dropout needs L <= 32 and dh <= 32 on the tensor-core path");
-      EBK_PROF(T_ATTN_FWD, attention_core_fwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st));
-      EBK_TRY(round_tf32_copy(ws.y0, ws.y0, (size_t)R * D, st));
+      EBK_CHECK_ARG(!dropy.on(), "seqenc_fwd: dropout needs L <= 32 and dh <= 32 on the tensor-core path");
+      EBK_PROF(T_ATTN_FWD, attention_core_fwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, y0, st));
+      if (pool) EBK_TRY(round_tf32_copy(y0, y0, (size_t)R * D, st));
     }
+    if (!pool) return EBK_OK;
     // (3) pre-activation of AttLayer2                                nrms.py:153-156, layers.py:65
     EBK_PROF(T_ATT_GEMM_FWD, gemm_tma(ws.y0, D, false, ws.attw_r, d->att, false, ws.hbuf, d->att, R, d->att, D, 0.0f,
                                       1.0f, st, -1));
@@ -248,7 +254,7 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   GemmOperandA ax{table_or_x, d->Din, false, tok, d->V, tok ? drop1 : none, d->Din};
   GemmOperandA ay{ws.y0, D, false, nullptr, 0, drop2, D};
   const bool pk_qkv = tc && gemm_tf32_eligible(ax, Wqkv, 3 * D, R, 3 * D, d->Din);
-  const bool pk_att = tc && gemm_tf32_eligible(ay, attW, d->att, R, d->att, D);
+  const bool pk_att = pool && tc && gemm_tf32_eligible(ay, attW, d->att, R, d->att, D);
   if (pk_qkv) {
     EBK_TRY(gemm_tf32_pack_b(ws.wqkv_f, x3 ? ws.wqkv_f_lo : nullptr, Wqkv, 3 * D, false, 3 * D, d->Din, st));
     if (!x3) EBK_TRY(gemm_tf32_pack_b(ws.wqkv_d, nullptr, Wqkv, 3 * D, true, d->Din, 3 * D, st));
@@ -263,11 +269,13 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
                                     (pk_qkv && x3) ? ws.wqkv_f_lo : nullptr));
   // (2) per-head softmax(QK^T/sqrt(dh)) and the adjoint product    layers.py:231-252
   // training with tf32 contractions: warp-level tensor-core attention; otherwise the exact fp32 kernel
-  if (d->math == EBK_MATH_TF32 && training && attention_mma_supported(d->L, d->dh, ws.qkv, ws.y0, ws.qkv)) {
-    EBK_PROF(T_ATTN_FWD, attention_core_fwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st));
+  float* y0o = pool ? ws.y0 : out;
+  if (d->math == EBK_MATH_TF32 && training && attention_mma_supported(d->L, d->dh, ws.qkv, y0o, ws.qkv)) {
+    EBK_PROF(T_ATTN_FWD, attention_core_fwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, y0o, st));
   } else {
-    EBK_PROF(T_ATTN_FWD, attention_core_fwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.y0, st));
+    EBK_PROF(T_ATTN_FWD, attention_core_fwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, y0o, st));
   }
+  if (!pool) return EBK_OK;
   // (3) pre-activation of AttLayer2: dropout2(Y0) . W              nrms.py:153-156, layers.py:65
   EBK_PROF(T_ATT_GEMM_FWD, gemm_dispatch(d->math, ay, pk_att ? ws.attw_f : attW, d->att, false, ws.hbuf, d->att, R,
                                          d->att, D, 0.0f, st, pk_att ? GEMM_B_PACKED : GEMM_B_RAW,
@@ -285,8 +293,9 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   EBK_TRY(check_desc(d));
   if (d->n_seq == 0) return EBK_OK;
   (void)attb;
-  EBK_CHECK_ARG(table_or_x && Wqkv && attW && attq && d_out && workspace, "seqenc_bwd: null pointer");
-  EBK_CHECK_ARG(dWqkv && dattW && dattb && dattq, "seqenc_bwd: null parameter-gradient pointer");
+  const bool pool = d->att > 0;   // att == 0: d_out is the gradient of the [n_seq*L, D] attention output
+  EBK_CHECK_ARG(table_or_x && Wqkv && d_out && workspace && (!pool || (attW && attq)), "seqenc_bwd: null pointer");
+  EBK_CHECK_ARG(dWqkv && (!pool || (dattW && dattb && dattq)), "seqenc_bwd: null parameter-gradient pointer");
   EBK_CHECK_ARG(tok == nullptr || d_x == nullptr || d_table == nullptr,
                 "seqenc_bwd: with token ids give d_table (scatter here) OR d_x (rows for ebk_embed_adam_step), not both");
   EBK_CHECK_ARG(tok != nullptr || d_table == nullptr, "seqenc_bwd: d_table needs token ids");
@@ -306,6 +315,9 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   if (tma_path(*d, ws)) {
     // ---- all-TMA path (see ebk_seqenc_fwd): ws.xd, ws.y0 (= tf32(dropout2(Y0))), ws.wqkv_r, ws.attw_r are
     // the forward's; dpre and dQKV are rounded to tf32 by the kernels that produce them ----
+    if (!pool) {
+      EBK_TRY(round_tf32_copy(ws.dy, d_out, (size_t)R * D, st));   // the attention kernel multiplies it as tf32
+    } else {
     EBK_PROF(T_POOL_BWD, attpool_bwd_fused(d->n_seq, d->L, D, d->att, ws.y0, ws.hbuf, attq, ws.w, d_out, ws.da, ws.dpre,
                                            ws.colpart, st));
     // db += sum_r dpre_r ; dq += sum_r h_r da_r   (second, deterministic stage over the per-sequence partials)
@@ -319,6 +331,7 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
     // (128-row tiles: this GEMM is epilogue-bound, so the double-buffered accumulator matters more than B traffic)
     EBK_PROF(T_ATT_DGRAD, gemm_tma(ws.dpre, d->att, false, ws.attw_r, d->att, true, ws.dy, D, R, D, d->att, 0.0f, 1.0f, st,
                                    0, &dy_epi));
+    }
     // SelfAttention core backward
     if (attention_pre_supported(d->L, d->dh, ws.qkv, ws.dy, ws.dqkv)) {
       EBK_PROF(T_ATTN_BWD, attention_core_bwd_pre(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, ws.dqkv, st));
@@ -346,11 +359,14 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   const bool rnd = tc && !x3;
   GemmOperandA adp{ws.dpre, d->att, false, nullptr, 0, none, 0};
   GemmOperandA adq{ws.dqkv, 3 * D, false, nullptr, 0, none, 0};
-  const bool pk_att = rnd && gemm_tf32_eligible(adp, attW, d->att, R, D, d->att) &&
+  const bool pk_att = pool && rnd && gemm_tf32_eligible(adp, attW, d->att, R, D, d->att) &&
                       gemm_tf32_eligible(GemmOperandA{ws.y0, D, false, nullptr, 0, drop2, D}, attW, d->att, R, d->att, D);
   const bool pk_qkv = rnd && gemm_tf32_eligible(adq, Wqkv, 3 * D, R, d->Din, 3 * D) &&
                       gemm_tf32_eligible(GemmOperandA{table_or_x, d->Din, false, tok, d->V, tok ? drop1 : none, d->Din},
                                          Wqkv, 3 * D, R, 3 * D, d->Din);
+  const float* dyp = pool ? ws.dy : d_out;
+  const Dropout dropy = pool ? drop2 : none;
+  if (pool) {
   // AttLayer2 backward (layers.py:55-81)
   EBK_PROF(T_POOL_BWD, attpool_bwd(d->n_seq, d->L, D, d->att, ws.y0, drop2, ws.hbuf, attq, ws.w, d_out, ws.da, ws.dpre,
                       ws.dy, rnd, st));
@@ -362,16 +378,17 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   // dX += dpre W^T
   EBK_PROF(T_ATT_DGRAD, gemm_dispatch(d->math, adp, pk_att ? ws.attw_d : attW, d->att, true, ws.dy, D, R, D, d->att,
                                       1.0f, st, pk_att ? GEMM_B_PACKED : GEMM_B_RAW));
+  }
   // SelfAttention core backward (dropout2 mask applied while reading dy)
   GemmOperandA axT{table_or_x, d->Din, true, tok, d->V, tok ? drop1 : none, d->Din};
   const bool pk_dq = rnd && gemm_tf32_eligible(axT, ws.dqkv, 3 * D, d->Din, 3 * D, R) &&
                      (d->dh == 8 || d->dh == 16 || d->dh == 20 || d->dh == 32);
-  if (d->math == EBK_MATH_TF32 && training && attention_mma_supported(d->L, d->dh, ws.qkv, ws.dy, ws.dqkv)) {
-    EBK_PROF(T_ATTN_BWD, attention_core_bwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, rnd, st,
+  if (d->math == EBK_MATH_TF32 && training && attention_mma_supported(d->L, d->dh, ws.qkv, dyp, ws.dqkv)) {
+    EBK_PROF(T_ATTN_BWD, attention_core_bwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, dyp, dropy, ws.dqkv, rnd, st,
                                                 pk_dq ? ws.dqkv_pk : nullptr,
                                                 pk_dq ? gemm_tf32_bn(3 * D, R, false) : 0));
   } else {
-    EBK_PROF(T_ATTN_BWD, attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, drop2, ws.dqkv, rnd, st,
+    EBK_PROF(T_ATTN_BWD, attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, dyp, dropy, ws.dqkv, rnd, st,
                                             pk_dq ? ws.dqkv_pk : nullptr,
                                             pk_dq ? gemm_tf32_bn(3 * D, R, false) : 0));
   }

@@ -88,9 +88,6 @@ class NRMSModel:
             self.word2vec_embedding = glorot_uniform(seed, (vocab_size, word_emb_dim))  # nrms.py:40-43
         else:
             self.word2vec_embedding = word2vec_embedding
-        if getattr(hparams, "newsencoder_units_per_layer", None):
-            raise NotImplementedError(
-                "newsencoder_units_per_layer (optional Dense/BN stack, nrms.py:142-152) is not built yet")
         data_loss = self._get_loss(hparams.loss)
         self._get_opt(hparams.optimizer, hparams.learning_rate)
         self.model, self.scorer = self._build_graph()
@@ -114,14 +111,33 @@ class NRMSModel:
         table = np.asarray(self.word2vec_embedding, dtype=np.float32)
         V, E = table.shape
         D, A = hp.head_num * hp.head_dim, hp.attention_hidden_dim
-        self._engine = NRMSEngine(V=V, E=E, T=hp.title_size, H=hp.history_size, nh=hp.head_num, dh=hp.head_dim,
-                                  att=A, dropout=hp.dropout, lr=hp.learning_rate, seed=self.seed,
-                                  math=getattr(self, "_math", _ebk.MATH_TF32))
         s = self.seed
-        weights = [table]
-        for din in (E, D):  # news encoder, then user encoder (Keras get_weights order)
-            weights += [glorot_uniform(s, (din, D), 1), glorot_uniform(s, (din, D), 2), glorot_uniform(s, (din, D), 3),
+        units = list(getattr(hp, "newsencoder_units_per_layer", None) or [])
+        if units:
+            # optional Dense/BatchNorm/Dropout stack between SelfAttention and AttLayer2 (nrms.py:142-152)
+            from ._engine_nrms_dense import NRMSDenseEngine
+
+            self._engine = NRMSDenseEngine(V=V, E=E, T=hp.title_size, H=hp.history_size, nh=hp.head_num, dh=hp.head_dim,
+                                           att=A, units=units, l2=getattr(hp, "newsencoder_l2_regularization", 1e-4),
+                                           dropout=hp.dropout, lr=hp.learning_rate, seed=self.seed,
+                                           math=getattr(self, "_math", _ebk.MATH_TF32))
+            weights = [table, glorot_uniform(s, (E, D), 1), glorot_uniform(s, (E, D), 2), glorot_uniform(s, (E, D), 3)]
+            din = D
+            for u in units:  # Keras: Dense kernel GlorotUniform (unseeded), bias 0; BN gamma 1, beta 0, mean 0, var 1
+                weights += [glorot_uniform(None, (din, u)), np.zeros((u,), np.float32), np.ones((u,), np.float32),
+                            np.zeros((u,), np.float32), np.zeros((u,), np.float32), np.ones((u,), np.float32)]
+                din = u
+            weights += [glorot_uniform(s, (din, A), 4), np.zeros((A,), np.float32), glorot_uniform(s, (A, 1), 5)]
+            weights += [glorot_uniform(s, (D, D), 1), glorot_uniform(s, (D, D), 2), glorot_uniform(s, (D, D), 3),
                         glorot_uniform(s, (D, A), 4), np.zeros((A,), np.float32), glorot_uniform(s, (A, 1), 5)]
+        else:
+            self._engine = NRMSEngine(V=V, E=E, T=hp.title_size, H=hp.history_size, nh=hp.head_num, dh=hp.head_dim,
+                                      att=A, dropout=hp.dropout, lr=hp.learning_rate, seed=self.seed,
+                                      math=getattr(self, "_math", _ebk.MATH_TF32))
+            weights = [table]
+            for din in (E, D):  # news encoder, then user encoder (Keras get_weights order)
+                weights += [glorot_uniform(s, (din, D), 1), glorot_uniform(s, (din, D), 2), glorot_uniform(s, (din, D), 3),
+                            glorot_uniform(s, (D, A), 4), np.zeros((A,), np.float32), glorot_uniform(s, (A, 1), 5)]
         self._engine.set_weights(weights)
         model = _NRMSTrainModel(self, self._engine, "model", "softmax")
         scorer = _NRMSTrainModel(self, self._engine, "scorer", "sigmoid")

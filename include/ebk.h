@@ -59,7 +59,10 @@ typedef struct {
   int32_t L;       /* sequence length: title_size T (news) or history_size H (user), <=64 */
   int32_t Din;     /* input width: table width E (news) or D (user); multiple of 4        */
   int32_t nh, dh;  /* heads, head dim (layers.py:137-141); D = nh*dh, dh <= 32            */
-  int32_t att;     /* attention_hidden_dim of AttLayer2 (layers.py:14-22)                 */
+  int32_t att;     /* attention_hidden_dim of AttLayer2 (layers.py:14-22); 0 = stop after the
+                      SelfAttention: out / d_out are [n_seq*L, D] and no Dropout follows it -- the
+                      optional Dense/BN stack of nrms.py:142-152 continues with ebk_dense_* and
+                      ebk_attlayer_*; attW/attb/attq and their gradients may then be NULL        */
   int32_t V;       /* table rows when gathering; ids outside [0,V) -> zero row, no grad   */
   float dropout;   /* Keras Dropout rate (nrms.py:136,153); used only when training != 0  */
   int32_t math;    /* ebk_math                                                             */

@@ -131,3 +131,35 @@ def test_float32_oracle_close_to_float64():
     a = O.nrms_predict(his, pred, P, nh, dh)
     b = O.nrms_predict(his, pred, P32, nh, dh)
     assert b.dtype == np.float32 and np.abs(a - b).max() < 1e-5
+
+
+def test_dense_stack_oracle_gradients_match_finite_differences():
+    """NRMS with the Dense/BN/Dropout stack (nrms.py:142-152): the analytic backward of
+    oracle/nrms_dense_oracle.py against central differences of its own float64 loss (training-mode BN,
+    dropout masks fixed by the seeds)."""
+    from oracle import nrms_dense_oracle as ND
+
+    rng = np.random.default_rng(5)
+    V, E, units, nh, dh, att, B, H, C, T = 30, 12, [10, 8], 2, 4, 6, 3, 4, 3, 5
+    P = ND.init_params(rng, V, E, units, nh, dh, att, dtype=np.float64)
+    for i, u in enumerate(units):
+        P[f"d{i}_b"] = rng.standard_normal(u) * 0.3 + 0.2
+        P[f"d{i}_gamma"] = 1 + rng.standard_normal(u) * 0.1
+    his, pred = rng.integers(0, V, (B, H, T)), rng.integers(0, V, (B, C, T))
+    y = np.zeros((B, C))
+    y[np.arange(B), rng.integers(0, C, B)] = 1
+    kw = dict(p_drop=0.2, seed1=11, seed_h=22, seed_c=33, l2=1e-2)
+    loss, _, G = ND.loss_and_grads(his, pred, y, P, len(units), nh, dh, **kw)
+    for k in ("table", "news_WQ", "d0_W", "d0_b", "d1_gamma", "d1_beta", "news_W", "news_q", "user_WV"):
+        idx = tuple(rng.integers(0, s) for s in P[k].shape)
+        if k == "table":
+            idx = (int(his[0, 0, 0]), idx[1])
+        old = P[k][idx]
+        eps = 1e-6
+        P[k][idx] = old + eps
+        lp = ND.loss_and_grads(his, pred, y, P, len(units), nh, dh, **kw)[0]
+        P[k][idx] = old - eps
+        lm = ND.loss_and_grads(his, pred, y, P, len(units), nh, dh, **kw)[0]
+        P[k][idx] = old
+        fd = (lp - lm) / (2 * eps)
+        assert abs(fd - G[k][idx]) < 1e-6 * max(1.0, abs(fd)) + 1e-8, (k, fd, G[k][idx])
