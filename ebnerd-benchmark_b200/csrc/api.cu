@@ -11,6 +11,10 @@
 namespace ebk {
 
 static thread_local char g_err[512] = "";
+// data parallel: CUDA event recorded right after the embedding-gradient scatter of the next ebk_seqenc_bwd
+// call of this thread, so the host can start the table-gradient collective while the remaining backward
+// kernels (the QKV weight-gradient GEMM) still run
+static thread_local cudaEvent_t g_table_grad_event = nullptr;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -151,6 +155,10 @@ namespace ebk { void gemm_tf32_set_debug(long long* buf, int target); }
 extern "C" int ebk_debug_gemm_timeline(long long* device_buf, int target) {
   ebk::gemm_tf32_set_debug(device_buf, target);
   return 0;
+}
+extern "C" int ebk_set_table_grad_event(void* cuda_event) {
+  g_table_grad_event = (cudaEvent_t)cuda_event;
+  return EBK_OK;
 }
 extern "C" long long ebk_launch_count(void) { return g_launches.load(); }
 extern "C" int ebk_prof_enable(int on) {
@@ -340,16 +348,21 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
     } else {
       EBK_PROF(T_ATTN_BWD, attention_core_bwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, none, ws.dqkv, true, st));
     }
-    // dWqkv += X^T dQKV  (X = dropout1(gather))
-    EBK_PROF(T_QKV_WGRAD, gemm_tma(ws.xd, d->Din, true, ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din, 3 * D, R, 1.0f, 1.0f,
-                                   st, -1));
-    // dX = dQKV Wqkv^T
+    // dX = dQKV Wqkv^T first: the table gradient is the large one, and in data parallel its collective can then
+    // overlap the weight-gradient GEMM below
     if (d_table != nullptr || d_x != nullptr) {
       float* dx = d_x ? d_x : ws.dx;
       EBK_PROF(T_QKV_DGRAD, gemm_tma(ws.dqkv, 3 * D, false, ws.wqkv_r, 3 * D, true, dx, d->Din, R, d->Din, 3 * D, 0.0f, 1.0f,
                                      st, -1));
       if (tok && d_table) EBK_PROF(T_SCATTER, scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
     }
+    if (tok && g_table_grad_event) {
+      EBK_CUDA(cudaEventRecord(g_table_grad_event, st));
+      g_table_grad_event = nullptr;
+    }
+    // dWqkv += X^T dQKV  (X = dropout1(gather))
+    EBK_PROF(T_QKV_WGRAD, gemm_tma(ws.xd, d->Din, true, ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din, 3 * D, R, 1.0f, 1.0f,
+                                   st, -1));
     return EBK_OK;
   }
   // tensor-core mode: the forward left the packed weights in the workspace, and the kernels that
@@ -402,6 +415,10 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
     EBK_PROF(T_QKV_DGRAD, gemm_dispatch(d->math, adq, pk_qkv ? ws.wqkv_d : Wqkv, 3 * D, true, dx, d->Din, R, d->Din,
                                         3 * D, 0.0f, st, pk_qkv ? GEMM_B_PACKED : GEMM_B_RAW));
     if (tok && d_table) EBK_PROF(T_SCATTER, scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
+  }
+  if (tok && g_table_grad_event) {
+    EBK_CUDA(cudaEventRecord(g_table_grad_event, st));
+    g_table_grad_event = nullptr;
   }
   return EBK_OK;
 }

@@ -333,6 +333,13 @@ class NRMSEngine:
                                       _ebk.ptr(d_user), _ebk.ptr(P.g("user_Wqkv")), _ebk.ptr(P.g("user_attW")),
                                       _ebk.ptr(P.g("user_attb")), _ebk.ptr(P.g("user_attq")), None,
                                       _ebk.ptr(dn_all), _ebk.stream()))
+        if self.world > 1:
+            # the table gradient is final after the scatter inside this call: apply_adam starts its
+            # reduce-scatter from that point, overlapping the weight-gradient GEMM that follows
+            dp = self._dp_state()
+            torch.cuda.current_stream().wait_event(dp["zeroed"])  # last step's clearing of the table gradient
+            lib.ebk_set_table_grad_event(C.c_void_p(dp["table_grad"].cuda_event))
+            dp["armed"] = True
         _ebk.check(lib.ebk_seqenc_bwd(C.byref(dn), _ebk.ptr(tok_all), _ebk.ptr(P.p("table")),
                                       _ebk.ptr(P.p("news_Wqkv")), _ebk.ptr(P.p("news_attW")),
                                       _ebk.ptr(P.p("news_attb")), _ebk.ptr(P.p("news_attq")), int(training),
@@ -378,15 +385,55 @@ class NRMSEngine:
                                                P.n, alpha, self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
             return
         dist = torch.distributed
+        tbl = P.offsets.get("news_Wqkv", 0)  # the table segment [0, tbl); everything behind it is small
+        dp = self._dp_state()
+        if tbl > 0 and tbl % (4 * self.world) == 0 and dp.get("armed"):
+            # table: reduce-scatter started on a side stream as soon as the scatter kernel finished (event armed
+            # in loss_and_grads_dev) -> rank-sharded Adam -> all-gather; remaining parameters: all-reduce + the
+            # same dense Adam on every rank
+            dp["armed"] = False
+            main, side = torch.cuda.current_stream(), dp["side"]
+            shard = tbl // self.world
+            lo = self.rank * shard
+            gsh = self._buf("grad_shard", (shard,))
+            side.wait_event(dp["table_grad"])
+            with torch.cuda.stream(side):
+                w_rs = dist.reduce_scatter_tensor(gsh, P.grad[:tbl], async_op=True)
+                w_rs.wait()                      # side stream: the gradient has been read ...
+                P.grad[:tbl].zero_()             # ... clear it for the next step off the critical path
+                dp["zeroed"].record(side)
+            w_ar = dist.all_reduce(P.grad[tbl:], async_op=True)
+            w_rs.wait()
+            th, m, v = P.theta[lo: lo + shard], P.m[lo: lo + shard], P.v[lo: lo + shard]
+            _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(th), _ebk.ptr(gsh), _ebk.ptr(m), _ebk.ptr(v), shard, alpha,
+                                               self.beta1, self.beta2, self.eps, 0, _ebk.stream()))
+            w_ag = dist.all_gather_into_tensor(P.theta[:tbl], th, async_op=True)
+            w_ar.wait()
+            tt, tg, tm, tv = P.theta[tbl:], P.grad[tbl:], P.m[tbl:], P.v[tbl:]
+            _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(tt), _ebk.ptr(tg), _ebk.ptr(tm), _ebk.ptr(tv), P.n - tbl, alpha,
+                                               self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
+            w_ag.wait()
+            return
         shard = P.n // self.world
         lo = self.rank * shard
-        gsh = self._buf("grad_shard", (shard,))
+        gsh = self._buf("grad_shard_full", (shard,))
         dist.reduce_scatter_tensor(gsh, P.grad)
         th, m, v = P.theta[lo: lo + shard], P.m[lo: lo + shard], P.v[lo: lo + shard]
         _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(th), _ebk.ptr(gsh), _ebk.ptr(m), _ebk.ptr(v), shard, alpha,
                                            self.beta1, self.beta2, self.eps, 0, _ebk.stream()))
         dist.all_gather_into_tensor(P.theta, th)
         P.grad.zero_()
+
+    def _dp_state(self) -> dict:
+        """Side stream and events of the overlapped data-parallel optimizer step."""
+        st = getattr(self, "_dp", None)
+        if st is None:
+            st = {"side": torch.cuda.Stream(device=self.device), "table_grad": torch.cuda.Event(),
+                  "zeroed": torch.cuda.Event(), "armed": False}
+            st["table_grad"].record()   # instantiate the CUDA events
+            st["zeroed"].record()
+            self._dp = st
+        return st
 
     def train_step_dev(self, tok_all, labels, B, C_):
         """One optimizer iteration.  Single GPU: the Embedding's row-sparse gradient never becomes a dense

@@ -98,6 +98,11 @@ int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, const float* ta
                    float* dWqkv, float* dattW, float* dattb, float* dattq,
                    float* d_table, float* d_x, void* stream);
 
+/* Data parallel: arm a cudaEvent_t (as void*) that the NEXT ebk_seqenc_bwd call of this thread with token ids
+ * records on its stream right after the embedding-gradient scatter -- the table gradient is then final, so its
+ * collective can start while the remaining backward kernels still run.  NULL disarms. */
+int ebk_set_table_grad_event(void* cuda_event);
+
 /* ------------------------------------------------------------------------------------
  * Dense(+ReLU) -> [BatchNormalization] -> [Dropout] layer of the NRMSDocVec news encoder
  * (nrms_docvec.py:118-130: Dense(units, relu, l2) + BatchNormalization() + Dropout(p); :130 the
