@@ -15,6 +15,8 @@ static thread_local char g_err[512] = "";
 // call of this thread, so the host can start the table-gradient collective while the remaining backward
 // kernels (the QKV weight-gradient GEMM) still run
 static thread_local cudaEvent_t g_table_grad_event = nullptr;
+// data parallel, rank-sharded table: peer mappings used by the embedding gather of the training forward
+static thread_local PeerTables g_peers = {0, 0, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -160,6 +162,44 @@ extern "C" int ebk_set_table_grad_event(void* cuda_event) {
   g_table_grad_event = (cudaEvent_t)cuda_event;
   return EBK_OK;
 }
+// ---- CUDA IPC plumbing for the rank-sharded table (one process per GPU, all on one NVSwitch box) ----------
+extern "C" int ebk_ipc_export(const void* ptr, void* handle64, size_t* offset) {
+  EBK_CHECK_ARG(ptr && handle64 && offset, "ipc_export: null pointer");
+  typedef int (*RangeFn)(unsigned long long*, size_t*, unsigned long long);
+  static RangeFn range = nullptr;
+  if (range == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    EBK_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q));
+    EBK_CHECK_ARG(fn != nullptr && q == cudaDriverEntryPointSuccess, "ipc_export: cuMemGetAddressRange unavailable");
+    range = reinterpret_cast<RangeFn>(fn);
+  }
+  unsigned long long base = 0;
+  size_t size = 0;
+  const int rc = range(&base, &size, (unsigned long long)(uintptr_t)ptr);
+  EBK_CHECK_ARG(rc == 0, "ipc_export: cuMemGetAddressRange failed (%d)", rc);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  EBK_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), reinterpret_cast<void*>((uintptr_t)base)));
+  *offset = (size_t)((unsigned long long)(uintptr_t)ptr - base);
+  return EBK_OK;
+}
+extern "C" int ebk_ipc_open(const void* handle64, size_t offset, void** out) {
+  EBK_CHECK_ARG(handle64 && out, "ipc_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void* base = nullptr;
+  EBK_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  *out = reinterpret_cast<char*>(base) + offset;
+  return EBK_OK;
+}
+// tables[r] = this process's mapping of rank r's table buffer (own pointer for r == rank); world <= 1 disarms
+extern "C" int ebk_set_peer_tables(const void* const* tables, int32_t world, size_t shard_floats) {
+  EBK_CHECK_ARG(world <= 8, "set_peer_tables: at most 8 ranks (one NVSwitch box)");
+  g_peers.world = world > 1 ? world : 0;
+  g_peers.shard_floats = shard_floats;
+  for (int r = 0; r < 8; ++r) g_peers.p[r] = (world > 1 && r < world) ? reinterpret_cast<const float*>(tables[r]) : nullptr;
+  return EBK_OK;
+}
 extern "C" long long ebk_launch_count(void) { return g_launches.load(); }
 extern "C" int ebk_prof_enable(int on) {
   g_prof = on != 0;
@@ -227,7 +267,8 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   if (tma_path(*d, ws)) {
     // ---- all-TMA path: every GEMM operand is materialised dense, masked and tf32-rounded by the layer
     // before it, so the tensor-core kernels spend no issue slots on operand preparation ----
-    EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st));
+    EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st,
+                                        (tok && training && g_peers.world > 1) ? &g_peers : nullptr));
     EBK_TRY(round_tf32_copy(ws.wqkv_r, Wqkv, (size_t)d->Din * 3 * D, st));
     if (pool) EBK_TRY(round_tf32_copy(ws.attw_r, attW, (size_t)D * d->att, st));
     // (1) Q|K|V = dropout1(gather(table, tok)) . Wqkv        nrms.py:134-139, layers.py:214-230

@@ -207,8 +207,13 @@ __global__ void split_tf32_copy_kernel(float* __restrict__ hi, float* __restrict
 }
 
 // Materialises the A operand of the QKV projection for the TMA GEMM: gather + dropout + tf32 rounding.
+// PEERS: the table is sharded over the ranks of one NVSwitch box and each 16-byte chunk is read from its OWNER's
+// HBM over NVLink (peer pointers mapped with CUDA IPC) -- the all-gather of the updated table that data
+// parallel would otherwise need every step is fused into the gather that has to happen anyway.
+template <bool PEERS>
 __global__ void embed_rows_kernel(long n4, int E4, int V, const int32_t* __restrict__ tok,
-                                  const float4* __restrict__ src, Dropout drop, float4* __restrict__ xd) {
+                                  const float4* __restrict__ src, Dropout drop, float4* __restrict__ xd,
+                                  PeerTables peers) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const int r = (int)(i / E4), c4 = (int)(i - (long)r * E4);
@@ -216,7 +221,12 @@ __global__ void embed_rows_kernel(long n4, int E4, int V, const int32_t* __restr
   if (tok != nullptr) {
     const int t = __ldg(tok + r);
     if (t >= 0 && t < V) {
-      const float4* p = src + (long)t * E4 + c4;
+      const long chunk = (long)t * E4 + c4;
+      const float4* p = src + chunk;
+      if (PEERS) {
+        const int owner = (int)(((unsigned long long)chunk * 4ull) / peers.shard_floats);
+        p = reinterpret_cast<const float4*>(peers.p[owner < peers.world ? owner : peers.world - 1]) + chunk;
+      }
       asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                    : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                    : "l"(p));
@@ -317,13 +327,23 @@ int split_tf32_copy(float* hi, float* lo, const float* src, size_t n, cudaStream
 }
 
 int embed_rows(int R, int E, int V, const int32_t* tok, const float* table_or_x, Dropout drop, float* xd,
-               cudaStream_t st) {
+               cudaStream_t st, const PeerTables* peers) {
   if (R <= 0) return EBK_OK;
   EBK_CHECK_ARG(E % 4 == 0, "embed_rows: E=%d must be a multiple of 4", E);
   const long n4 = (long)R * (E / 4);
-  embed_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, E / 4, V, tok,
+  if (peers != nullptr && peers->world > 1 && tok != nullptr) {
+    EBK_CHECK_ARG(peers->world <= 8 && peers->shard_floats % 4 == 0 && peers->shard_floats > 0, "embed_rows: bad peer table");
+    embed_rows_kernel<true><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
+        n4, E / 4, V, tok, reinterpret_cast<const float4*>(table_or_x), drop, reinterpret_cast<float4*>(xd), *peers);
+    EBK_LAUNCH_CHECK();
+    return EBK_OK;
+  }
+  PeerTables none;
+  none.world = 1;
+  none.shard_floats = 0;
+  embed_rows_kernel<false><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, E / 4, V, tok,
                                                                  reinterpret_cast<const float4*>(table_or_x), drop,
-                                                                 reinterpret_cast<float4*>(xd));
+                                                                 reinterpret_cast<float4*>(xd), none);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

@@ -249,8 +249,15 @@ int bias_act(float* z, const float* b, long n, int U, int relu, cudaStream_t st)
 int act_bwd(const float* dy, const float* y, long n, Dropout drop, int relu, int round_out, float* dz, cudaStream_t st);
 
 // Xd[r, :] = tf32(dropout(table[tok[r], :]))  (ids outside [0, V) -> zero row); tok == NULL: Xd = tf32(x)
+// Data parallel with a rank-sharded table: float index f of the table lives in the buffer of rank f / shard_floats
+// (every rank maps every peer's full-size table buffer through CUDA IPC; only the owner's slice is current).
+struct PeerTables {
+  int world;                 // <= 1: single table
+  unsigned long long shard_floats;
+  const float* p[8];
+};
 int embed_rows(int R, int E, int V, const int32_t* tok, const float* table_or_x, Dropout drop, float* xd,
-               cudaStream_t st);
+               cudaStream_t st, const PeerTables* peers = nullptr);
 // d_table[tok[r], :] += dX[r, :] * dropout(r*E + e)
 int scatter_rows_add(int R, int E, int V, const int32_t* tok, const float* dX, Dropout drop,
                      float* d_table, cudaStream_t st);

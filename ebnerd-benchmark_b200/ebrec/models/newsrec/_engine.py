@@ -118,6 +118,7 @@ class NRMSEngine:
                 P.p(f"{pre}_attq").copy_(w[o + 5].reshape(-1))
 
     def get_weights(self) -> list[np.ndarray]:
+        self._sync_table()
         P, D = self.params, self.D
         out = [P.p("table").cpu().numpy()]
         for pre in ("news", "user"):
@@ -165,6 +166,10 @@ class NRMSEngine:
         N = tok_all.shape[0]
         if Hh != self.H:
             raise ValueError(f"history length {Hh} != hparams.history_size {self.H}")
+        if training:
+            self._arm_peer_tables()
+        else:
+            self._sync_table()
         dn = self._desc("news", N, training)
         wn = self._workspace("news", dn)
         n_all = self._buf("n_all", (N, self.D))
@@ -253,6 +258,7 @@ class NRMSEngine:
 
     def encode_news_dev(self, tok: torch.Tensor) -> torch.Tensor:
         """[N, T] int32 token rows (device) -> [N, D] news vectors, inference arithmetic."""
+        self._sync_table()
         lib, P = _ebk.lib(), self.params
         dn = self._desc("news", tok.shape[0])
         wn = self._workspace("news", dn)
@@ -291,6 +297,7 @@ class NRMSEngine:
         lib, P = _ebk.lib(), self.params
         x = np.asarray(x)
         if kind == "news":
+            self._sync_table()
             tok = torch.from_numpy(np.ascontiguousarray(x.reshape(-1, self.T), dtype=np.int32)).to(self.device)
             dn = self._desc("news", tok.shape[0])
             wn = self._workspace("news", dn)
@@ -407,12 +414,20 @@ class NRMSEngine:
             th, m, v = P.theta[lo: lo + shard], P.m[lo: lo + shard], P.v[lo: lo + shard]
             _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(th), _ebk.ptr(gsh), _ebk.ptr(m), _ebk.ptr(v), shard, alpha,
                                                self.beta1, self.beta2, self.eps, 0, _ebk.stream()))
-            w_ag = dist.all_gather_into_tensor(P.theta[:tbl], th, async_op=True)
+            sharded = self._peer_tables(tbl) is not None
+            w_ag = None if sharded else dist.all_gather_into_tensor(P.theta[:tbl], th, async_op=True)
             w_ar.wait()
             tt, tg, tm, tv = P.theta[tbl:], P.grad[tbl:], P.m[tbl:], P.v[tbl:]
             _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(tt), _ebk.ptr(tg), _ebk.ptr(tm), _ebk.ptr(tv), P.n - tbl, alpha,
                                                self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
-            w_ag.wait()
+            if sharded:
+                # rank-sharded table: no all-gather -- the next forward's Embedding gather reads each chunk from its
+                # owner over NVLink (ebk_set_peer_tables).  A one-element all-reduce orders every rank's Adam
+                # before any rank's next gather.
+                self._table_stale = True
+                dist.all_reduce(self._buf("dp_fence", (1,)))
+            else:
+                w_ag.wait()
             return
         shard = P.n // self.world
         lo = self.rank * shard
@@ -423,6 +438,65 @@ class NRMSEngine:
                                            self.beta1, self.beta2, self.eps, 0, _ebk.stream()))
         dist.all_gather_into_tensor(P.theta, th)
         P.grad.zero_()
+
+    def _peer_tables(self, tbl: int):
+        """CUDA-IPC mappings of every rank's parameter buffer (data parallel on one NVSwitch box, world <= 8), or
+        None when the table cannot be sharded (EBK_DP_SHARDED_TABLE=0, world > 8, unaligned shard)."""
+        import os
+
+        if hasattr(self, "_peers"):
+            return self._peers
+        self._peers = None
+        dist = torch.distributed
+        ok = (os.environ.get("EBK_DP_SHARDED_TABLE", "1") != "0" and 1 < self.world <= 8 and tbl > 0
+              and tbl % (4 * self.world) == 0 and type(self) is NRMSEngine)
+        flag = torch.tensor([1 if ok else 0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 0:
+            return None
+        lib = _ebk.lib()
+        handle = (C.c_char * 64)()
+        off = C.c_size_t(0)
+        _ebk.check(lib.ebk_ipc_export(_ebk.ptr(self.params.theta), C.cast(handle, C.c_void_p), C.byref(off)))
+        mine = (bytes(handle.raw), int(off.value))
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine)
+        ptrs = []
+        for r, (hb, o) in enumerate(allh):
+            if r == self.rank:
+                ptrs.append(self.params.theta.data_ptr())
+            else:
+                out = C.c_void_p()
+                buf = C.create_string_buffer(hb, 64)
+                _ebk.check(lib.ebk_ipc_open(C.cast(buf, C.c_void_p), o, C.byref(out)))
+                ptrs.append(out.value)
+        self._peers = {"ptrs": (C.c_void_p * self.world)(*ptrs), "shard": tbl // self.world}
+        return self._peers
+
+    def _arm_peer_tables(self) -> None:
+        """Point the training forward's Embedding gather at the owners' table shards (no-op on one GPU)."""
+        if self.world <= 1:
+            return
+        pt = self._peer_tables(self.params.offsets.get("news_Wqkv", 0))
+        lib = _ebk.lib()
+        if pt is None or not getattr(self, "_table_stale", False):
+            lib.ebk_set_peer_tables(None, 0, 0)   # every replica is current (first step / after a sync)
+        else:
+            _ebk.check(lib.ebk_set_peer_tables(pt["ptrs"], self.world, pt["shard"]))
+
+    def _sync_table(self) -> None:
+        """Make this rank's replica of the table current (all-gather of the owners' shards); needed before any
+        inference / validation forward or weight export after sharded training steps.  Collective: every rank
+        reaches it (validation and checkpointing run in lockstep on all ranks)."""
+        if self.world > 1 and getattr(self, "_table_stale", False):
+            P = self.params
+            tbl = P.offsets["news_Wqkv"]
+            shard = tbl // self.world
+            th = P.theta[self.rank * shard: (self.rank + 1) * shard]
+            torch.distributed.all_gather_into_tensor(P.theta[:tbl], th)
+            self._table_stale = False
+        if self.world > 1:
+            _ebk.lib().ebk_set_peer_tables(None, 0, 0)
 
     def _dp_state(self) -> dict:
         """Side stream and events of the overlapped data-parallel optimizer step."""

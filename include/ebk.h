@@ -103,6 +103,16 @@ int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, const float* ta
  * collective can start while the remaining backward kernels still run.  NULL disarms. */
 int ebk_set_table_grad_event(void* cuda_event);
 
+/* Data parallel, rank-sharded embedding table (all ranks on one NVSwitch box, <= 8).  After
+ * ebk_set_peer_tables the TRAINING forward of ebk_seqenc_fwd reads every 16-byte chunk of a gathered table row
+ * from the rank that owns float index f (owner = f / shard_floats) through the peer mappings -- the all-gather of
+ * the updated table is fused into the Embedding gather (nrms.py:125-134) over NVLink.  ebk_ipc_export /
+ * ebk_ipc_open wrap cudaIpcGetMemHandle / cudaIpcOpenMemHandle (handle64: 64 bytes; offset of ptr inside its
+ * allocation) so that the host code can exchange the mappings with any byte transport. */
+int ebk_ipc_export(const void* ptr, void* handle64, size_t* offset);
+int ebk_ipc_open(const void* handle64, size_t offset, void** out);
+int ebk_set_peer_tables(const void* const* tables, int32_t world, size_t shard_floats);
+
 /* ------------------------------------------------------------------------------------
  * Dense(+ReLU) -> [BatchNormalization] -> [Dropout] layer of the NRMSDocVec news encoder
  * (nrms_docvec.py:118-130: Dense(units, relu, l2) + BatchNormalization() + Dropout(p); :130 the

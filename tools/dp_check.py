@@ -24,7 +24,7 @@ rank, world = dist.get_rank(), dist.get_world_size()
 V, E, nh, dh, att, Bg, H, C, T = 4096, 64, 4, 8, 24, 8 * world, 10, 5, 12
 rng = np.random.default_rng(0)
 P = O.init_nrms_params(rng, V, E, nh, dh, att)
-lr, steps = 1e-3, 3
+lr, steps = 1e-3, 4
 batches = []
 for _ in range(steps):
     his = rng.integers(0, V, (Bg, H, T)).astype(np.int32)
@@ -38,6 +38,7 @@ def run(engine, sl):
     for his, pred, y in batches:
         tok, lab = engine.to_device_batch(his[sl], pred[sl], y[sl])
         engine.train_step_dev(tok, lab, his[sl].shape[0], C)
+    engine._sync_table()   # rank-sharded table: bring this replica up to date (no-op on one GPU)
     torch.cuda.synchronize()
     return engine.params.theta.clone()
 
