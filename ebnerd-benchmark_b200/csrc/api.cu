@@ -15,6 +15,21 @@ static thread_local char g_err[512] = "";
 // call of this thread, so the host can start the table-gradient collective while the remaining backward
 // kernels (the QKV weight-gradient GEMM) still run
 static thread_local cudaEvent_t g_table_grad_event = nullptr;
+// Deferred weight gradient: the QKV wgrad GEMM (tensor-pipe bound) is independent of everything the optimizer's
+// table pass (HBM bound) needs, so on request it runs on a library-owned side stream, forked after the dgrad
+// GEMM, and is joined by ebk_join_deferred() before its output is consumed.
+static thread_local bool g_defer_wgrad = false;
+static thread_local bool g_side_pending = false;
+static thread_local cudaStream_t g_side = nullptr;
+static thread_local cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+static int side_stream_init() {
+  if (g_side == nullptr) {
+    EBK_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+    EBK_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+    EBK_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+  }
+  return EBK_OK;
+}
 // data parallel, rank-sharded table: peer mappings used by the embedding gather of the training forward
 static thread_local PeerTables g_peers = {0, 0, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
 
@@ -151,12 +166,25 @@ int check_desc(const ebk_seqenc_desc* d) {
 using namespace ebk;
 
 extern "C" const char* ebk_last_error(void) { return g_err; }
+extern "C" int ebk_join_deferred(void* stream);
 namespace ebk { void gemm_tf32_set_debug(long long* buf, int target); }
 // debugging aid: device buffer of 3*96*4 int64 receiving clock64() stamps of CTA 0 of the target-th
 // tcgen05 GEMM launched after this call (NULL disarms)
 extern "C" int ebk_debug_gemm_timeline(long long* device_buf, int target) {
   ebk::gemm_tf32_set_debug(device_buf, target);
   return 0;
+}
+extern "C" int ebk_set_deferred_wgrad(int on) {
+  g_defer_wgrad = on != 0;
+  return EBK_OK;
+}
+extern "C" int ebk_join_deferred(void* stream) {
+  if (g_side_pending) {
+    EBK_CUDA(cudaEventRecord(g_ev_join, g_side));
+    EBK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, g_ev_join, 0));
+    g_side_pending = false;
+  }
+  return EBK_OK;
 }
 extern "C" int ebk_set_table_grad_event(void* cuda_event) {
   g_table_grad_event = (cudaEvent_t)cuda_event;
@@ -259,6 +287,7 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
     return EBK_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  EBK_TRY(ebk_join_deferred(stream));   // a forgotten deferred weight gradient may still read this workspace
   g_prof_user = tok == nullptr;
   const int R = d->n_seq * d->L, D = d->nh * d->dh;
   Dropout drop1 = make_dropout(training != 0, d->dropout, seed1);
@@ -401,7 +430,21 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
       EBK_CUDA(cudaEventRecord(g_table_grad_event, st));
       g_table_grad_event = nullptr;
     }
-    // dWqkv += X^T dQKV  (X = dropout1(gather))
+    // dWqkv += X^T dQKV  (X = dropout1(gather)); deferred mode: on the side stream, behind the dgrad GEMM
+    if (g_defer_wgrad && tok != nullptr) {
+      EBK_TRY(side_stream_init());
+      EBK_CUDA(cudaEventRecord(g_ev_fork, st));
+      EBK_CUDA(cudaStreamWaitEvent(g_side, g_ev_fork, 0));
+      cudaStream_t main_st = st;
+      {
+        cudaStream_t st = g_side;   // EBK_PROF records its events on `st`
+        EBK_PROF(T_QKV_WGRAD, gemm_tma(ws.xd, d->Din, true, ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din, 3 * D, R, 1.0f,
+                                       1.0f, st, -1));
+      }
+      (void)main_st;
+      g_side_pending = true;
+      return EBK_OK;
+    }
     EBK_PROF(T_QKV_WGRAD, gemm_tma(ws.xd, d->Din, true, ws.dqkv, 3 * D, false, dWqkv, 3 * D, d->Din, 3 * D, R, 1.0f, 1.0f,
                                    st, -1));
     return EBK_OK;

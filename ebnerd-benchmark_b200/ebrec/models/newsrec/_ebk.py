@@ -22,7 +22,7 @@ MATH_TF32X3 = 2
 
 SYMBOLS = [
     "ebk_last_error", "ebk_version", "ebk_device_ok",
-    "ebk_seqenc_workspace_bytes", "ebk_seqenc_fwd", "ebk_seqenc_bwd", "ebk_set_table_grad_event", "ebk_ipc_export", "ebk_ipc_open", "ebk_set_peer_tables",
+    "ebk_seqenc_workspace_bytes", "ebk_seqenc_fwd", "ebk_seqenc_bwd", "ebk_set_table_grad_event", "ebk_set_deferred_wgrad", "ebk_join_deferred", "ebk_ipc_export", "ebk_ipc_open", "ebk_set_peer_tables",
     "ebk_score_softmax_ce", "ebk_score_sigmoid", "ebk_adam_keras_step",
     "ebk_embed_adam_workspace_bytes", "ebk_embed_adam_step",
     "ebk_dense_workspace_bytes", "ebk_dense_fwd", "ebk_dense_bwd", "ebk_sumsq_accum",
@@ -93,6 +93,8 @@ def lib() -> C.CDLL:
     l.ebk_seqenc_bwd.argtypes = [dp, vp, vp, vp, vp, vp, vp, C.c_int, u64, u64, vp, sz, vp,
                                  vp, vp, vp, vp, vp, vp, vp]
     l.ebk_set_table_grad_event.argtypes = [vp]
+    l.ebk_set_deferred_wgrad.argtypes = [C.c_int]
+    l.ebk_join_deferred.argtypes = [vp]
     l.ebk_ipc_export.argtypes = [vp, vp, C.POINTER(sz)]
     l.ebk_ipc_open.argtypes = [vp, sz, C.POINTER(vp)]
     l.ebk_set_peer_tables.argtypes = [C.POINTER(vp), i32, sz]

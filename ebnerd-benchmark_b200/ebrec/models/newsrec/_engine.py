@@ -14,6 +14,7 @@ Reference: src/ebrec/models/newsrec/nrms.py:23-210 (graph wiring, loss, optimize
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -382,6 +383,7 @@ class NRMSEngine:
                                                self.dropout, seed1, _ebk.ptr(P.theta), _ebk.ptr(P.grad), _ebk.ptr(P.m),
                                                _ebk.ptr(P.v), alpha, self.beta1, self.beta2, self.eps, _ebk.ptr(ws),
                                                ws.numel(), _ebk.stream()))
+            _ebk.check(lib.ebk_join_deferred(_ebk.stream()))   # the deferred QKV weight gradient is needed from here on
             lo = P.offsets["news_Wqkv"]  # everything behind the table
             th, g, m, v = P.theta[lo:], P.grad[lo:], P.m[lo:], P.v[lo:]
             _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(th), _ebk.ptr(g), _ebk.ptr(m), _ebk.ptr(v), P.n - lo, alpha,
@@ -521,7 +523,14 @@ class NRMSEngine:
             self.apply_adam()
             return loss, probs
         seeds = self.step_seeds()
-        loss, probs = self.loss_and_grads_dev(tok_all, labels, B, C_, training=True, seeds=seeds, sparse_table=sparse)
+        lib = _ebk.lib()
+        defer = os.environ.get("EBK_DEFER_WGRAD", "1") != "0"
+        # the QKV weight-gradient GEMM (tensor bound) overlaps the table's Adam pass (HBM bound): see ebk.h
+        lib.ebk_set_deferred_wgrad(1 if defer else 0)
+        try:
+            loss, probs = self.loss_and_grads_dev(tok_all, labels, B, C_, training=True, seeds=seeds, sparse_table=sparse)
+        finally:
+            lib.ebk_set_deferred_wgrad(0)
         self.apply_adam(sparse=(tok_all, seeds[0]) if sparse else None)
         return loss, probs
 

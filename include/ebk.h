@@ -98,6 +98,14 @@ int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, const float* ta
                    float* dWqkv, float* dattW, float* dattb, float* dattq,
                    float* d_table, float* d_x, void* stream);
 
+/* Deferred weight gradient (single-GPU optimizer overlap).  After ebk_set_deferred_wgrad(1), ebk_seqenc_bwd calls
+ * of this thread WITH token ids launch their QKV weight-gradient GEMM (tensor-pipe bound) on a library-owned side
+ * stream, forked behind the input-gradient GEMM, and return without joining it: the caller may then enqueue work
+ * that does not touch dWqkv or the call's workspace (the HBM-bound table pass of the optimizer) on its own stream
+ * and MUST call ebk_join_deferred(stream) before anything that does (and before the next forward). */
+int ebk_set_deferred_wgrad(int on);
+int ebk_join_deferred(void* stream);
+
 /* Data parallel: arm a cudaEvent_t (as void*) that the NEXT ebk_seqenc_bwd call of this thread with token ids
  * records on its stream right after the embedding-gradient scatter -- the table gradient is then final, so its
  * collective can start while the remaining backward kernels still run.  NULL disarms. */
