@@ -314,6 +314,8 @@ def run_ours(args, w, wname):
     # (every rank runs the steps -- they contain the gradient collective -- only rank 0 records events)
     prof = {}
     psteps = min(args.steps, 10)
+    # per-kernel durations are taken with the wgrad/Adam overlap switched off, so that each kernel is timed alone
+    os.environ["EBK_DEFER_WGRAD"] = "0"
     if rank == 0:
         lib.ebk_prof_enable(1)
     for i in range(psteps):
@@ -322,6 +324,7 @@ def run_ours(args, w, wname):
     if rank == 0:
         prof = {k: (ms_ / psteps, max(1, c // psteps)) for k, (ms_, c) in _ebk.prof_collect().items()}
         lib.ebk_prof_enable(0)
+    os.environ.pop("EBK_DEFER_WGRAD", None)
     sync_all()
 
     cpu = None
