@@ -188,6 +188,24 @@ class NRMSEngine:
                                       _ebk.ptr(u), _ebk.stream()))
         return n_all, u, (dn, wn, du, wu)
 
+    # ------------------------------------------------------------------ device-resident article matrix (8f row 1)
+    def set_article_matrix(self, matrix: np.ndarray) -> None:
+        """Upload the [n_articles + 1, T] token matrix of a dataloader once; batches then carry row indices."""
+        m = np.ascontiguousarray(np.asarray(matrix), dtype=np.int32)
+        if m.ndim != 2 or m.shape[1] != self.T:
+            raise ValueError(f"article matrix must be [n_articles, title_size={self.T}], got {m.shape}")
+        self.article_matrix = torch.from_numpy(m).to(self.device)
+
+    def tokens_from_indices(self, his_idx: np.ndarray, pred_idx: np.ndarray) -> torch.Tensor:
+        """[B,H] + [B,C] article row indices -> [B*H + B*C, T] int32 token rows on the device (history first)."""
+        if getattr(self, "article_matrix", None) is None:
+            raise ValueError("index batches need set_article_matrix(lookup_article_matrix) first")
+        idx = np.concatenate([np.asarray(his_idx).reshape(-1), np.asarray(pred_idx).reshape(-1)]).astype(np.int64)
+        n = self.article_matrix.shape[0]
+        if idx.size and (idx.min() < 0 or idx.max() >= n):
+            raise IndexError(f"article row index outside [0, {n})")
+        return self.article_matrix.index_select(0, torch.from_numpy(idx).to(self.device, non_blocking=True))
+
     @staticmethod
     def pack_tokens(his: np.ndarray, pred: np.ndarray) -> np.ndarray:
         """[B,H,T] + [B,C,T] -> [B*H + B*C, T] int32 (history rows first)."""
@@ -229,17 +247,26 @@ class NRMSEngine:
         encoder; device-side index_select puts the vectors back in [B, C] order for the score kernel."""
         lib = _ebk.lib()
         his, pred = np.asarray(his), np.asarray(pred)
-        B, H, T = his.shape
+        B, H = his.shape[0], his.shape[1]
         C_ = pred.shape[1]
         if H != self.H:
             raise ValueError(f"history length {H} != hparams.history_size {self.H}")
-        rows = np.concatenate([his.reshape(B * H, T), pred.reshape(B * C_, T)]).astype(np.int32, copy=False)
-        uniq, inv = np.unique(rows, axis=0, return_inverse=True)
+        if his.ndim == 2:   # device feed: article row indices; distinct articles = distinct indices
+            rows = np.concatenate([his.reshape(-1), pred.reshape(-1)])
+            ids, inv = np.unique(rows, return_inverse=True)
+            if getattr(self, "article_matrix", None) is None:
+                raise ValueError("index batches need set_article_matrix(lookup_article_matrix) first")
+            uniq = self.article_matrix.index_select(0, torch.from_numpy(ids.astype(np.int64)).to(self.device))
+        else:
+            T = his.shape[2]
+            rows = np.concatenate([his.reshape(B * H, T), pred.reshape(B * C_, T)]).astype(np.int32, copy=False)
+            uniq, inv = np.unique(rows, axis=0, return_inverse=True)
+            uniq = torch.from_numpy(np.ascontiguousarray(uniq)).to(self.device)
         inv = inv.reshape(-1)
         users, uinv = np.unique(inv[: B * H].reshape(B, H), axis=0, return_inverse=True)
         uinv = uinv.reshape(-1)
         dev = self.device
-        n_u = self.encode_news_dev(torch.from_numpy(np.ascontiguousarray(uniq)).to(dev))
+        n_u = self.encode_news_dev(uniq)
         hist = n_u.index_select(0, torch.from_numpy(users.reshape(-1).astype(np.int64)).to(dev)).contiguous()
         u_u = self.encode_user_dev(hist, users.shape[0])
         news_c = n_u.index_select(0, torch.from_numpy(inv[B * H:].astype(np.int64)).to(dev)).contiguous()
@@ -536,7 +563,10 @@ class NRMSEngine:
 
     # ------------------------------------------------------------------ host-array convenience
     def to_device_batch(self, his: np.ndarray, pred: np.ndarray, y: np.ndarray | None = None):
-        tok = torch.from_numpy(self.pack_tokens(np.asarray(his), np.asarray(pred))).to(self.device, non_blocking=True)
+        if np.asarray(his).ndim == 2:   # article row indices of a device-feed loader
+            tok = self.tokens_from_indices(his, pred)
+        else:
+            tok = torch.from_numpy(self.pack_tokens(np.asarray(his), np.asarray(pred))).to(self.device, non_blocking=True)
         lab = None
         if y is not None:
             lab = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).to(self.device, non_blocking=True)

@@ -198,6 +198,11 @@ class KerasLikeModel:
     def _batches(self, x, y, batch_size, shuffle, rng):
         """Yield (inputs_tuple, y_or_None).  Arrays: Keras shuffles samples; Sequence: batch order."""
         if _is_sequence(x):
+            if getattr(x, "device_feed", False) and hasattr(self._engine, "set_article_matrix"):
+                # device-resident feed: upload the loader's token matrix once, batches are row indices
+                if getattr(self._engine, "_article_matrix_src", None) is not x.lookup_article_matrix:
+                    self._engine.set_article_matrix(x.lookup_article_matrix)
+                    self._engine._article_matrix_src = x.lookup_article_matrix
             order = np.arange(len(x))
             if shuffle:
                 rng.shuffle(order)

@@ -150,6 +150,32 @@ class NRMSDataLoader(NewsrecDataLoader):
 
 
 @dataclass
+class NRMSDataLoaderDevice(NRMSDataLoader):
+    """Device-resident batch feed (not in the reference): the
+    ``[n_articles + 1, title_size]`` token matrix (``lookup_article_matrix``) is uploaded to HBM once by the model
+    (``fit`` / ``predict`` see ``device_feed``) and a batch is only the article ROW INDICES --
+    train: ((his_idx [B,H] int32, pred_idx [B,C] int32), y [B,C]); eval: ((his_idx [sumN,H], pred_idx [sumN,1]), y [sumN,1])
+    -- 30x fewer host->device bytes than the token tensors of NRMSDataLoader and no per-batch host gather
+    (dataloader.py:110-118).  ``lookup_article_matrix[batch indices]`` reproduces NRMSDataLoader's batch exactly."""
+
+    device_feed = True
+
+    def __getitem__(self, idx):
+        sl = self._slice(idx)
+        hist, inview, y = self._hist_idx[sl], self._inview_idx[sl], self.y[sl]
+        if self.eval_mode:
+            repeats = np.array([len(r) for r in inview])
+            batch_y = np.array([v for row in y for v in row]).reshape(-1, 1)
+            his_idx = np.repeat(np.array(hist, dtype=np.int32), repeats, axis=0)
+            pred_idx = np.array([v for row in inview for v in row], dtype=np.int32)[:, None]
+        else:
+            batch_y = np.array(y)
+            his_idx = np.array(hist, dtype=np.int32)
+            pred_idx = np.array(inview, dtype=np.int32)
+        return (his_idx, pred_idx), batch_y
+
+
+@dataclass
 class NRMSDataLoaderPretransform(NRMSDataLoader):
     """Reference: pre-transforms the whole frame in __post_init__ (dataloader.py:122-180).  Every loader
     of this build already does that, so this is the same class under the reference's name."""

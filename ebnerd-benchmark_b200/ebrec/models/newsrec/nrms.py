@@ -30,8 +30,9 @@ class _NRMSTrainModel(KerasLikeModel):
 
     def _pack(self, inputs, y=None):
         his, pred = (np.asarray(a) for a in inputs)
-        if his.ndim != 3 or pred.ndim != 3:
-            raise ValueError(f"expected his [B,H,T] and pred [B,C,T], got {his.shape} and {pred.shape}")
+        if his.ndim != pred.ndim or his.ndim not in (2, 3):
+            raise ValueError(f"expected his [B,H,T] and pred [B,C,T] (or [B,H] / [B,C] article indices of a device-feed "
+                             f"loader), got {his.shape} and {pred.shape}")
         B, C_ = pred.shape[0], pred.shape[1]
         tok, lab = self._engine.to_device_batch(his, pred, y)
         return tok, lab, B, C_
@@ -49,8 +50,8 @@ class _NRMSTrainModel(KerasLikeModel):
     def _predict_batch(self, inputs):
         # distinct articles / histories are encoded once (the eval-mode loader repeats the history per candidate)
         his, pred = (np.asarray(a) for a in inputs)
-        if his.ndim != 3 or pred.ndim != 3:
-            raise ValueError(f"expected his [B,H,T] and pred [B,C,T], got {his.shape} and {pred.shape}")
+        if his.ndim != pred.ndim or his.ndim not in (2, 3):
+            raise ValueError(f"expected his [B,H,T] and pred [B,C,T] (or article indices), got {his.shape} and {pred.shape}")
         return self._engine.predict_host_dedup(his, pred, head=self._head).cpu().numpy()
 
 

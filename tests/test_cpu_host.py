@@ -78,6 +78,29 @@ def test_nrms_dataloader_contract(sample):
     assert len(last[1]) == sum(len(r) for r in beh["article_ids_inview"][(len(test) - 1) * BATCH:])
 
 
+def test_device_feed_loader_indices_reproduce_token_batches(sample):
+    """NRMSDataLoaderDevice: lookup_article_matrix[batch indices] == NRMSDataLoader's batch,
+    train and eval mode, so gather indices stay bit-exact when the gather moves to the device."""
+    from ebrec.models.newsrec.dataloader import NRMSDataLoader, NRMSDataLoaderDevice
+
+    beh, mapping = sample
+    nmin = min(len(r) for r in beh["article_ids_inview"])
+    keep = [i for i, r in enumerate(beh["article_ids_inview"]) if len(r) == nmin]
+    train = {k: [v[i] for i in keep] for k, v in beh.items()}
+    kw = dict(article_dict=mapping, history_column="article_id_fixed", unknown_representation="zeros", batch_size=64)
+    for frame, eval_mode in ((train, False), (beh, True)):
+        host = NRMSDataLoader(behaviors=frame, eval_mode=eval_mode, **kw)
+        dev = NRMSDataLoaderDevice(behaviors=frame, eval_mode=eval_mode, **kw)
+        assert dev.device_feed and len(dev) == len(host)
+        for i in (0, len(host) - 1):
+            (his, pred), y = host[i]
+            (hi, pi), yi = dev[i]
+            assert hi.dtype == np.int32 and hi.ndim == 2 and pi.ndim == 2
+            assert np.array_equal(dev.lookup_article_matrix[hi], his)
+            assert np.array_equal(dev.lookup_article_matrix[pi], pred)
+            assert np.array_equal(y, yi)
+
+
 def test_unknown_article_ids_map_to_row_zero(sample):
     from ebrec.models.newsrec.dataloader import NRMSDataLoader
 
