@@ -118,14 +118,14 @@ __global__ void __launch_bounds__(PT) attpool_bwd_fused_kernel(int L, int D, int
                                                                 const float* __restrict__ hbuf,
                                                                 const float* __restrict__ attq,
                                                                 const float* __restrict__ w,
-                                                                const float* __restrict__ d_out,
+                                                                const float* __restrict__ d_out, int dout_ld,
                                                                 float* __restrict__ da, float* __restrict__ dpre,
                                                                 float* __restrict__ colpart) {
   __shared__ float dw_s[64];
   __shared__ float da_s[64];
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = PT / 32;
-  const float4* g4 = reinterpret_cast<const float4*>(d_out + (long)n * D);
+  const float4* g4 = reinterpret_cast<const float4*>(d_out + (long)n * dout_ld);
   const int D4 = D >> 2;
   for (int t = warp; t < L; t += nwarp) {
     const float4* x4 = reinterpret_cast<const float4*>(y0 + ((long)n * L + t) * D);
@@ -285,10 +285,13 @@ int attpool_bwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop,
 }
 
 int attpool_bwd_fused(int n_seq, int L, int D, int att, const float* y0, const float* hbuf, const float* attq,
-                      const float* w, const float* d_out, float* da, float* dpre, float* colpart, cudaStream_t st) {
+                      const float* w, const float* d_out, float* da, float* dpre, float* colpart, cudaStream_t st,
+                      int dout_ld) {
   if (n_seq <= 0) return EBK_OK;
-  EBK_CHECK_ARG(L <= 64 && D % 4 == 0, "attpool: L=%d > 64 or D=%d not a multiple of 4", L, D);
-  attpool_bwd_fused_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, hbuf, attq, w, d_out, da, dpre, colpart);
+  if (dout_ld <= 0) dout_ld = D;
+  EBK_CHECK_ARG(L <= 64 && D % 4 == 0 && dout_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0,
+                "attpool: L=%d > 64, or D=%d / dout_ld=%d not multiples of 4", L, D, dout_ld);
+  attpool_bwd_fused_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, hbuf, attq, w, d_out, dout_ld, da, dpre, colpart);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

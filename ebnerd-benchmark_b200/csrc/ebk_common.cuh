@@ -237,7 +237,8 @@ int attpool_bwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop,
 // TMA-path variant: y0 is already dropout(Y0); dy is NOT written (the dpre.W^T GEMM adds w_t*d_out in its
 // epilogue); per-sequence column sums of dpre and of h*da go to colpart [n_seq, 2*att] (dattb | dattq partials)
 int attpool_bwd_fused(int n_seq, int L, int D, int att, const float* y0, const float* hbuf, const float* attq,
-                      const float* w, const float* d_out, float* da, float* dpre, float* colpart, cudaStream_t st);
+                      const float* w, const float* d_out, float* da, float* dpre, float* colpart, cudaStream_t st,
+                      int dout_ld = 0 /*0 => D*/);
 // column sums: out[j] += sum_r coef[r] * X[r,j]   (coef may be NULL => 1); deterministic
 // two-stage reduction through `partial` (colsum_partial_floats(R, Ncols) floats of scratch)
 int colsum_accum_ws(int R, int Ncols, const float* X, int ldx, const float* coef, float* out, float* partial,

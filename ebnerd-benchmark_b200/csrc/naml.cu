@@ -14,6 +14,8 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 struct AttWs {
   float *hbuf, *w, *da, *dpre, *colsum, *w_f, *w_f_lo, *w_d;
+  // TMA path (EBK_MATH_TF32): tf32(dropout(x)), tf32(W), per-sequence column partials and their reduction scratch
+  float *xd, *w_r, *colpart, *colsum2;
   size_t bytes;
 };
 AttWs att_layout(const ebk_attlayer_desc& d, void* base) {
@@ -33,8 +35,17 @@ AttWs att_layout(const ebk_attlayer_desc& d, void* base) {
   w.w_f = take(gemm_tf32_packed_floats(d.att, d.D, false));
   w.w_f_lo = take(gemm_tf32_packed_floats(d.att, d.D, false));
   w.w_d = take(gemm_tf32_packed_floats(d.D, d.att, true));
+  w.xd = take(R * d.D + 64);
+  w.w_r = take((size_t)d.D * d.att + 64);
+  w.colpart = take((size_t)d.n_seq * 2 * d.att);
+  w.colsum2 = take(colsum_partial_floats(d.n_seq, 2 * d.att));
   w.bytes = off;
   return w;
+}
+// all-TMA path of the standalone AttLayer2 (same kernels as the sequence encoder's, api.cu)
+bool att_tma(const ebk_attlayer_desc& d, const AttWs& ws, int ld_out) {
+  return d.math == EBK_MATH_TF32 && d.att % 4 == 0 && ld_out % 4 == 0 &&
+         gemm_tma_eligible(ws.xd, d.D, ws.w_r, d.att, 1, 1, 1);
 }
 int check_att(const ebk_attlayer_desc* d) {
   EBK_CHECK_ARG(d != nullptr, "attlayer: null descriptor");
@@ -70,6 +81,8 @@ ConvGeom conv_geom(const ebk_conv1d_desc& d) {
 }
 struct ConvWs {
   float *xg, *dzp, *dx, *wrev, *colsum, *wc_f, *wrev_f;
+  // TMA path (EBK_MATH_TF32): outputs over the whole padded row space + tf32 copies of the kernels
+  float *yp, *dxp, *wc_r;
   int32_t* gidx;
   size_t bytes;
 };
@@ -90,8 +103,17 @@ ConvWs conv_layout(const ebk_conv1d_desc& d, void* base) {
   w.wc_f = take(gemm_tf32_packed_floats(d.F, d.window * d.E, false));
   w.wrev_f = take(gemm_tf32_packed_floats(d.E, d.window * d.F, false));
   w.gidx = reinterpret_cast<int32_t*>(take((size_t)g.R));
+  w.yp = take((size_t)g.Q * d.F + 64);
+  w.dxp = take((size_t)g.Q * d.E + 64);
+  w.wc_r = take((size_t)d.window * d.E * d.F + 64);
   w.bytes = off;
   return w;
+}
+// all-TMA path: the convolution windows are rows of an OVERLAPPING strided view (row stride E, row length
+// window*E) of the padded embedding buffer -- a plain 2-D tensor map -- evaluated at every padded row; the
+// (window-1) junk rows per article are dropped when the bias/activation pass compacts the result.
+bool conv_tma(const ebk_conv1d_desc& d, const ConvWs& ws) {
+  return d.math == EBK_MATH_TF32 && gemm_tma_eligible(ws.xg, d.E, ws.wc_r, d.F, 1, 1, 1) && d.n_seq * (d.L + d.window - 1) > d.window;
 }
 int check_conv(const ebk_conv1d_desc* d) {
   EBK_CHECK_ARG(d != nullptr, "conv1d: null descriptor");
@@ -106,7 +128,8 @@ int check_conv(const ebk_conv1d_desc* d) {
 
 // XG rows (incl. guard and pad rows, which are zero): 128-bit gather of table rows, dropout mask applied
 __global__ void embed_pad_kernel(float4* __restrict__ xg, const int32_t* __restrict__ tok, const float4* __restrict__ table,
-                                 long rows, long Q, int L, int Lp, int padL, int G, int E4, int V, Dropout drop) {
+                                 long rows, long Q, int L, int Lp, int padL, int G, int E4, int V, Dropout drop,
+                                 int round_out) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= rows * E4) return;
   const long row = i / E4;
@@ -125,10 +148,39 @@ __global__ void embed_pad_kernel(float4* __restrict__ xg, const int32_t* __restr
           const float4 f = drop.factor4_group((uint64_t)(r * E4 + c4));
           v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
         }
+        if (round_out) {
+          v.x = round_tf32_bits(v.x); v.y = round_tf32_bits(v.y); v.z = round_tf32_bits(v.z); v.w = round_tf32_bits(v.w);
+        }
       }
     }
   }
   xg[i] = v;
+}
+
+// y[r, :] = act(yp[gidx[r], :] + b): drops the junk rows of the padded-space convolution
+__global__ void bias_act_gather_kernel(float4* __restrict__ y, const float4* __restrict__ yp, const int32_t* __restrict__ gidx,
+                                       const float4* __restrict__ b, long R, int F4, int relu) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= R * F4) return;
+  const long r = i / F4;
+  const int c4 = (int)(i - r * F4);
+  float4 v = yp[(long)gidx[r] * F4 + c4];
+  const float4 bb = b[c4];
+  v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+  if (relu) {
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+  }
+  y[i] = v;
+}
+
+// dx[r, :] = dxp[gidx[r], :]   (compaction of the padded-space data gradient)
+__global__ void gather_rows_kernel(float4* __restrict__ dx, const float4* __restrict__ dxp, const int32_t* __restrict__ gidx,
+                                   long R, int E4, long rows_p) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= R * E4) return;
+  const long r = i / E4;
+  const long q = gidx[r];
+  dx[i] = q < rows_p ? dxp[q * E4 + (i - r * E4)] : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // dzp rows: dz = dy * dropout_out' * act'(y) at the token rows, zero at the pad rows
@@ -272,6 +324,15 @@ extern "C" int ebk_attlayer_fwd(const ebk_attlayer_desc* d, const float* x, cons
   cudaStream_t st = (cudaStream_t)stream;
   const int R = d->n_seq * d->L, D = d->D;
   const Dropout drop = make_dropout(training != 0, d->dropout, seed);
+  if (att_tma(*d, ws, out_ld)) {
+    // tf32(dropout(x)) is materialised once; the GEMM and the pooling read it without touching the mask again
+    const Dropout none = make_dropout(false, 0.f, 0);
+    EBK_TRY(embed_rows(R, D, 0, nullptr, x, drop, ws.xd, st));
+    EBK_TRY(round_tf32_copy(ws.w_r, W, (size_t)D * d->att, st));
+    EBK_PROF(T_ATT_GEMM_FWD, gemm_tma(ws.xd, D, false, ws.w_r, d->att, false, ws.hbuf, d->att, R, d->att, D, 0.0f, 1.0f, st, -1));
+    EBK_PROF(T_POOL_FWD, attpool_fwd(d->n_seq, d->L, D, d->att, ws.xd, none, ws.hbuf, b, q, ws.w, out, st, out_ld));
+    return EBK_OK;
+  }
   const bool tc = d->math != EBK_MATH_FP32, x3 = d->math == EBK_MATH_TF32X3;
   GemmOperandA ax{x, D, false, nullptr, 0, drop, D};
   const bool pk = tc && gemm_tf32_eligible(ax, W, d->att, R, d->att, D);
@@ -303,6 +364,19 @@ extern "C" int ebk_attlayer_bwd(const ebk_attlayer_desc* d, const float* x, cons
   const int R = d->n_seq * d->L, D = d->D;
   const Dropout drop = make_dropout(training != 0, d->dropout, seed);
   const Dropout none = make_dropout(false, 0.f, 0);
+  if (att_tma(*d, ws, d_out_ld)) {
+    // ws.xd / ws.w_r / ws.hbuf / ws.w are the forward's
+    EBK_PROF(T_POOL_BWD, attpool_bwd_fused(d->n_seq, d->L, D, d->att, ws.xd, ws.hbuf, q, ws.w, d_out, ws.da, ws.dpre,
+                                           ws.colpart, st, d_out_ld));
+    EBK_PROF(T_COLSUM, colsum_accum_ws(d->n_seq, d->att, ws.colpart, 2 * d->att, nullptr, db, ws.colsum2, st));
+    EBK_PROF(T_COLSUM, colsum_accum_ws(d->n_seq, d->att, ws.colpart + d->att, 2 * d->att, nullptr, dq, ws.colsum2, st));
+    EBK_PROF(T_ATT_WGRAD, gemm_tma(ws.xd, D, true, ws.dpre, d->att, false, dW, d->att, D, d->att, R, 1.0f, 1.0f, st, -1));
+    // dx = w_t d_out + dpre W^T (gradient w.r.t. the MASKED input; the producer of x applies the mask)
+    const GemmEpilogue dx_epi{ws.w, d_out, d_out_ld, d->L, none, 0, false};
+    EBK_PROF(T_ATT_DGRAD, gemm_tma(ws.dpre, d->att, false, ws.w_r, d->att, true, dx, D, R, D, d->att, 0.0f, 1.0f, st, 0,
+                                   &dx_epi));
+    return EBK_OK;
+  }
   const bool tc = d->math != EBK_MATH_FP32, x3 = d->math == EBK_MATH_TF32X3;
   const bool rnd = tc && !x3;
   GemmOperandA adp{ws.dpre, d->att, false, nullptr, 0, none, 0};
@@ -348,12 +422,25 @@ extern "C" int ebk_conv1d_fwd(const ebk_conv1d_desc* d, const int32_t* tok, cons
     const long rows = g.Q + 2 * g.G, n4 = rows * (E / 4);
     embed_pad_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(ws.xg), tok,
                                                                    reinterpret_cast<const float4*>(table), rows, g.Q, d->L,
-                                                                   g.Lp, g.padL, g.G, E / 4, d->V, drop);
+                                                                   g.Lp, g.padL, g.G, E / 4, d->V, drop,
+                                                                   conv_tma(*d, ws) ? 1 : 0);
     EBK_LAUNCH_CHECK();
     conv_gidx_kernel<<<(unsigned)((g.R + 255) / 256), 256, 0, st>>>(ws.gidx, g.R, d->L, g.Lp);
     EBK_LAUNCH_CHECK();
   }
   if (prof_on()) prof_end(T_EMBED_PAD, st);
+  if (conv_tma(*d, ws)) {
+    EBK_TRY(round_tf32_copy(ws.wc_r, Wc, (size_t)KW * F, st));
+    // yp[q] = window(q) . Wc for every padded row q (window(q) = XG rows G+q .. G+q+w-1, contiguous)
+    EBK_PROF(T_CONV_FWD, gemm_tma(ws.xg + (size_t)g.G * E, E, false, ws.wc_r, F, false, ws.yp, F, (int)g.Q, F, KW, 0.0f, 1.0f,
+                                  st, -1));
+    const long n4 = g.R * (F / 4);
+    bias_act_gather_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(ws.yp), ws.gidx, reinterpret_cast<const float4*>(bc),
+        g.R, F / 4, d->relu);
+    EBK_LAUNCH_CHECK();
+    return EBK_OK;
+  }
   const bool tc = d->math != EBK_MATH_FP32, x3 = d->math == EBK_MATH_TF32X3;
   GemmOperandA ax{ws.xg + (size_t)g.G * E, E, false, ws.gidx, (int)g.Q, none, 0};
   const bool pk = tc && !x3 && gemm_tf32_eligible(ax, Wc, F, (int)g.R, F, KW);
@@ -395,6 +482,27 @@ extern "C" int ebk_conv1d_bwd(const ebk_conv1d_desc* d, const int32_t* tok, cons
   }
   if (prof_on()) prof_end(T_CONV_DZ, st);
   EBK_PROF(T_COLSUM, colsum_accum_ws((int)g.Q, F, ws.dzp, F, nullptr, dbc, ws.colsum, st));  // pad rows are zero
+  if (conv_tma(*d, ws)) {
+    // ws.xg holds tf32(dropout(gather)) from the forward, dzp was rounded by conv_dz_kernel
+    EBK_PROF(T_CONV_WGRAD, gemm_tma(ws.xg + (size_t)(g.G - g.padR) * E, E, true, ws.dzp, F, false, dWc, F, KW, F, (int)g.Q, 1.0f,
+                                    1.0f, st, -1));
+    if (d_table != nullptr) {
+      const long nw = (long)w * E * F;
+      conv_wrev_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(ws.wrev, Wc, w, E, F);
+      EBK_LAUNCH_CHECK();
+      EBK_TRY(round_tf32_copy(ws.wc_r, ws.wrev, (size_t)nw, st));   // wc_r is free again: reuse it for tf32(wrev)
+      // dxp[q] = dz-window(q) . wrev for the padded rows whose window stays inside dzp
+      const long rows_p = g.Q - (w - 1);
+      EBK_PROF(T_CONV_DGRAD, gemm_tma(ws.dzp, F, false, ws.wc_r, E, false, ws.dxp, E, (int)rows_p, E, w * F, 0.0f, 1.0f, st, -1));
+      const long n4 = g.R * (E / 4);
+      gather_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(ws.dx),
+                                                                       reinterpret_cast<const float4*>(ws.dxp), ws.gidx, g.R,
+                                                                       E / 4, rows_p);
+      EBK_LAUNCH_CHECK();
+      EBK_PROF(T_SCATTER, scatter_rows_add((int)g.R, E, d->V, tok, ws.dx, drop_in, d_table, st));
+    }
+    return EBK_OK;
+  }
   // dWc += XG_window^T dzp over the whole padded row space (guard rows make every window readable)
   GemmOperandA axT{ws.xg + (size_t)(g.G - g.padR) * E, E, true, nullptr, 0, none, 0};
   EBK_PROF(T_CONV_WGRAD, gemm_dispatch(d->math, axT, ws.dzp, F, false, dWc, F, KW, F, (int)g.Q, 1.0f, st,
