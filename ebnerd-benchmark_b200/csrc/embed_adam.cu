@@ -12,6 +12,8 @@
 // Rows referenced more than CAP times (padding / very frequent tokens in real data) are pre-reduced with
 // atomics into the dense gradient buffer by a separate pass and read from there, so one warp never walks
 // a long list.  HBM bytes per step: 24 B/parameter + R*E*4 instead of 32 B/parameter + 3*R*E*4.
+#include <stdlib.h>
+
 #include "ebk_common.cuh"
 
 namespace ebk {
@@ -232,20 +234,23 @@ extern "C" int ebk_embed_adam_step(int32_t R, int32_t E, int32_t V, const int32_
   const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
   const long warps = V;
   const long blocks = (warps * 32 + 255) / 256;
-  const long cap = 148L * 8 * 8;
+  static const int env_ch = getenv("EBK_ADAM_CH") ? atoi(getenv("EBK_ADAM_CH")) : 0;      // tuning knobs
+  static const int env_cap = getenv("EBK_ADAM_CAP") ? atoi(getenv("EBK_ADAM_CAP")) : 0;
+  const long cap = 148L * (env_cap > 0 ? env_cap : 8) * 8;
   const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
   if (prof_on()) prof_begin(T_ADAM, st);
   const int nc = ceil_div(E4, 32);
-  if (nc % 3 == 0)
-    embed_adam_kernel<3><<<grid, 256, 0, st>>>(V, E4, count, offset, perm, reinterpret_cast<const float4*>(dX), drop,
-                                               reinterpret_cast<float4*>(d_table), reinterpret_cast<float4*>(theta),
-                                               reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), alpha, omb1,
-                                               omb2, eps);
-  else
-    embed_adam_kernel<2><<<grid, 256, 0, st>>>(V, E4, count, offset, perm, reinterpret_cast<const float4*>(dX), drop,
-                                               reinterpret_cast<float4*>(d_table), reinterpret_cast<float4*>(theta),
-                                               reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), alpha, omb1,
-                                               omb2, eps);
+  // measured on B200 (tools/sweep_adam.sh, E = 768): slices of 2 x 32 float4 -> 0.85 ms, 3 -> 0.97, 6 -> 1.13:
+  // fewer live registers = more resident warps = more loads in flight
+  (void)nc;
+  int ch = env_ch > 0 ? env_ch : 2;
+#define RUN(CH_)                                                                                                  \
+  embed_adam_kernel<CH_><<<grid, 256, 0, st>>>(V, E4, count, offset, perm, reinterpret_cast<const float4*>(dX), drop, \
+                                               reinterpret_cast<float4*>(d_table), reinterpret_cast<float4*>(theta),  \
+                                               reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), alpha, omb1, \
+                                               omb2, eps)
+  if (ch == 1) RUN(1); else if (ch == 2) RUN(2); else if (ch == 3) RUN(3); else RUN(6);
+#undef RUN
   if (prof_on()) prof_end(T_ADAM, st);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
