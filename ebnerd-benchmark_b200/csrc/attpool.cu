@@ -7,7 +7,7 @@
 namespace ebk {
 namespace {
 
-constexpr int PT = 128;  // threads per CTA
+constexpr int PT = 256;  // threads per CTA (measured: 256 beats 128 -- 4 rows per warp instead of 8 in flight)
 constexpr float K_EPS = 1e-7f;  // keras.backend.epsilon()
 
 // hbuf [R, att]: in = X W (pre-activation without bias), out = tanh(. + b)
@@ -21,13 +21,25 @@ __global__ void __launch_bounds__(PT) attpool_fwd_kernel(int L, int D, int att, 
   __shared__ float w_s[64];
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = PT / 32;
+  const bool vec = (att & 3) == 0 && ((reinterpret_cast<uintptr_t>(hbuf) | reinterpret_cast<uintptr_t>(attb) |
+                                      reinterpret_cast<uintptr_t>(attq)) & 15) == 0;
   for (int t = warp; t < L; t += nwarp) {
     float* hrow = hbuf + ((long)n * L + t) * att;
     float acc = 0.0f;
-    for (int j = lane; j < att; j += 32) {
-      float h = tanhf(hrow[j] + attb[j]);
-      hrow[j] = h;
-      acc = fmaf(h, attq[j], acc);
+    if (vec) {
+      for (int j = lane; j < (att >> 2); j += 32) {
+        float4 h = reinterpret_cast<float4*>(hrow)[j];
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(attb) + j), qq = __ldg(reinterpret_cast<const float4*>(attq) + j);
+        h.x = tanhf(h.x + bb.x); h.y = tanhf(h.y + bb.y); h.z = tanhf(h.z + bb.z); h.w = tanhf(h.w + bb.w);
+        reinterpret_cast<float4*>(hrow)[j] = h;
+        acc = fmaf(h.x, qq.x, fmaf(h.y, qq.y, fmaf(h.z, qq.z, fmaf(h.w, qq.w, acc))));
+      }
+    } else {
+      for (int j = lane; j < att; j += 32) {
+        float h = tanhf(hrow[j] + attb[j]);
+        hrow[j] = h;
+        acc = fmaf(h, attq[j], acc);
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) a_s[t] = acc;
