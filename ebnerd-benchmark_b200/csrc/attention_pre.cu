@@ -316,8 +316,8 @@ __global__ void __launch_bounds__(WARPS * 32, 5) attn_fwd_pre_kernel(int n_seq, 
   }
 }
 
-template <int DH, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32, 3) attn_bwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
+template <int DH, int STAGES, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) attn_bwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
                                                                   const float* __restrict__ dy, float* __restrict__ dqkv) {
   extern __shared__ __align__(16) float smem[];
   constexpr int MAT = Cfg<DH>::MAT;
@@ -361,8 +361,12 @@ __global__ void __launch_bounds__(WARPS * 32, 3) attn_bwd_pre_kernel(int n_seq, 
     const float* Gs = Vs + MAT;  // dO
     float* Ds = Vs;              // dS overlays V and dO once dV is done
     float a_acc[2][4][4], d_acc[2][4][4];
+    float o[2][Cfg<DH>::NT][4];
     gemm_xyT<DH>(a_acc, Qs, Ks, g, t);   // A = softmax(Q K^T / sqrt(dh))
     softmax_rows(a_acc, inv, L, t);
+    // dV first: afterwards A is only needed for the dS algebra, so A, dA and an output tile are never all live
+    gemm_regP<DH>(o, a_acc, Gs, g, t);   // dV[q, d] = sum_k A[q, k] dO[k, d]
+    store_rows<DH>(o, 1.0f, dqkv, row0, 3 * D, 2 * D + h * DH, L, g, t);
     gemm_xyT<DH>(d_acc, Vs, Gs, g, t);   // dA = V dO^T
     // dS = A o (dA - rowsum(dA o A))
 #pragma unroll
@@ -382,9 +386,6 @@ __global__ void __launch_bounds__(WARPS * 32, 3) attn_bwd_pre_kernel(int n_seq, 
           for (int e = 0; e < 2; ++e)
             d_acc[mt][nt][hf * 2 + e] = a_acc[mt][nt][hf * 2 + e] * (d_acc[mt][nt][hf * 2 + e] - dot);
       }
-    float o[2][Cfg<DH>::NT][4];
-    gemm_regP<DH>(o, a_acc, Gs, g, t);   // dV[q, d] = sum_k A[q, k] dO[k, d]
-    store_rows<DH>(o, 1.0f, dqkv, row0, 3 * D, 2 * D + h * DH, L, g, t);
     __syncwarp();                        // everyone is done reading V and dO
     store_frag(Ds, d_acc, g, t);         // only the transposed use (dK) needs dS in shared memory
     gemm_regP<DH>(o, d_acc, Ks, g, t);   // dQ[q, d] = sum_k dS[q, k] K[k, d] / sqrt(dh)
@@ -412,6 +413,15 @@ int cfg(Kern kern, size_t smem, long total, int* grid) {
   const long cap = (long)sms * (occ > 0 ? occ : 1);  // persistent: every resident warp walks its items
   *grid = (int)(blocks < cap ? blocks : cap);
   return EBK_OK;
+}
+
+int att_minb() {   // backward kernel: CTAs per SM the register allocation targets (3: no spills, 4: 128 registers)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EBK_ATT_MINB");
+    v = (e && e[0] == '4') ? 4 : 3;
+  }
+  return v;
 }
 
 int att_stages() {
@@ -461,8 +471,13 @@ int attention_core_bwd_pre(int n_seq, int L, int nh, int dh, const float* qkv, c
 #define RUN2(DH_, ST_)                                                                            \
   {                                                                                               \
     const size_t smem = (size_t)WARPS * (ST_ * 4 * Cfg<DH_>::MAT) * sizeof(float) + 64; /* n-tile overhang */ \
-    EBK_TRY(cfg(attn_bwd_pre_kernel<DH_, ST_>, smem, total, &grid));                              \
-    attn_bwd_pre_kernel<DH_, ST_><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, qkv, dy, dqkv);   \
+    if (att_minb() == 4) {                                                                        \
+      EBK_TRY(cfg(attn_bwd_pre_kernel<DH_, ST_, 4>, smem, total, &grid));                         \
+      attn_bwd_pre_kernel<DH_, ST_, 4><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, qkv, dy, dqkv); \
+    } else {                                                                                      \
+      EBK_TRY(cfg(attn_bwd_pre_kernel<DH_, ST_, 3>, smem, total, &grid));                         \
+      attn_bwd_pre_kernel<DH_, ST_, 3><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, qkv, dy, dqkv); \
+    }                                                                                             \
   }
 #define RUN(DH_) { if (att_stages() == 2) RUN2(DH_, 2) else RUN2(DH_, 1) }
   EBK_ATT_DISPATCH(RUN)
