@@ -96,10 +96,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// The single producer / MMA threads share their SM sub-partitions with epilogue warps: after a few failed polls
+// they back off, so that a long wait (epilogue-bound GEMMs, a full stage ring) does not burn the issue slots the
+// epilogue needs.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > SPIN_LIMIT) __trap();  // a protocol bug traps instead of hanging the GPU
+    if (++spins > 4) __nanosleep(40);
+    if (spins > SPIN_LIMIT) __trap();  // a protocol bug traps instead of hanging the GPU
   }
 }
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {

@@ -562,12 +562,32 @@ class NRMSEngine:
         return loss, probs
 
     # ------------------------------------------------------------------ host-array convenience
+    def _h2d(self, key: str, arr: np.ndarray) -> torch.Tensor:
+        """Host array -> device through a small ring of PINNED staging buffers (asynchronous copy: the host goes on
+        launching kernels while the DMA runs).  A slot is reused only after the copy that last read it finished."""
+        ring = self.__dict__.setdefault("_pin_ring", {})
+        slots = ring.setdefault((key, arr.shape, arr.dtype.str), {"i": 0, "bufs": []})
+        if len(slots["bufs"]) < 4:
+            slots["bufs"].append([torch.empty(arr.shape, dtype=torch.from_numpy(arr).dtype).pin_memory(), None])
+            slot = slots["bufs"][-1]
+        else:
+            slot = slots["bufs"][slots["i"] % 4]
+            slots["i"] += 1
+            if slot[1] is not None:
+                slot[1].synchronize()
+        slot[0].numpy()[...] = arr
+        dev = slot[0].to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        slot[1] = ev
+        return dev
+
     def to_device_batch(self, his: np.ndarray, pred: np.ndarray, y: np.ndarray | None = None):
         if np.asarray(his).ndim == 2:   # article row indices of a device-feed loader
             tok = self.tokens_from_indices(his, pred)
         else:
-            tok = torch.from_numpy(self.pack_tokens(np.asarray(his), np.asarray(pred))).to(self.device, non_blocking=True)
+            tok = self._h2d("tok", self.pack_tokens(np.asarray(his), np.asarray(pred)))
         lab = None
         if y is not None:
-            lab = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).to(self.device, non_blocking=True)
+            lab = self._h2d("lab", np.ascontiguousarray(y, dtype=np.float32))
         return tok, lab
