@@ -22,11 +22,14 @@ static thread_local bool g_defer_wgrad = false;
 static thread_local bool g_side_pending = false;
 static thread_local cudaStream_t g_side = nullptr;
 static thread_local cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
+constexpr int GATHER_CHUNKS = 4;
+static thread_local cudaEvent_t g_ev_chunk[GATHER_CHUNKS] = {nullptr, nullptr, nullptr, nullptr};
 static int side_stream_init() {
   if (g_side == nullptr) {
     EBK_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
     EBK_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
     EBK_CUDA(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+    for (int c = 0; c < GATHER_CHUNKS; ++c) EBK_CUDA(cudaEventCreateWithFlags(&g_ev_chunk[c], cudaEventDisableTiming));
   }
   return EBK_OK;
 }
@@ -296,15 +299,47 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   if (tma_path(*d, ws)) {
     // ---- all-TMA path: every GEMM operand is materialised dense, masked and tf32-rounded by the layer
     // before it, so the tensor-core kernels spend no issue slots on operand preparation ----
-    EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st,
-                                        (tok && training && g_peers.world > 1) ? &g_peers : nullptr));
+    const bool remote = tok && training && g_peers.world > 1;   // rank-sharded table: rows come over NVLink
     EBK_TRY(round_tf32_copy(ws.wqkv_r, Wqkv, (size_t)d->Din * 3 * D, st));
     if (pool) EBK_TRY(round_tf32_copy(ws.attw_r, attW, (size_t)D * d->att, st));
-    // (1) Q|K|V = dropout1(gather(table, tok)) . Wqkv        nrms.py:134-139, layers.py:214-230
     // (stored rounded to tf32: the attention kernels feed it to mma.sync without touching it again)
     const GemmEpilogue round_epi{nullptr, nullptr, 0, 1, none, 0, true};
-    EBK_PROF(T_QKV_FWD, gemm_tma(ws.xd, d->Din, false, ws.wqkv_r, 3 * D, false, ws.qkv, 3 * D, R, 3 * D, d->Din, 0.0f,
-                                 1.0f, st, -1, &round_epi));
+    // opt-in (EBK_DP_CHUNKED_GATHER=1): measured on 2 GPUs it does not pay (5.81 vs 5.73 ms/step: the remote share
+    // of the gather is small there and four partial GEMM waves cost more); not yet measured on 8
+    const char* env_ch = getenv("EBK_DP_CHUNKED_GATHER");
+    const bool env_chunked = env_ch != nullptr && atoi(env_ch) != 0;
+    if (remote && env_chunked && R >= GATHER_CHUNKS * 4096) {
+      // The peer-memory gather is NVLink-bound (630 GB/s, ~0.8 ms on 8 GPUs) and the QKV projection tensor-bound:
+      // software-pipeline them over row chunks -- the gather of chunk c+1 runs on the side stream while the GEMM
+      // of chunk c runs here.
+      EBK_TRY(side_stream_init());
+      EBK_CUDA(cudaEventRecord(g_ev_fork, st));
+      EBK_CUDA(cudaStreamWaitEvent(g_side, g_ev_fork, 0));
+      const int chunk = ceil_div(ceil_div(R, GATHER_CHUNKS), 256) * 256;
+      for (int c = 0; c < GATHER_CHUNKS; ++c) {
+        const int r0 = c * chunk, rows = (r0 + chunk <= R ? chunk : R - r0);
+        if (rows <= 0) break;
+        {
+          cudaStream_t st = g_side;   // EBK_PROF records its events on `st`
+          EBK_PROF(T_EMBED_GATHER, embed_rows(rows, d->Din, d->V, tok + r0, table_or_x, drop1, ws.xd + (size_t)r0 * d->Din, st,
+                                              &g_peers, r0));
+        }
+        EBK_CUDA(cudaEventRecord(g_ev_chunk[c], g_side));
+      }
+      for (int c = 0; c < GATHER_CHUNKS; ++c) {
+        const int r0 = c * chunk, rows = (r0 + chunk <= R ? chunk : R - r0);
+        if (rows <= 0) break;
+        EBK_CUDA(cudaStreamWaitEvent(st, g_ev_chunk[c], 0));
+        EBK_PROF(T_QKV_FWD, gemm_tma(ws.xd + (size_t)r0 * d->Din, d->Din, false, ws.wqkv_r, 3 * D, false,
+                                     ws.qkv + (size_t)r0 * 3 * D, 3 * D, rows, 3 * D, d->Din, 0.0f, 1.0f, st, -1, &round_epi));
+      }
+    } else {
+      EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st,
+                                          remote ? &g_peers : nullptr));
+      // (1) Q|K|V = dropout1(gather(table, tok)) . Wqkv        nrms.py:134-139, layers.py:214-230
+      EBK_PROF(T_QKV_FWD, gemm_tma(ws.xd, d->Din, false, ws.wqkv_r, 3 * D, false, ws.qkv, 3 * D, R, 3 * D, d->Din, 0.0f,
+                                   1.0f, st, -1, &round_epi));
+    }
     // (2) attention core; its output is stored as tf32(dropout2(Y0)) -- the only form AttLayer2 reads
     float* y0 = pool ? ws.y0 : out;
     const Dropout dropy = pool ? drop2 : none;

@@ -225,7 +225,7 @@ __global__ void split_tf32_copy_kernel(float* __restrict__ hi, float* __restrict
 template <bool PEERS>
 __global__ void embed_rows_kernel(long n4, int E4, int V, const int32_t* __restrict__ tok,
                                   const float4* __restrict__ src, Dropout drop, float4* __restrict__ xd,
-                                  PeerTables peers) {
+                                  PeerTables peers, long group0) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const int r = (int)(i / E4), c4 = (int)(i - (long)r * E4);
@@ -247,7 +247,7 @@ __global__ void embed_rows_kernel(long n4, int E4, int V, const int32_t* __restr
     v = __ldg(src + i);
   }
   if (drop.on()) {
-    const float4 f = drop.factor4_group((uint64_t)i);
+    const float4 f = drop.factor4_group((uint64_t)(group0 + i));   // group0: first group of this row chunk
     v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
   }
   v.x = round_tf32_bits(v.x); v.y = round_tf32_bits(v.y); v.z = round_tf32_bits(v.z); v.w = round_tf32_bits(v.w);
@@ -342,14 +342,15 @@ int split_tf32_copy(float* hi, float* lo, const float* src, size_t n, cudaStream
 }
 
 int embed_rows(int R, int E, int V, const int32_t* tok, const float* table_or_x, Dropout drop, float* xd,
-               cudaStream_t st, const PeerTables* peers) {
+               cudaStream_t st, const PeerTables* peers, long row_offset) {
   if (R <= 0) return EBK_OK;
   EBK_CHECK_ARG(E % 4 == 0, "embed_rows: E=%d must be a multiple of 4", E);
   const long n4 = (long)R * (E / 4);
   if (peers != nullptr && peers->world > 1 && tok != nullptr) {
     EBK_CHECK_ARG(peers->world <= 8 && peers->shard_floats % 4 == 0 && peers->shard_floats > 0, "embed_rows: bad peer table");
     embed_rows_kernel<true><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
-        n4, E / 4, V, tok, reinterpret_cast<const float4*>(table_or_x), drop, reinterpret_cast<float4*>(xd), *peers);
+        n4, E / 4, V, tok, reinterpret_cast<const float4*>(table_or_x), drop, reinterpret_cast<float4*>(xd), *peers,
+        row_offset * (E / 4));
     EBK_LAUNCH_CHECK();
     return EBK_OK;
   }
@@ -358,7 +359,7 @@ int embed_rows(int R, int E, int V, const int32_t* tok, const float* table_or_x,
   none.shard_floats = 0;
   embed_rows_kernel<false><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, E / 4, V, tok,
                                                                  reinterpret_cast<const float4*>(table_or_x), drop,
-                                                                 reinterpret_cast<float4*>(xd), none);
+                                                                 reinterpret_cast<float4*>(xd), none, row_offset * (E / 4));
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

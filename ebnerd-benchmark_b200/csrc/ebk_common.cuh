@@ -258,7 +258,7 @@ struct PeerTables {
   const float* p[8];
 };
 int embed_rows(int R, int E, int V, const int32_t* tok, const float* table_or_x, Dropout drop, float* xd,
-               cudaStream_t st, const PeerTables* peers = nullptr);
+               cudaStream_t st, const PeerTables* peers = nullptr, long row_offset = 0 /* rows before this chunk: dropout index */);
 // d_table[tok[r], :] += dX[r, :] * dropout(r*E + e)
 int scatter_rows_add(int R, int E, int V, const int32_t* tok, const float* dX, Dropout drop,
                      float* d_table, cudaStream_t st);
