@@ -346,3 +346,27 @@ def test_peer_table_gather_paths_match_local_gather(monkeypatch):
         # loss and table gradient are summed with atomics (order noise); the gathered rows themselves are identical
         assert abs(l - outs[0][0]) < 1e-6 * abs(outs[0][0])
         assert float((g - outs[0][1]).abs().max()) < 1e-6
+
+
+def test_nrms_dummy_script_flow(capsys):
+    """examples/quick_start/nrms_dummy.py statement for statement (default hparams_nrms, float64 1000x100 table,
+    BATCH_SIZE 10, npratio 4): summary / fit / predict through the overlay package, nothing adapted."""
+    from ebrec.models.newsrec.model_config import hparams_nrms
+    from ebrec.models.newsrec.nrms import NRMSModel
+
+    config = hparams_nrms
+    BATCH_SIZE, HISTORY_SIZE, TITLE_SIZE, NPRATIO = 10, config.history_size, config.title_size, 4
+    word_embeddings = np.random.rand(1000, 100)
+    model = NRMSModel(hparams=config, word2vec_embedding=word_embeddings)
+    model.model.summary()
+    assert "860,800" in capsys.readouterr().out          # Keras' parameter count for this configuration
+    his_input_title = np.random.randint(0, 1000, (BATCH_SIZE, HISTORY_SIZE, TITLE_SIZE))
+    pred_input_title = np.random.randint(0, 1000, (BATCH_SIZE, NPRATIO + 1, TITLE_SIZE))
+    label_data = np.zeros((BATCH_SIZE, NPRATIO + 1), dtype=int)
+    for row in label_data:
+        row[np.random.choice(NPRATIO + 1)] = 1
+    input = (his_input_title, pred_input_title)
+    hist = model.model.fit(input, label_data)
+    out = model.model.predict(input)
+    assert out.shape == (BATCH_SIZE, NPRATIO + 1) and np.allclose(out.sum(1), 1.0, atol=1e-5)
+    assert np.isfinite(hist.history["loss"]).all()
