@@ -236,3 +236,58 @@ def test_data_parallel_gradient_identity_gloo_world2(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
                         "127.0.0.1", "--master-port", "29517", str(script)], env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "DP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+_DP_ADAM_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["EBK_ROOT"])
+from oracle import nrms_oracle as O
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(1)
+V, E, nh, dh, att, B, H, C, T = 32, 8, 2, 4, 6, 4, 3, 3, 5
+P = O.init_nrms_params(rng, V, E, nh, dh, att, dtype=np.float64)
+names = O.NRMS_PARAM_ORDER
+sizes = [P[k].size for k in names]
+n = sum(sizes); pad = (-n) % world; shard = (n + pad) // world          # flat buffer divisible into rank shards
+flat = lambda d: np.concatenate([d[k].ravel() for k in names] + [np.zeros(pad)])
+theta = flat(P); m = np.zeros_like(theta); v = np.zeros_like(theta)      # replicated state of the DP run
+Pd = {k: P[k].copy() for k in names}; md = {k: np.zeros_like(P[k]) for k in names}; vd = {k: np.zeros_like(P[k]) for k in names}
+lr = 1e-2
+for t in range(1, 4):
+    his = rng.integers(0, V, (B, H, T)); pred = rng.integers(0, V, (B, C, T))
+    y = np.zeros((B, C)); y[np.arange(B), rng.integers(0, C, B)] = 1
+    # ---- data parallel: shard of the batch, loss scaled by 1/world, reduce-scatter, Adam on the shard, all-gather
+    Pcur = {}; o = 0
+    for k, sz in zip(names, sizes):
+        Pcur[k] = theta[o:o + sz].reshape(P[k].shape); o += sz
+    sl = slice(rank * B // world, (rank + 1) * B // world)
+    _, _, G = O.nrms_loss_and_grads(his[sl], pred[sl], y[sl], Pcur, nh, dh, training=False, loss_scale=1.0 / world)
+    g = torch.from_numpy(flat(G)); dist.all_reduce(g)                    # gloo: reduce-scatter = all-reduce + own slice
+    lo = rank * shard
+    th_s, m_s, v_s = theta[lo:lo + shard].copy(), m[lo:lo + shard], v[lo:lo + shard]
+    O.keras_adam_step(th_s, g.numpy()[lo:lo + shard], m_s, v_s, t, lr)
+    parts = [torch.empty(shard, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(th_s))
+    theta = torch.cat(parts).numpy()
+    # ---- single process, whole batch, dense Adam
+    _, _, Gd = O.nrms_loss_and_grads(his, pred, y, Pd, nh, dh, training=False)
+    for k in names:
+        O.keras_adam_step(Pd[k], Gd[k], md[k], vd[k], t, lr)
+err = float(np.abs(theta[:n] - flat(Pd)[:n]).max())
+assert err < 1e-12, err
+if rank == 0: print("DP_ADAM_OK", err)
+dist.destroy_process_group()
+'''
+
+
+def test_data_parallel_sharded_adam_equals_dense_gloo_world2(tmp_path):
+    """The optimizer step of the data-parallel engine (reduce-scatter of the flat gradient, Keras Adam on this
+    rank's 1/world slice of theta/m/v, all-gather of theta) against a single-process dense Adam on the whole batch:
+    3 steps, world 2 over gloo, float64 oracle arithmetic."""
+    script = tmp_path / "dp_adam_worker.py"
+    script.write_text(_DP_ADAM_WORKER)
+    env = dict(os.environ, EBK_ROOT=str(ROOT), MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29519", str(script)], env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "DP_ADAM_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
