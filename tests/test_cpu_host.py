@@ -176,6 +176,22 @@ def test_product_path_fails_loudly_without_cuda():
         NRMSModel(hparams_nrms, word2vec_embedding=np.random.rand(50, 8))
 
 
+def test_unique_rows_helper_of_the_dedup_scorer():
+    """Host half of the deduplicating predict path: distinct[inverse] reproduces the rows."""
+    from ebrec.models.newsrec._engine import unique_rows
+
+    rng = np.random.default_rng(0)
+    pool = rng.integers(0, 250002, (50, 30)).astype(np.int32)
+    rows = pool[rng.integers(0, 50, 700)]
+    uniq, inv = unique_rows(rows)
+    assert uniq.shape[0] == len({r.tobytes() for r in rows}) <= 50 and inv.shape == (700,)
+    assert np.array_equal(uniq[inv], rows)
+    u2, i2 = unique_rows(np.array([[3, 1], [3, 1], [0, 2]], dtype=np.int64))
+    assert u2.shape == (2, 2) and np.array_equal(u2[i2], [[3, 1], [3, 1], [0, 2]])
+    u3, i3 = unique_rows(np.zeros((0, 5), np.int32))
+    assert u3.shape[0] == 0 and i3.shape == (0,)
+
+
 def test_facade_rejects_unknown_loss_and_optimizer():
     from ebrec.models.newsrec.model_config import hparams_nrms
     from ebrec.models.newsrec.nrms import NRMSModel
