@@ -540,6 +540,20 @@ class NRMSEngine:
         if self.world > 1:
             _ebk.lib().ebk_set_peer_tables(None, 0, 0)
 
+    def sync_optimizer_state(self) -> None:
+        """Data parallel: Adam's m / v of the table live only on the rank that owns each slice; gather them (and the
+        table itself) into every replica before a checkpoint is written.  Collective; no-op on one GPU."""
+        self._sync_table()
+        if self.world <= 1 or self.step_count == 0:
+            return
+        P = self.params
+        tbl = P.offsets.get("news_Wqkv", 0)
+        n = tbl if (tbl > 0 and tbl % (4 * self.world) == 0 and type(self) is NRMSEngine) else P.n
+        shard = n // self.world
+        lo = self.rank * shard
+        for buf in (P.m, P.v):
+            torch.distributed.all_gather_into_tensor(buf[:n], buf[lo: lo + shard].clone())
+
     def _dp_state(self) -> dict:
         """Side stream and events of the overlapped data-parallel optimizer step."""
         st = getattr(self, "_dp", None)

@@ -164,6 +164,8 @@ class KerasLikeModel:
 
         os.makedirs(os.path.dirname(str(filepath)) or ".", exist_ok=True)
         e = self._engine
+        if hasattr(e, "sync_optimizer_state"):
+            e.sync_optimizer_state()   # data parallel: every rank must call save_weights (collective)
         state = {"weights": [torch.from_numpy(w) for w in e.get_weights()], "step_count": e.step_count,
                  "adam_m": e.params.m.cpu(), "adam_v": e.params.v.cpu(), "lr": e.lr}
         torch.save(state, str(filepath))
