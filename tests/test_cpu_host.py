@@ -163,6 +163,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.ebk_version() >= 100  # pure host call; no compute without a GPU
 
 
+def test_c_abi_header_is_plain_c():
+    """include/ebk.h is the drop-in boundary: it must compile as C99 (no C++ / torch types in the signatures)."""
+    import shutil
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", str(ROOT / "include" / "ebk.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_product_path_fails_loudly_without_cuda():
     import torch
 
