@@ -1,0 +1,127 @@
+"""Pins the oracle to the REFERENCE: oracle/*.py against tests/golden/ref_*.npz.
+
+The ref_*.npz fixtures are outputs of the reference's own model source
+(/root/reference/src/ebrec/models/newsrec/{layers,nrms,nrms_docvec,naml}.py, imported unmodified) executed over
+oracle/tf_shim by tests/golden/make_reference_fixtures.py: predictions, scorer outputs, encoder outputs, losses and
+autograd gradients in float64.  The float64 oracle must reproduce them to round-off -- that covers the AttLayer2
+arithmetic (exp without max-subtraction, +1e-7), the adjoint product of SelfAttention, the absence of masks and
+biases, the Keras weight order, where the two Dropout layers sit, BatchNorm statistics per TimeDistributed call, the
+L2 terms, and the oracle's hand-derived backward.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLD = Path(__file__).resolve().parent / "golden"
+sys.path.insert(0, str(GOLD))
+import ref_cases as RC  # noqa: E402
+
+from oracle import docvec_oracle as DV, naml_oracle as NA, nrms_dense_oracle as ND, nrms_oracle as O  # noqa: E402
+
+TOL = 2e-10
+
+
+def close(got, want, tol=TOL):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return float(np.abs(got - want).max() / (np.abs(want).max() + 1e-300)) < tol
+
+
+@pytest.mark.parametrize("name", list(RC.NRMS_CASES))
+def test_nrms_oracle_matches_reference_source(name):
+    (V, E, nh, dh, att, B, H, C, T), ws, his, pred, y = RC.nrms_case(name)
+    ref = np.load(GOLD / f"ref_nrms_{name}.npz")
+    P = dict(zip(O.NRMS_PARAM_ORDER, ws))
+    z, (_, _, _, D, _, _, Nc, u) = O.nrms_forward(his, pred, P, nh, dh)
+    assert np.ptp(ref["logits"], axis=1).min() >= 1.0            # the gate is not vacuous
+    assert close(z, ref["logits"]) and close(O.softmax(z), ref["probs"])
+    assert close(O.nrms_score(his, pred[:, :1], P, nh, dh), ref["scores"])
+    assert close(Nc.reshape(B * C, D), ref["news_vec"]) and close(u, ref["user_vec"])
+    for tag, kw in (("nodrop", dict(training=False)),
+                    ("drop", dict(training=True, p_drop=0.2, seed1=RC.DROPOUT_SEEDS[0], seed2=RC.DROPOUT_SEEDS[1]))):
+        loss, _, G = O.nrms_loss_and_grads(his, pred, y, P, nh, dh, **kw)
+        assert abs(loss - float(ref[f"loss_{tag}"])) < 1e-9 * max(1.0, abs(loss)), (tag, loss)
+        for k in O.NRMS_PARAM_ORDER:
+            gmax = float(ref[f"gmax_{tag}_{k}"])
+            assert abs(RC.probe(k, G[k]) - float(ref[f"gp_{tag}_{k}"])) < 1e-8 * gmax * np.sqrt(G[k].size), (tag, k)
+            assert abs(np.abs(G[k]).max() - gmax) < 1e-9 * gmax
+            if f"g_{tag}_{k}" in ref.files:
+                assert close(G[k], ref[f"g_{tag}_{k}"], 1e-9), (tag, k)
+
+
+def test_nrms_two_adam_steps_match_reference_source():
+    """train_on_batch x 2 through the reference graph + Keras-form Adam (restated in the shim and in the oracle)."""
+    (V, E, nh, dh, att, B, H, C, T), ws, his, pred, y = RC.nrms_case("small")
+    ref = np.load(GOLD / "ref_nrms_small.npz")
+    P = {k: w.copy() for k, w in zip(O.NRMS_PARAM_ORDER, ws)}
+    m = {k: np.zeros_like(v) for k, v in P.items()}
+    v = {k: np.zeros_like(v_) for k, v_ in P.items()}
+    for t in (1, 2):
+        loss, _, G = O.nrms_loss_and_grads(his, pred, y, P, nh, dh, training=False)
+        assert abs(loss - ref["train_losses"][t - 1]) < 1e-9 * max(1.0, abs(loss))
+        for k in P:
+            O.keras_adam_step(P[k], G[k], m[k], v[k], t, 1e-3)
+    for k in P:
+        # Adam's first steps move every weight by ~lr*sign(g): compare against the travel, not the weight
+        assert np.abs(P[k] - ref[f"w2_{k}"]).max() < 1e-6 * 2e-3, k
+
+
+def test_nrms_dense_oracle_matches_reference_source():
+    c, ws, his, pred, y = RC.nrms_dense_case()
+    ref = np.load(GOLD / "ref_nrms_dense.npz")
+    n_layers = len(c["units"])
+    keys = ND.param_order(n_layers)
+    assert len(keys) == len(ws)
+    P = dict(zip(keys, ws))
+    assert close(ND.predict(his, pred, P, n_layers, c["nh"], c["dh"]), ref["probs"])
+    assert close(ND.score(his, pred[:, :1], P, n_layers, c["nh"], c["dh"]), ref["scores"])
+    stats = {}
+    loss, _, G = ND.loss_and_grads(his, pred, y, P, n_layers, c["nh"], c["dh"], training=True, p_drop=0.0, l2=1e-3,
+                                   new_stats=stats)
+    assert abs(loss - float(ref["loss"])) < 1e-9 * abs(loss)
+    for i, k in enumerate(keys):
+        if k.endswith(("_mean", "_var")):
+            assert close(stats[k], ref[f"w_after_{i}"], 1e-12), k   # BN moving averages: history call, then candidates
+        else:
+            assert close(G[k], ref[f"g_{i}"], 1e-8), k
+
+
+def test_docvec_oracle_matches_reference_source():
+    c, ws, his, pred, y = RC.docvec_case()
+    ref = np.load(GOLD / "ref_docvec.npz")
+    n_layers = len(c["units"])
+    keys = []
+    for i in range(n_layers):
+        keys += [f"d{i}_W", f"d{i}_b", f"d{i}_gamma", f"d{i}_beta", f"d{i}_mean", f"d{i}_var"]
+    keys += ["out_W", "out_b", "user_WQ", "user_WK", "user_WV", "user_W", "user_b", "user_q"]
+    assert len(keys) == len(ws)
+    P = dict(zip(keys, ws))
+    assert close(DV.docvec_predict(his, pred, P, n_layers, c["nh"], c["dh"]), ref["probs"])
+    assert close(DV.docvec_score(his, pred[:, :1], P, n_layers, c["nh"], c["dh"]), ref["scores"])
+    loss, _, G, stats = DV.docvec_loss_and_grads(his, pred, y, P, n_layers, c["nh"], c["dh"], p_drop=0.0, l2=1e-3)
+    assert abs(loss - float(ref["loss"])) < 1e-9 * abs(loss)
+    for i, k in enumerate(keys):
+        if k.endswith(("_mean", "_var")):
+            assert close(stats[k], ref[f"w_after_{i}"], 1e-12), k
+        else:
+            assert close(G[k], ref[f"g_{i}"], 1e-8), k
+
+
+def test_naml_oracle_matches_reference_source():
+    c, ws, x, y = RC.naml_case()
+    ref = np.load(GOLD / "ref_naml.npz")
+    assert len(NA.NAML_PARAM_ORDER) == len(ws)
+    P = dict(zip(NA.NAML_PARAM_ORDER, ws))
+    art, B, H, C = NA.pack_inputs(*x)
+    T, Tb = c["T"], c["Tb"]
+    assert close(NA.naml_predict(art, B, H, C, P, T, Tb), ref["probs"])
+    one = [a[:, :1] for a in x[4:]]
+    art1, _, _, _ = NA.pack_inputs(*x[:4], *one)
+    assert close(NA.naml_score(art1, B, H, 1, P, T, Tb), ref["scores"])
+    for tag, kw in (("nodrop", dict(p_drop=0.0)), ("drop", dict(p_drop=0.2, seeds=tuple(int(s) for s in ref["drop_seeds"])))):
+        loss, _, G = NA.naml_loss_and_grads(art, B, H, C, y, P, T, Tb, **kw)
+        assert abs(loss - float(ref[f"loss_{tag}"])) < 1e-9 * abs(loss), tag
+        for i, k in enumerate(NA.NAML_PARAM_ORDER):
+            assert close(G[k], ref[f"g_{tag}_{i}"], 1e-8), (tag, k)

@@ -1,0 +1,234 @@
+"""CUDA path (through the C-ABI) against the REFERENCE-generated golden vectors of tests/golden/ref_*.npz.
+
+Those fixtures are outputs of the reference's own model source run over oracle/tf_shim
+(tests/golden/make_reference_fixtures.py).  Gates here are on LOGITS (and encoder vectors), on cases built so
+that every impression's logit spread is >= 1 -- a softmax over near-equal logits would pass with any kernel.
+The north-star tolerance (forward click scores within 1e-3 relative) is asserted on the inference arithmetic
+(3xTF32) AND measured on the benchmarked single-pass TF32 TMA training kernels at E=768 / D=400 / att=200 /
+T=30 / H in {20, 50}; the measured figures are printed (pytest -s) and quoted in DESIGN.md section 3.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = Path(__file__).resolve().parent / "golden"
+sys.path.insert(0, str(GOLD))
+import ref_cases as RC  # noqa: E402
+
+from oracle import naml_oracle as NA, nrms_dense_oracle as ND, nrms_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+MATH_FP32, MATH_TF32, MATH_TF32X3 = 0, 1, 2
+
+
+def rel(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return float(np.abs(got - want).max() / (np.abs(want).max() + 1e-30))
+
+
+def logits_of(eng, x, B, C_, training=False, seeds=None):
+    kw = {} if seeds is None else {"seeds": seeds}
+    _, news_c, u, _ = eng.forward_logits_parts(x, B, C_, training, **kw)
+    return (news_c * u[:, None, :]).sum(-1).cpu().numpy(), news_c.reshape(B * C_, -1).cpu().numpy(), u.cpu().numpy()
+
+
+def nrms_engine(name, math, dropout):
+    from ebrec.models.newsrec._engine import NRMSEngine
+
+    (V, E, nh, dh, att, B, H, C, T), ws, his, pred, y = RC.nrms_case(name)
+    eng = NRMSEngine(V=V, E=E, T=T, H=H, nh=nh, dh=dh, att=att, dropout=dropout, lr=1e-3, seed=3, math=math)
+    eng.set_weights(ws)
+    tok, lab = eng.to_device_batch(his.astype(np.int32), pred.astype(np.int32), y.astype(np.float32))
+    return eng, tok, lab, (B, C, H, T, nh * dh)
+
+
+@pytest.mark.parametrize("name", list(RC.NRMS_CASES))
+def test_nrms_inference_logits_match_reference(name):
+    """model.predict / scorer.predict arithmetic (3xTF32): logits, probabilities, sigmoid scores, encoder vectors."""
+    ref = np.load(GOLD / f"ref_nrms_{name}.npz")
+    assert np.ptp(ref["logits"], axis=1).min() >= 1.0
+    eng, tok, _, (B, C, H, T, D) = nrms_engine(name, MATH_TF32, 0.2)
+    z, nv, uv = logits_of(eng, tok, B, C)
+    errs = {"logits": rel(z, ref["logits"]), "news_vec": rel(nv, ref["news_vec"]), "user_vec": rel(uv, ref["user_vec"]),
+            "probs": rel(eng.predict_dev(tok, B, C).cpu().numpy(), ref["probs"])}
+    (V, E, nh, dh, att, _, _, _, _), ws, his, pred, y = RC.nrms_case(name)
+    tok1, _ = eng.to_device_batch(his.astype(np.int32), pred[:, :1].astype(np.int32))
+    errs["scores"] = rel(eng.predict_dev(tok1, B, 1, head="sigmoid").cpu().numpy(), ref["scores"])
+    print(f"[parity] NRMS {name} inference (3xTF32) rel err vs reference: " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v < 1e-3, (k, v)
+
+
+@pytest.mark.parametrize("name", ["c1", "e768", "h50"])
+def test_nrms_training_kernels_forward_error_measured(name):
+    """The BENCHMARKED arithmetic: single-pass tcgen05 kind::tf32 on the all-TMA path (gemm_tma_kernel,
+    attn_fwd_pre_kernel), dropout 0, at the BASELINE widths.  Operands are rounded to 10-bit mantissas, so the
+    expected logit error is a few 1e-4 of max|logit| independent of K; the bound asserted is 3e-3 and the measured
+    value is printed."""
+    ref = np.load(GOLD / f"ref_nrms_{name}.npz")
+    eng, tok, _, (B, C, H, T, D) = nrms_engine(name, MATH_TF32, 0.0)
+    z, nv, uv = logits_of(eng, tok, B, C, training=True, seeds=(1, 2))
+    e = {"logits": rel(z, ref["logits"]), "news_vec": rel(nv, ref["news_vec"]), "user_vec": rel(uv, ref["user_vec"])}
+    p = np.exp(z - z.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    e["probs"] = rel(p, ref["probs"])
+    print(f"[parity] NRMS {name} TRAINING kernels (1xTF32, TMA path) rel err vs reference: "
+          + ", ".join(f"{k} {v:.2e}" for k, v in e.items()))
+    for k, v in e.items():
+        assert v < 3e-3, (k, v)
+
+
+@pytest.mark.parametrize("math", [MATH_FP32, MATH_TF32])
+@pytest.mark.parametrize("tag", ["nodrop", "drop"])
+@pytest.mark.parametrize("name", list(RC.NRMS_CASES))
+def test_nrms_loss_and_gradients_match_reference(name, tag, math):
+    """Training loss and gradients, with the Dropout layers where the reference has them (masks = the build's
+    counter-based function, which the fixture generator fed to the reference graph)."""
+    ref = np.load(GOLD / f"ref_nrms_{name}.npz")
+    eng, tok, lab, (B, C, H, T, D) = nrms_engine(name, math, 0.2 if tag == "drop" else 0.0)
+    eng.params.grad.zero_()
+    loss, _ = eng.loss_and_grads_dev(tok, lab, B, C, training=True, seeds=RC.DROPOUT_SEEDS)
+    want = float(ref[f"loss_{tag}"])
+    ltol = 1e-4 if math == MATH_FP32 else 3e-3
+    assert abs(float(loss) - want) < ltol * max(1.0, abs(want)), (float(loss), want)
+    P = eng.params
+    got = {"table": P.g("table"), "news_W": P.g("news_attW"), "news_b": P.g("news_attb"), "news_q": P.g("news_attq").view(-1, 1),
+           "user_W": P.g("user_attW"), "user_b": P.g("user_attb"), "user_q": P.g("user_attq").view(-1, 1)}
+    for pre in ("news", "user"):
+        W = P.g(f"{pre}_Wqkv")
+        got[f"{pre}_WQ"], got[f"{pre}_WK"], got[f"{pre}_WV"] = W[:, :D], W[:, D:2 * D], W[:, 2 * D:]
+    gtol = 2e-4 if math == MATH_FP32 else 2e-2
+    worst = {}
+    for k in O.NRMS_PARAM_ORDER:
+        g = got[k].cpu().numpy().astype(np.float64)
+        gmax = float(ref[f"gmax_{tag}_{k}"])
+        if f"g_{tag}_{k}" in ref.files:
+            worst[k] = np.abs(g - ref[f"g_{tag}_{k}"]).max() / gmax
+        else:   # stored as a fixed random projection: |error| of a projection of N elements ~ sqrt(N) * element error
+            worst[k] = abs(RC.probe(k, g) - float(ref[f"gp_{tag}_{k}"])) / (gmax * np.sqrt(g.size))
+    print(f"[parity] NRMS {name}/{tag} math={math}: loss {float(loss):.6f} (ref {want:.6f}); grad err / max|g|: "
+          + ", ".join(f"{k} {v:.1e}" for k, v in worst.items()))
+    # WQ/WK (softmax-Jacobian cancellation) get the conditioning allowance of test_gpu_nrms.py; here a flat 5x
+    for k, v in worst.items():
+        assert v < gtol * (5.0 if k.endswith(("WQ", "WK")) else 1.0), (k, v)
+
+
+def test_nrms_two_adam_steps_match_reference():
+    ref = np.load(GOLD / "ref_nrms_small.npz")
+    eng, tok, lab, (B, C, H, T, D) = nrms_engine("small", MATH_FP32, 0.0)
+    for t in range(2):
+        loss, _ = eng.train_step_dev(tok, lab, B, C)
+        assert abs(float(loss) - ref["train_losses"][t]) < 2e-4 * max(1.0, abs(ref["train_losses"][t]))
+    for k, w in zip(O.NRMS_PARAM_ORDER, eng.get_weights()):
+        assert np.abs(w - ref[f"w2_{k}"]).mean() < 0.02 * 2e-3, k     # 2 steps of ~lr travel each
+
+
+def _dense_engine(math, dropout=0.0):
+    from ebrec.models.newsrec._engine_nrms_dense import NRMSDenseEngine
+
+    c, ws, his, pred, y = RC.nrms_dense_case()
+    e = NRMSDenseEngine(V=c["V"], E=c["E"], T=c["T"], H=c["H"], nh=c["nh"], dh=c["dh"], att=c["att"], units=c["units"],
+                        l2=1e-3, dropout=dropout, lr=1e-3, seed=3, math=math)
+    e.set_weights(ws)
+    return e, c, his.astype(np.int32), pred.astype(np.int32), y.astype(np.float32)
+
+
+@pytest.mark.parametrize("math", [MATH_FP32, MATH_TF32])
+def test_nrms_dense_stack_matches_reference(math):
+    ref = np.load(GOLD / "ref_nrms_dense.npz")
+    e, c, his, pred, y = _dense_engine(math)
+    B, C = c["B"], c["C"]
+    tok, lab = e.to_device_batch(his, pred, y)
+    tol = 1e-4 if math == MATH_FP32 else 1e-3
+    assert rel(e.predict_dev(tok, B, C).cpu().numpy(), ref["probs"]) < tol
+    tok1, _ = e.to_device_batch(his, pred[:, :1])
+    assert rel(e.predict_dev(tok1, B, 1, head="sigmoid").cpu().numpy(), ref["scores"]) < tol
+    e.params.grad.zero_()
+    loss, _ = e.loss_and_grads_dev(tok, lab, B, C, training=True, seeds=(1, 2, 3))
+    assert abs(float(loss) - float(ref["loss"])) < (1e-4 if math == MATH_FP32 else 3e-3) * abs(float(ref["loss"]))
+    keys = ND.param_order(len(c["units"]))
+    for i, k in enumerate(keys):
+        if k.endswith("_mean"):
+            assert rel(e.bn_mean[int(k[1])].cpu().numpy(), ref[f"w_after_{i}"]) < 1e-3, k
+        elif k.endswith("_var"):
+            assert rel(e.bn_var[int(k[1])].cpu().numpy(), ref[f"w_after_{i}"]) < 1e-3, k
+    if math == MATH_FP32:
+        D = c["nh"] * c["dh"]
+        Wn = e.params.g("news_Wqkv").cpu().numpy()
+        got = {"table": e.params.g("table").cpu().numpy(), "news_WV": Wn[:, 2 * D:], "d0_W": e.params.g("d0_W").cpu().numpy(),
+               "d1_gamma": e.params.g("d1_gamma").cpu().numpy(), "news_W": e.params.g("news_attW").cpu().numpy()}
+        for k, g in got.items():
+            assert rel(g, ref[f"g_{keys.index(k)}"]) < 1e-3, k
+
+
+@pytest.mark.parametrize("math", [MATH_FP32, MATH_TF32])
+def test_docvec_matches_reference(math):
+    from ebrec.models.newsrec._engine_docvec import DocVecEngine
+
+    ref = np.load(GOLD / "ref_docvec.npz")
+    c, ws, his, pred, y = RC.docvec_case()
+    e = DocVecEngine(Ddoc=c["Ddoc"], units=c["units"], H=c["H"], nh=c["nh"], dh=c["dh"], att=c["att"], dropout=0.0,
+                     lr=1e-3, l2=1e-3, seed=3, math=math)
+    e.set_weights(ws)
+    B, C = c["B"], c["C"]
+    x, lab = e.to_device_batch(his, pred, y.astype(np.float32))
+    z, _, _ = logits_of(e, x, B, C)
+    want = np.log(ref["probs"])                       # logits up to a per-row constant
+    zc, wc = z - z.mean(1, keepdims=True), want - want.mean(1, keepdims=True)
+    assert np.ptp(wc, axis=1).min() >= 1.0
+    tol = 1e-4 if math == MATH_FP32 else 1e-3
+    assert rel(zc, wc) < tol, rel(zc, wc)
+    assert rel(e.predict_dev(x, B, C).cpu().numpy(), ref["probs"]) < tol
+    x1, _ = e.to_device_batch(his, pred[:, :1])
+    assert rel(e.predict_dev(x1, B, 1, head="sigmoid").cpu().numpy(), ref["scores"]) < tol
+    e.params.grad.zero_()
+    loss, _ = e.loss_and_grads_dev(x, lab, B, C, training=True, seeds=(1, 2))
+    assert abs(float(loss) - float(ref["loss"])) < (1e-4 if math == MATH_FP32 else 3e-3) * abs(float(ref["loss"]))
+    n = len(c["units"])
+    for i in range(n):                                # BatchNorm moving statistics after the step
+        assert rel(e.bn_mean[i].cpu().numpy(), ref[f"w_after_{6 * i + 4}"]) < 1e-3
+        assert rel(e.bn_var[i].cpu().numpy(), ref[f"w_after_{6 * i + 5}"]) < 1e-3
+    if math == MATH_FP32:
+        assert rel(e.params.g("d0_W").cpu().numpy(), ref["g_0"]) < 1e-3
+        assert rel(e.params.g("out_W").cpu().numpy(), ref[f"g_{6 * n}"]) < 1e-3
+
+
+@pytest.mark.parametrize("math", [MATH_FP32, MATH_TF32])
+def test_naml_matches_reference(math):
+    from ebrec.models.newsrec._engine_naml import NAMLEngine
+
+    ref = np.load(GOLD / "ref_naml.npz")
+    c, ws, x, y = RC.naml_case()
+    def engine(dropout):
+        e = NAMLEngine(V=c["V"], E=c["E"], T=c["T"], Tb=c["Tb"], H=c["H"], F=c["F"], att=c["att"], window=c["window"],
+                       vert_num=c["vert_num"], vert_dim=c["vert_dim"], subvert_num=c["sub_num"], subvert_dim=c["sub_dim"],
+                       dropout=dropout, lr=1e-3, seed=3, math=math)
+        e.set_weights(ws)
+        return e
+    e = engine(0.2)
+    B, C = c["B"], c["C"]
+    xd, lab = e.to_device_batch(x, y.astype(np.float32))
+    tol = 1e-4 if math == MATH_FP32 else 1e-3
+    z, _, _ = logits_of(e, xd, B, C)
+    want = np.log(ref["probs"])
+    zc, wc = z - z.mean(1, keepdims=True), want - want.mean(1, keepdims=True)
+    assert np.ptp(wc, axis=1).min() >= 1.0
+    assert rel(zc, wc) < tol, rel(zc, wc)
+    assert rel(e.predict_dev(xd, B, C).cpu().numpy(), ref["probs"]) < tol
+    x1, _ = e.to_device_batch(x[:4] + [a[:, :1] for a in x[4:]])
+    assert rel(e.predict_dev(x1, B, 1, head="sigmoid").cpu().numpy(), ref["scores"]) < tol
+    for tag, drop, seeds in (("nodrop", 0.0, (1, 2, 3, 4)), ("drop", 0.2, tuple(int(s) for s in ref["drop_seeds"]))):
+        e = engine(drop)
+        xd, lab = e.to_device_batch(x, y.astype(np.float32))
+        e.params.grad.zero_()
+        loss, _ = e.loss_and_grads_dev(xd, lab, B, C, training=True, seeds=seeds)
+        want_l = float(ref[f"loss_{tag}"])
+        assert abs(float(loss) - want_l) < (1e-4 if math == MATH_FP32 else 3e-3) * abs(want_l), (tag, float(loss), want_l)
+        if math == MATH_FP32:
+            gw = dict(zip(NA.NAML_PARAM_ORDER, [ref[f"g_{tag}_{i}"] for i in range(len(NA.NAML_PARAM_ORDER))]))
+            assert rel(e.params.g("table").cpu().numpy(), gw["table"]) < 1e-3, tag
