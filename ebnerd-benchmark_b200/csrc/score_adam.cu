@@ -9,9 +9,11 @@ namespace {
 constexpr int SC_MAXC = 32;  // candidates handled per impression per pass by the CE kernel
 
 // one CTA (128 threads = 4 warps) per impression
-__global__ void __launch_bounds__(128) score_ce_kernel(int C, int D, const float* __restrict__ news,
+// kind 0: categorical cross-entropy from the softmax's logits; kind 1: Keras binary_crossentropy on that output,
+// which Keras evaluates as sigmoid cross-entropy of the SAME cached logits, averaged over the C candidates.
+__global__ void __launch_bounds__(128) score_ce_kernel(int kind, int C, int D, const float* __restrict__ news,
                                                         const float* __restrict__ user,
-                                                        const float* __restrict__ labels, float loss_scale,
+                                                        const float* __restrict__ labels, float grad_scale, float loss_scale,
                                                         float* __restrict__ probs, float* __restrict__ loss_sum,
                                                         float* __restrict__ d_news, float* __restrict__ d_user) {
   extern __shared__ float sm[];  // z[C], dz[C]
@@ -44,12 +46,23 @@ __global__ void __launch_bounds__(128) score_ce_kernel(int C, int D, const float
     yz = warp_sum(yz);
     float lse = mx + logf(s);
     float rs = 1.0f / s;
+    float bce = 0.0f;
+    const float invC = 1.0f / (float)C;
     for (int c = lane; c < C; c += 32) {
       float p = expf(z[c] - mx) * rs;
       probs[(long)b * C + c] = p;
-      dz[c] = (p * ysum - labels[(long)b * C + c]) * loss_scale;
+      const float y = labels[(long)b * C + c];
+      if (kind == 0) {
+        dz[c] = (p * ysum - y) * grad_scale;
+      } else {
+        // sigmoid_cross_entropy_with_logits: max(z,0) - z*y + log(1 + exp(-|z|)); d/dz = sigmoid(z) - y
+        const float zc = z[c];
+        bce += fmaxf(zc, 0.0f) - zc * y + log1pf(expf(-fabsf(zc)));
+        dz[c] = (1.0f / (1.0f + expf(-zc)) - y) * invC * grad_scale;
+      }
     }
-    if (lane == 0) atomicAdd(loss_sum, (lse * ysum - yz) * loss_scale);
+    if (kind != 0) bce = warp_sum(bce);
+    if (lane == 0) atomicAdd(loss_sum, (kind == 0 ? (lse * ysum - yz) : bce * invC) * loss_scale);
   }
   if (d_news == nullptr) return;
   __syncthreads();
@@ -122,22 +135,30 @@ __global__ void dropout_mask_kernel(uint64_t seed, uint32_t thr, size_t n, float
 
 using namespace ebk;
 
-extern "C" int ebk_score_softmax_ce(int32_t B, int32_t C, int32_t D, const float* news, const float* user,
-                                    const float* labels, float loss_scale, float* probs, float* loss_sum,
-                                    float* d_news, float* d_user, void* stream) {
+extern "C" int ebk_score_loss(int32_t kind, int32_t B, int32_t C, int32_t D, const float* news, const float* user,
+                              const float* labels, float grad_scale, float loss_scale, float* probs, float* loss_sum,
+                              float* d_news, float* d_user, void* stream) {
   if (B <= 0) return EBK_OK;
-  EBK_CHECK_ARG(C >= 1 && D >= 1, "score_softmax_ce: bad shape C=%d D=%d", C, D);
-  EBK_CHECK_ARG(news && user && labels && probs && loss_sum, "score_softmax_ce: null pointer");
-  EBK_CHECK_ARG((d_news == nullptr) == (d_user == nullptr), "score_softmax_ce: d_news/d_user must both be set or both NULL");
-  EBK_CHECK_ARG(C <= 4096, "score_softmax_ce: C=%d > 4096", C);
+  EBK_CHECK_ARG(kind == EBK_LOSS_CATEGORICAL_CE || kind == EBK_LOSS_BINARY_CE, "score_loss: unknown loss kind %d", kind);
+  EBK_CHECK_ARG(C >= 1 && D >= 1, "score_loss: bad shape C=%d D=%d", C, D);
+  EBK_CHECK_ARG(news && user && labels && probs && loss_sum, "score_loss: null pointer");
+  EBK_CHECK_ARG((d_news == nullptr) == (d_user == nullptr), "score_loss: d_news/d_user must both be set or both NULL");
+  EBK_CHECK_ARG(C <= 4096, "score_loss: C=%d > 4096", C);
   (void)SC_MAXC;
   cudaStream_t st = (cudaStream_t)stream;
   if (prof_on()) prof_begin(T_SCORE, st);
-  score_ce_kernel<<<B, 128, 2 * C * sizeof(float), st>>>(C, D, news, user, labels, loss_scale, probs, loss_sum,
-                                                         d_news, d_user);
+  score_ce_kernel<<<B, 128, 2 * C * sizeof(float), st>>>(kind, C, D, news, user, labels, grad_scale, loss_scale, probs,
+                                                         loss_sum, d_news, d_user);
   if (prof_on()) prof_end(T_SCORE, st);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
+}
+
+extern "C" int ebk_score_softmax_ce(int32_t B, int32_t C, int32_t D, const float* news, const float* user,
+                                    const float* labels, float loss_scale, float* probs, float* loss_sum,
+                                    float* d_news, float* d_user, void* stream) {
+  return ebk_score_loss(EBK_LOSS_CATEGORICAL_CE, B, C, D, news, user, labels, loss_scale, loss_scale, probs, loss_sum,
+                        d_news, d_user, stream);
 }
 
 extern "C" int ebk_score_sigmoid(int32_t B, int32_t C, int32_t D, const float* news, const float* user,

@@ -19,11 +19,13 @@ LIB_PATH = Path(os.environ.get("EBK_LIB", _PKG_ROOT / "csrc" / "libebk.so"))
 MATH_FP32 = 0
 MATH_TF32 = 1
 MATH_TF32X3 = 2
+LOSS_CATEGORICAL_CE = 0   # hparams.loss "cross_entropy_loss"
+LOSS_BINARY_CE = 1        # hparams.loss "log_loss"
 
 SYMBOLS = [
     "ebk_last_error", "ebk_version", "ebk_device_ok",
     "ebk_seqenc_workspace_bytes", "ebk_seqenc_fwd", "ebk_seqenc_bwd", "ebk_set_table_grad_event", "ebk_set_deferred_wgrad", "ebk_join_deferred", "ebk_ipc_export", "ebk_ipc_open", "ebk_set_peer_tables",
-    "ebk_score_softmax_ce", "ebk_score_sigmoid", "ebk_adam_keras_step",
+    "ebk_score_softmax_ce", "ebk_score_loss", "ebk_score_sigmoid", "ebk_adam_keras_step",
     "ebk_embed_adam_workspace_bytes", "ebk_embed_adam_step",
     "ebk_dense_workspace_bytes", "ebk_dense_fwd", "ebk_dense_bwd", "ebk_sumsq_accum",
     "ebk_attlayer_workspace_bytes", "ebk_attlayer_fwd", "ebk_attlayer_bwd",
@@ -118,6 +120,7 @@ def lib() -> C.CDLL:
     l.ebk_catview_fwd.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp, i32, vp]
     l.ebk_catview_bwd.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp, i32, vp, vp, vp, vp]
     l.ebk_score_softmax_ce.argtypes = [i32, i32, i32, vp, vp, vp, f32, vp, vp, vp, vp, vp]
+    l.ebk_score_loss.argtypes = [i32, i32, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp]
     l.ebk_score_sigmoid.argtypes = [i32, i32, i32, vp, vp, vp, vp]
     l.ebk_adam_keras_step.argtypes = [vp, vp, vp, vp, sz, f32, f64, f64, f32, C.c_int, vp]
     l.ebk_embed_adam_workspace_bytes.restype = sz

@@ -84,6 +84,10 @@ class FlatParams:
 class NRMSEngine:
     """NRMS on one GPU (one process per GPU under torch.distributed for data parallel)."""
 
+    # hparams.loss: "cross_entropy_loss" -> categorical CE (default), "log_loss" -> Keras binary_crossentropy
+    # (nrms.py:56-67); set by the model facade
+    loss_kind = _ebk.LOSS_CATEGORICAL_CE
+
     def __init__(self, *, V, E, T, H, nh, dh, att, dropout, lr, seed=None, math=_ebk.MATH_TF32,
                  device=None, beta1=0.9, beta2=0.999, eps=1e-7):
         _ebk.require_device()
@@ -329,8 +333,8 @@ class NRMSEngine:
         probs = self._buf("probs", (B, C_))
         loss = self._buf("loss", (1,))
         loss.zero_()
-        _ebk.check(lib.ebk_score_softmax_ce(B, C_, self.D, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(labels), 1.0 / B,
-                                            _ebk.ptr(probs), _ebk.ptr(loss), None, None, _ebk.stream()))
+        _ebk.check(lib.ebk_score_loss(self.loss_kind, B, C_, self.D, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(labels), 0.0,
+                                      1.0 / B, _ebk.ptr(probs), _ebk.ptr(loss), None, None, _ebk.stream()))
         return loss, probs
 
     def encode_host(self, kind: str, x: np.ndarray) -> np.ndarray:
@@ -371,10 +375,10 @@ class NRMSEngine:
         dn_all = self._buf("dn_all", (N, self.D))
         d_user = self._buf("d_user", (B, self.D))
         d_news_c = dn_all[B * self.H:]
-        scale = 1.0 / (B * self.world)
-        _ebk.check(lib.ebk_score_softmax_ce(B, C_, self.D, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(labels), scale,
-                                            _ebk.ptr(probs), _ebk.ptr(loss), _ebk.ptr(d_news_c), _ebk.ptr(d_user),
-                                            _ebk.stream()))
+        # gradient of the GLOBAL-batch mean (summed over ranks by the collective); reported loss = this rank's mean
+        _ebk.check(lib.ebk_score_loss(self.loss_kind, B, C_, self.D, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(labels),
+                                      1.0 / (B * self.world), 1.0 / B, _ebk.ptr(probs), _ebk.ptr(loss),
+                                      _ebk.ptr(d_news_c), _ebk.ptr(d_user), _ebk.stream()))
         _ebk.check(lib.ebk_seqenc_bwd(C.byref(du), None, _ebk.ptr(n_all), _ebk.ptr(P.p("user_Wqkv")),
                                       _ebk.ptr(P.p("user_attW")), _ebk.ptr(P.p("user_attb")),
                                       _ebk.ptr(P.p("user_attq")), 0, 0, 0, _ebk.ptr(wu), wu.numel(),

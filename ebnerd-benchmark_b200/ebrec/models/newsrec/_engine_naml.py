@@ -174,8 +174,9 @@ class NAMLEngine(NRMSEngine):
         loss.zero_()
         dn_all = self._buf("dn_all", (N, F_))
         d_user = self._buf("d_user", (B, F_))
-        _ebk.check(lib.ebk_score_softmax_ce(B, C_, F_, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(labels), 1.0 / (B * self.world),
-                                            _ebk.ptr(probs), _ebk.ptr(loss), _ebk.ptr(dn_all[BH:]), _ebk.ptr(d_user), st))
+        _ebk.check(lib.ebk_score_loss(self.loss_kind, B, C_, F_, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(labels),
+                                      1.0 / (B * self.world), 1.0 / B, _ebk.ptr(probs), _ebk.ptr(loss),
+                                      _ebk.ptr(dn_all[BH:]), _ebk.ptr(d_user), st))
         # user AttLayer2: its input gradient IS the gradient of the history rows of n_all
         _ebk.check(lib.ebk_attlayer_bwd(C.byref(ctx["du"]), _ebk.ptr(n_all), _ebk.ptr(P.p("user_W")), _ebk.ptr(P.p("user_q")), 0, 0,
                                         _ebk.ptr(ctx["wu"]), ctx["wu"].numel(), _ebk.ptr(d_user), F_, _ebk.ptr(P.g("user_W")),

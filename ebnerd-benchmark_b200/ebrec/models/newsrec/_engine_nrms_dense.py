@@ -192,13 +192,12 @@ class NRMSDenseEngine(NRMSEngine):
         loss.zero_()
         dn_all = self._buf("dn_all", (N, self.D))
         d_user = self._buf("d_user", (B, self.D))
-        scale = 1.0 / (B * self.world)
-        _ebk.check(lib.ebk_score_softmax_ce(B, C_, self.D, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(labels), scale,
-                                            _ebk.ptr(probs), _ebk.ptr(loss), _ebk.ptr(dn_all[BH:]), _ebk.ptr(d_user),
-                                            _ebk.stream()))
+        _ebk.check(lib.ebk_score_loss(self.loss_kind, B, C_, self.D, _ebk.ptr(news_c), _ebk.ptr(u), _ebk.ptr(labels),
+                                      1.0 / (B * self.world), 1.0 / B, _ebk.ptr(probs), _ebk.ptr(loss),
+                                      _ebk.ptr(dn_all[BH:]), _ebk.ptr(d_user), _ebk.stream()))
         for i in range(len(self.units)):  # + l2 * sum ||W||^2  (nrms.py:147-149)
             W = P.p(f"d{i}_W")
-            _ebk.check(lib.ebk_sumsq_accum(_ebk.ptr(W), W.numel(), self.l2 / self.world, _ebk.ptr(loss), _ebk.stream()))
+            _ebk.check(lib.ebk_sumsq_accum(_ebk.ptr(W), W.numel(), self.l2, _ebk.ptr(loss), _ebk.stream()))
         _ebk.check(lib.ebk_seqenc_bwd(C.byref(du), None, _ebk.ptr(n_all), _ebk.ptr(P.p("user_Wqkv")), _ebk.ptr(P.p("user_attW")),
                                       _ebk.ptr(P.p("user_attb")), _ebk.ptr(P.p("user_attq")), 0, 0, 0, _ebk.ptr(wu), wu.numel(),
                                       _ebk.ptr(d_user), _ebk.ptr(P.g("user_Wqkv")), _ebk.ptr(P.g("user_attW")),

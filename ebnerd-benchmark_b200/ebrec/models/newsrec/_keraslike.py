@@ -139,6 +139,11 @@ class KerasLikeModel:
     def compile(self, optimizer=None, loss=None, metrics=None, **_):
         if loss is not None:
             self.loss = loss
+            kinds = {"categorical_crossentropy": 0, "binary_crossentropy": 1}   # _ebk.LOSS_*
+            if isinstance(loss, str):
+                if loss not in kinds:
+                    raise ValueError(f"loss {loss!r} is not on the B200 path (categorical_crossentropy / binary_crossentropy)")
+                self._engine.loss_kind = kinds[loss]
         if metrics is not None:
             self._metrics = [str(m).lower() for m in metrics]
         if optimizer is not None and not isinstance(optimizer, AdamHandle):

@@ -71,7 +71,7 @@ class NAMLModel:
         if loss == "cross_entropy_loss":
             return "categorical_crossentropy"
         elif loss == "log_loss":
-            raise NotImplementedError("log_loss (binary_crossentropy) is not on the B200 path")
+            return "binary_crossentropy"   # base_model.py:63-66 (ebk_score_loss, EBK_LOSS_BINARY_CE)
         raise ValueError(f"this loss not defined {loss}")  # base_model.py:72
 
     def _get_opt(self, optimizer: str, lr: float):
@@ -111,6 +111,8 @@ class NAMLModel:
         for _ in ("news", "user"):
             weights += [glorot_uniform(s, (F, A)), np.zeros(A, np.float32), glorot_uniform(s, (A, 1))]
         self._engine.set_weights(weights)
+        self._engine.loss_kind = (_ebk.LOSS_BINARY_CE if self._get_loss(hp.loss) == "binary_crossentropy"
+                                  else _ebk.LOSS_CATEGORICAL_CE)
         model = _NAMLTrainModel(self, self._engine, "model", "softmax")
         scorer = _NAMLTrainModel(self, self._engine, "scorer", "sigmoid")
         self.newsencoder = _EncoderView(self._engine, "news")

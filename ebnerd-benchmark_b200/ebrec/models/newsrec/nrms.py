@@ -98,8 +98,7 @@ class NRMSModel:
         if loss == "cross_entropy_loss":
             return "categorical_crossentropy"
         elif loss == "log_loss":
-            raise NotImplementedError("log_loss (binary_crossentropy) is not on the B200 path; the shipped "
-                                      "hparams and scripts use cross_entropy_loss")
+            return "binary_crossentropy"   # nrms.py:63-64 (ebk_score_loss, EBK_LOSS_BINARY_CE)
         raise ValueError(f"this loss not defined {loss}")
 
     def _get_opt(self, optimizer: str, lr: float):
@@ -140,6 +139,8 @@ class NRMSModel:
                 weights += [glorot_uniform(s, (din, D), 1), glorot_uniform(s, (din, D), 2), glorot_uniform(s, (din, D), 3),
                             glorot_uniform(s, (D, A), 4), np.zeros((A,), np.float32), glorot_uniform(s, (A, 1), 5)]
         self._engine.set_weights(weights)
+        self._engine.loss_kind = (_ebk.LOSS_BINARY_CE if self._get_loss(hp.loss) == "binary_crossentropy"
+                                  else _ebk.LOSS_CATEGORICAL_CE)
         model = _NRMSTrainModel(self, self._engine, "model", "softmax")
         scorer = _NRMSTrainModel(self, self._engine, "scorer", "sigmoid")
         self.newsencoder = _EncoderView(self._engine, "news")

@@ -58,7 +58,7 @@ class NRMSDocVec:
         if loss == "cross_entropy_loss":
             return "categorical_crossentropy"
         elif loss == "log_loss":
-            raise NotImplementedError("log_loss (binary_crossentropy) is not on the B200 path")
+            return "binary_crossentropy"   # nrms_docvec.py:46-47 (ebk_score_loss, EBK_LOSS_BINARY_CE)
         raise ValueError(f"this loss not defined {loss}")  # nrms_docvec.py:49
 
     def _get_opt(self, optimizer: str, lr: float):
@@ -81,6 +81,8 @@ class NRMSDocVec:
         w += [glorot_uniform(s, (D, D)), glorot_uniform(s, (D, D)), glorot_uniform(s, (D, D)), glorot_uniform(s, (D, A)),
               np.zeros(A, np.float32), glorot_uniform(s, (A, 1))]
         self._engine.set_weights(w)
+        self._engine.loss_kind = (_ebk.LOSS_BINARY_CE if self._get_loss(hp.loss) == "binary_crossentropy"
+                                  else _ebk.LOSS_CATEGORICAL_CE)
         model = _DocVecTrainModel(self, self._engine, "model", "softmax")
         scorer = _DocVecTrainModel(self, self._engine, "scorer", "sigmoid")
         self.newsencoder = _EncoderView(self._engine, "news")

@@ -235,6 +235,18 @@ int ebk_score_softmax_ce(int32_t B, int32_t C, int32_t D, const float* news, con
                          const float* labels, float loss_scale, float* probs, float* loss_sum,
                          float* d_news, float* d_user, void* stream);
 
+/* The same with the loss selected by `kind` and separate scales for the gradient and for the value added to
+ * loss_sum (data parallel: gradient scaled by 1/(B*world), reported loss by 1/B):
+ *   EBK_LOSS_CATEGORICAL_CE  hparams.loss == "cross_entropy_loss" -> "categorical_crossentropy" (nrms.py:61-62)
+ *   EBK_LOSS_BINARY_CE       hparams.loss == "log_loss" -> "binary_crossentropy" (nrms.py:63-64, base_model.py:63-66).
+ *       The model output is still the softmax Activation (nrms.py:202); Keras' backend.binary_crossentropy picks up
+ *       the logits cached on that output (`_keras_logits`) and evaluates sigmoid_cross_entropy_with_logits on
+ *       them: loss_b = mean_c [max(z,0) - z*y + log(1 + exp(-|z|))], dz = (sigmoid(z) - y) / C.  probs stay softmax. */
+typedef enum { EBK_LOSS_CATEGORICAL_CE = 0, EBK_LOSS_BINARY_CE = 1 } ebk_loss_kind;
+int ebk_score_loss(int32_t kind, int32_t B, int32_t C, int32_t D, const float* news, const float* user,
+                   const float* labels, float grad_scale, float loss_scale, float* probs, float* loss_sum,
+                   float* d_news, float* d_user, void* stream);
+
 /* scorer head: sigmoid(news . user), nrms.py:204-205.  news [B, C, D] -> out [B, C]. */
 int ebk_score_sigmoid(int32_t B, int32_t C, int32_t D, const float* news, const float* user,
                       float* out, void* stream);

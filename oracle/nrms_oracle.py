@@ -269,6 +269,18 @@ def softmax_ce(z, y):
     return loss, p, dz
 
 
+def sigmoid_ce_on_softmax_logits(z, y):
+    """hparams.loss == "log_loss" -> Keras "binary_crossentropy" (nrms.py:63-64) on the softmax Activation output of
+    nrms.py:202.  keras.backend.binary_crossentropy looks for logits cached on its argument (`_keras_logits`, set by
+    BOTH keras.activations.softmax and .sigmoid) and, finding the softmax's, evaluates
+    tf.nn.sigmoid_cross_entropy_with_logits on them: max(z,0) - z*y + log(1 + exp(-|z|)), mean over the candidate
+    axis, then mean over the batch.  The model's predictions stay the softmax probabilities."""
+    y = y.astype(z.dtype)
+    per = (np.maximum(z, 0) - z * y + np.log1p(np.exp(-np.abs(z)))).mean(axis=-1)
+    dz = (sigmoid(z) - y) / z.dtype.type(z.shape[-1] * z.shape[0])
+    return per.mean(), softmax(z), dz
+
+
 # ---------------------------------------------------------------------------
 # Whole model
 # ---------------------------------------------------------------------------
@@ -302,10 +314,11 @@ def nrms_score(his, pred_one, P, nh, dh):
     return sigmoid(z)
 
 
-def nrms_loss_and_grads(his, pred, y, P, nh, dh, *, training=True, p_drop=0.0, seed1=0, seed2=0, loss_scale=1.0):
+def nrms_loss_and_grads(his, pred, y, P, nh, dh, *, training=True, p_drop=0.0, seed1=0, seed2=0, loss_scale=1.0,
+                        loss_kind="cross_entropy_loss"):
     z, (B, H, C, D, c_news, c_user, Nc, u) = nrms_forward(
         his, pred, P, nh, dh, training=training, p_drop=p_drop, seed1=seed1, seed2=seed2)
-    loss, prob, dz = softmax_ce(z, y)
+    loss, prob, dz = softmax_ce(z, y) if loss_kind == "cross_entropy_loss" else sigmoid_ce_on_softmax_logits(z, y)
     dz = dz * z.dtype.type(loss_scale)
     grads = {k: np.zeros_like(v) for k, v in P.items()}
     dNc = dz[..., None] * u[:, None, :]

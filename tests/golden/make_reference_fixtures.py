@@ -91,6 +91,16 @@ def nrms_fixture(name, with_grads_full):
         out[f"gp_drop_{k}"] = RC.probe(k, g)
         out[f"gmax_drop_{k}"] = np.abs(g).max()
     if with_grads_full:
+        # hparams.loss = "log_loss" -> binary_crossentropy on the softmax output (nrms.py:63-64)
+        SH._Phase.dropout_masks = lambda shape, layer: None   # Dropout off
+        hp2 = hp_of(hp, loss="log_loss")
+        m2 = NRMSModel(hp2, word2vec_embedding=ws[0], seed=1)
+        m2.model.set_weights(ws)
+        assert m2.model.loss == "binary_crossentropy"
+        loss, _, grads = m2.model.loss_and_grads((his, pred), y, training=True)
+        out["loss_logloss"] = loss
+        for k, g in zip(keys, grads):
+            out[f"g_logloss_{k}"] = g
         # two optimizer steps (Keras-form Adam as restated in the shim) without dropout
         SH._Phase.dropout_masks = lambda shape, layer: None   # Dropout off
         m.model.optimizer = tf.keras.optimizers.Adam(learning_rate=1e-3)

@@ -51,6 +51,17 @@ def test_nrms_oracle_matches_reference_source(name):
                 assert close(G[k], ref[f"g_{tag}_{k}"], 1e-9), (tag, k)
 
 
+def test_nrms_log_loss_matches_reference_source():
+    """hparams.loss = "log_loss": binary_crossentropy on the softmax output = sigmoid CE of the cached logits."""
+    (V, E, nh, dh, att, B, H, C, T), ws, his, pred, y = RC.nrms_case("small")
+    ref = np.load(GOLD / "ref_nrms_small.npz")
+    P = dict(zip(O.NRMS_PARAM_ORDER, ws))
+    loss, _, G = O.nrms_loss_and_grads(his, pred, y, P, nh, dh, training=False, loss_kind="log_loss")
+    assert abs(loss - float(ref["loss_logloss"])) < 1e-10
+    for k in O.NRMS_PARAM_ORDER:
+        assert close(G[k], ref[f"g_logloss_{k}"], 1e-9), k
+
+
 def test_nrms_two_adam_steps_match_reference_source():
     """train_on_batch x 2 through the reference graph + Keras-form Adam (restated in the shim and in the oracle)."""
     (V, E, nh, dh, att, B, H, C, T), ws, his, pred, y = RC.nrms_case("small")

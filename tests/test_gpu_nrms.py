@@ -243,23 +243,35 @@ def test_scorer_dedup_matches_plain_predict():
     assert float(np.abs(dedup - want).max() / np.abs(want).max()) < 1e-3     # and the fp32-oracle gate of the scorer
 
 
-def test_auc_parity_with_oracle_trained_model():
+AUC_CASES = {
+    # V, E, nh, dh, att, B, H, C, T, topics, topic-token fraction, lr, steps, held-out impressions
+    "small": (400, 32, 4, 8, 24, 64, 8, 5, 10, 8, 0.5, 2e-3, 60, 2048),
+    # xlm-roberta-base width, the BASELINE config-3 encoder (20 heads x 20, attention_hidden 200)
+    "e768_d400": (20000, 768, 20, 20, 200, 32, 8, 5, 10, 16, 0.35, 1e-3, 24, 1024),
+}
+
+
+@pytest.mark.parametrize("case", list(AUC_CASES))
+def test_auc_parity_with_oracle_trained_model(case):
     """North-star gate: AUC within +-0.002 of the reference.  The same NRMS (same initial weights, same batches,
-    same dropout masks) is trained for 60 Adam steps by the GPU engine (tcgen05 tf32 path) and by the float64
-    oracle; both models then score a held-out set and are compared on the reference's AucScore
-    (mean per-impression roc_auc_score, evaluation/metrics_protocols.py:73-86).  The task is learnable: the
-    clicked candidate shares tokens with the user's history."""
+    same dropout masks) is trained by the GPU engine (tcgen05 tf32 TMA path -- the benchmarked arithmetic) and by
+    the float64 oracle (pinned to the reference source by tests/test_cpu_reference_golden.py); both models then
+    score a held-out set and are compared on the reference's AucScore (mean per-impression roc_auc_score,
+    evaluation/metrics_protocols.py:73-86).  The task is learnable: the clicked candidate shares tokens with the
+    user's history.  "e768_d400" runs it at the BASELINE encoder dimensions (E=768, D=400, att=200)."""
     from sklearn.metrics import roc_auc_score
 
-    V, E, nh, dh, att, B, H, C, T = 400, 32, 4, 8, 24, 64, 8, 5, 10
+    V, E, nh, dh, att, B, H, C, T, n_topics, frac, lr, steps, n_held = AUC_CASES[case]
     rng = np.random.default_rng(2024)
     P, _, _, _ = make_case(rng, V, E, nh, dh, att, 2, H, C, T)
+    if E >= 256:
+        P["table"] = rng.normal(0, 0.02, (V, E))
 
     def batch(n):
-        topic = rng.integers(0, 8, n)                                   # each user reads one of 8 "topics"
+        topic = rng.integers(0, n_topics, n)                            # each user reads one "topic"
 
-        def toks(shape, tp):                                            # half of the tokens carry the topic
-            return np.where(rng.random(shape) < 0.5, tp * 50 + rng.integers(0, 50, shape),
+        def toks(shape, tp):                                            # a fraction of the tokens carries the topic
+            return np.where(rng.random(shape) < frac, tp * 50 + rng.integers(0, 50, shape),
                             rng.integers(0, V, shape)).astype(np.int32)
 
         his = toks((n, H, T), topic[:, None, None])
@@ -270,7 +282,7 @@ def test_auc_parity_with_oracle_trained_model():
         y[np.arange(n), pos] = 1
         return his, pred, y
 
-    lr, p_drop, steps = 2e-3, 0.2, 60
+    p_drop = 0.2
     eng = make_engine(P, V, E, T, H, nh, dh, att, p_drop, lr, 1, seed=5)
     Po = {k: v.copy() for k, v in P.items()}
     Pm = {k: np.zeros_like(v) for k, v in P.items()}
@@ -283,13 +295,14 @@ def test_auc_parity_with_oracle_trained_model():
         _, _, G = O.nrms_loss_and_grads(his, pred, y, Po, nh, dh, training=True, p_drop=p_drop, seed1=s1, seed2=s2)
         for k in Po:
             O.keras_adam_step(Po[k], G[k], Pm[k], Pv[k], t, lr)
-    his, pred, y = batch(2048)
+    his, pred, y = batch(n_held)
     tok, _ = eng.to_device_batch(his, pred)
-    p_gpu = eng.predict_dev(tok, 2048, C).cpu().numpy()
+    p_gpu = eng.predict_dev(tok, n_held, C).cpu().numpy()
     p_orc = O.nrms_predict(his, pred, Po, nh, dh)
     auc = lambda p: float(np.mean([roc_auc_score(y[i], p[i]) for i in range(len(y))]))
     a_gpu, a_orc = auc(p_gpu), auc(p_orc)
-    assert 0.7 < a_orc < 0.97, a_orc               # mid-training: learned, not saturated (measured 0.88)
+    print(f"[parity] AUC {case}: GPU-trained {a_gpu:.4f} vs oracle-trained {a_orc:.4f} (|diff| {abs(a_gpu - a_orc):.4f})")
+    assert 0.7 < a_orc < 0.99, a_orc               # learned, not saturated
     assert abs(a_gpu - a_orc) <= 0.002, (a_gpu, a_orc)
 
 

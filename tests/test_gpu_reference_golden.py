@@ -118,6 +118,20 @@ def test_nrms_loss_and_gradients_match_reference(name, tag, math):
         assert v < gtol * (5.0 if k.endswith(("WQ", "WK")) else 1.0), (k, v)
 
 
+def test_nrms_log_loss_matches_reference():
+    """hparams.loss = "log_loss" (nrms.py:63-64): loss value and table / WV gradients vs the reference fixture."""
+    ref = np.load(GOLD / "ref_nrms_small.npz")
+    eng, tok, lab, (B, C, H, T, D) = nrms_engine("small", MATH_FP32, 0.0)
+    eng.loss_kind = 1   # EBK_LOSS_BINARY_CE
+    eng.params.grad.zero_()
+    loss, probs = eng.loss_and_grads_dev(tok, lab, B, C, training=True, seeds=(1, 2))
+    assert abs(float(loss) - float(ref["loss_logloss"])) < 1e-4
+    assert rel(probs.cpu().numpy(), ref["probs"]) < 1e-4                  # predictions stay the softmax
+    assert rel(eng.params.g("table").cpu().numpy(), ref["g_logloss_table"]) < 2e-4
+    assert rel(eng.params.g("news_Wqkv")[:, 2 * D:].cpu().numpy(), ref["g_logloss_news_WV"]) < 2e-4
+    assert rel(eng.params.g("user_attW").cpu().numpy(), ref["g_logloss_user_W"]) < 2e-4
+
+
 def test_nrms_two_adam_steps_match_reference():
     ref = np.load(GOLD / "ref_nrms_small.npz")
     eng, tok, lab, (B, C, H, T, D) = nrms_engine("small", MATH_FP32, 0.0)
