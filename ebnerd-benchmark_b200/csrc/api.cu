@@ -11,14 +11,10 @@
 namespace ebk {
 
 static thread_local char g_err[512] = "";
-// data parallel: CUDA event recorded right after the embedding-gradient scatter of the next ebk_seqenc_bwd
-// call of this thread, so the host can start the table-gradient collective while the remaining backward
-// kernels (the QKV weight-gradient GEMM) still run
-static thread_local cudaEvent_t g_table_grad_event = nullptr;
-// Deferred weight gradient: the QKV wgrad GEMM (tensor-pipe bound) is independent of everything the optimizer's
-// table pass (HBM bound) needs, so on request it runs on a library-owned side stream, forked after the dgrad
-// GEMM, and is joined by ebk_join_deferred() before its output is consumed.
-static thread_local bool g_defer_wgrad = false;
+// Deferred weight gradient (ebk_seqenc_opts.defer_wgrad): the QKV wgrad GEMM (tensor-pipe bound) is independent of
+// everything the optimizer's table pass (HBM bound) needs, so on request it runs on a library-owned side stream,
+// forked after the dgrad GEMM, and is joined by ebk_join_deferred() before its output is consumed.  The only state
+// kept between calls is "a fork is outstanding on this thread's side stream".
 static thread_local bool g_side_pending = false;
 static thread_local cudaStream_t g_side = nullptr;
 static thread_local cudaEvent_t g_ev_fork = nullptr, g_ev_join = nullptr;
@@ -33,8 +29,22 @@ static int side_stream_init() {
   }
   return EBK_OK;
 }
-// data parallel, rank-sharded table: peer mappings used by the embedding gather of the training forward
-static thread_local PeerTables g_peers = {0, 0, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
+// per-call options -> kernel-side peer-table descriptor (data parallel, rank-sharded table)
+static int peers_from_opts(const ebk_seqenc_opts* o, PeerTables* out) {
+  PeerTables pt = {0, 0, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
+  if (o != nullptr && o->peer_tables != nullptr && o->peer_world > 1) {
+    EBK_CHECK_ARG(o->peer_world <= 8, "seqenc: at most 8 peer tables (one NVSwitch box), got %d", o->peer_world);
+    EBK_CHECK_ARG(o->peer_shard_floats > 0 && o->peer_shard_floats % 4 == 0, "seqenc: peer_shard_floats must be a positive multiple of 4");
+    pt.world = o->peer_world;
+    pt.shard_floats = o->peer_shard_floats;
+    for (int r = 0; r < o->peer_world; ++r) {
+      EBK_CHECK_ARG(o->peer_tables[r] != nullptr, "seqenc: peer table %d is NULL", r);
+      pt.p[r] = reinterpret_cast<const float*>(o->peer_tables[r]);
+    }
+  }
+  *out = pt;
+  return EBK_OK;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -169,7 +179,6 @@ int check_desc(const ebk_seqenc_desc* d) {
 using namespace ebk;
 
 extern "C" const char* ebk_last_error(void) { return g_err; }
-extern "C" int ebk_join_deferred(void* stream);
 namespace ebk { void gemm_tf32_set_debug(long long* buf, int target); }
 // debugging aid: device buffer of 3*96*4 int64 receiving clock64() stamps of CTA 0 of the target-th
 // tcgen05 GEMM launched after this call (NULL disarms)
@@ -177,20 +186,12 @@ extern "C" int ebk_debug_gemm_timeline(long long* device_buf, int target) {
   ebk::gemm_tf32_set_debug(device_buf, target);
   return 0;
 }
-extern "C" int ebk_set_deferred_wgrad(int on) {
-  g_defer_wgrad = on != 0;
-  return EBK_OK;
-}
 extern "C" int ebk_join_deferred(void* stream) {
   if (g_side_pending) {
     EBK_CUDA(cudaEventRecord(g_ev_join, g_side));
     EBK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, g_ev_join, 0));
     g_side_pending = false;
   }
-  return EBK_OK;
-}
-extern "C" int ebk_set_table_grad_event(void* cuda_event) {
-  g_table_grad_event = (cudaEvent_t)cuda_event;
   return EBK_OK;
 }
 // ---- CUDA IPC plumbing for the rank-sharded table (one process per GPU, all on one NVSwitch box) ----------
@@ -221,14 +222,6 @@ extern "C" int ebk_ipc_open(const void* handle64, size_t offset, void** out) {
   void* base = nullptr;
   EBK_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
   *out = reinterpret_cast<char*>(base) + offset;
-  return EBK_OK;
-}
-// tables[r] = this process's mapping of rank r's table buffer (own pointer for r == rank); world <= 1 disarms
-extern "C" int ebk_set_peer_tables(const void* const* tables, int32_t world, size_t shard_floats) {
-  EBK_CHECK_ARG(world <= 8, "set_peer_tables: at most 8 ranks (one NVSwitch box)");
-  g_peers.world = world > 1 ? world : 0;
-  g_peers.shard_floats = shard_floats;
-  for (int r = 0; r < 8; ++r) g_peers.p[r] = (world > 1 && r < world) ? reinterpret_cast<const float*>(tables[r]) : nullptr;
   return EBK_OK;
 }
 extern "C" long long ebk_launch_count(void) { return g_launches.load(); }
@@ -274,11 +267,26 @@ extern "C" size_t ebk_seqenc_workspace_bytes(const ebk_seqenc_desc* d) {
   return seq_layout(*d, nullptr).bytes;
 }
 
+extern "C" int ebk_seqenc_uses_tma(const ebk_seqenc_desc* d) {
+  if (check_desc(d) != EBK_OK) return 0;
+  return tma_path(*d, seq_layout(*d, nullptr)) ? 1 : 0;
+}
+
 extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, const float* table_or_x,
                               const float* Wqkv, const float* attW, const float* attb, const float* attq,
                               int training, uint64_t seed1, uint64_t seed2, void* workspace,
                               size_t workspace_bytes, float* out, void* stream) {
+  return ebk_seqenc_fwd_opts(d, nullptr, tok, table_or_x, Wqkv, attW, attb, attq, training, seed1, seed2, workspace,
+                             workspace_bytes, out, stream);
+}
+
+extern "C" int ebk_seqenc_fwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_opts* opts, const int32_t* tok,
+                                   const float* table_or_x, const float* Wqkv, const float* attW, const float* attb,
+                                   const float* attq, int training, uint64_t seed1, uint64_t seed2, void* workspace,
+                                   size_t workspace_bytes, float* out, void* stream) {
   EBK_TRY(check_desc(d));
+  PeerTables peers;
+  EBK_TRY(peers_from_opts(opts, &peers));
   if (d->n_seq == 0) return EBK_OK;
   const bool pool = d->att > 0;   // att == 0: stop after the SelfAttention, out = [n_seq*L, D] (no dropout on it)
   EBK_CHECK_ARG(table_or_x && Wqkv && out && workspace && (!pool || (attW && attb && attq)), "seqenc_fwd: null pointer");
@@ -299,7 +307,7 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
   if (tma_path(*d, ws)) {
     // ---- all-TMA path: every GEMM operand is materialised dense, masked and tf32-rounded by the layer
     // before it, so the tensor-core kernels spend no issue slots on operand preparation ----
-    const bool remote = tok && training && g_peers.world > 1;   // rank-sharded table: rows come over NVLink
+    const bool remote = tok && peers.world > 1;   // rank-sharded table: rows come over NVLink
     EBK_TRY(round_tf32_copy(ws.wqkv_r, Wqkv, (size_t)d->Din * 3 * D, st));
     if (pool) EBK_TRY(round_tf32_copy(ws.attw_r, attW, (size_t)D * d->att, st));
     // (stored rounded to tf32: the attention kernels feed it to mma.sync without touching it again)
@@ -322,7 +330,7 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
         {
           cudaStream_t st = g_side;   // EBK_PROF records its events on `st`
           EBK_PROF(T_EMBED_GATHER, embed_rows(rows, d->Din, d->V, tok + r0, table_or_x, drop1, ws.xd + (size_t)r0 * d->Din, st,
-                                              &g_peers, r0));
+                                              &peers, r0));
         }
         EBK_CUDA(cudaEventRecord(g_ev_chunk[c], g_side));
       }
@@ -335,7 +343,7 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
       }
     } else {
       EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st,
-                                          remote ? &g_peers : nullptr));
+                                          remote ? &peers : nullptr));
       // (1) Q|K|V = dropout1(gather(table, tok)) . Wqkv        nrms.py:134-139, layers.py:214-230
       EBK_PROF(T_QKV_FWD, gemm_tma(ws.xd, d->Din, false, ws.wqkv_r, 3 * D, false, ws.qkv, 3 * D, R, 3 * D, d->Din, 0.0f,
                                    1.0f, st, -1, &round_epi));
@@ -360,6 +368,9 @@ extern "C" int ebk_seqenc_fwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
     EBK_PROF(T_POOL_FWD, attpool_fwd(d->n_seq, d->L, D, d->att, ws.y0, none, ws.hbuf, attb, attq, ws.w, out, st));
     return EBK_OK;
   }
+  // only the all-TMA path gathers through peer mappings: anything else would silently read a stale local shard
+  EBK_CHECK_ARG(peers.world <= 1, "seqenc_fwd: peer tables need the all-TMA path (EBK_MATH_TF32, att %% 4 == 0, "
+                "16-byte aligned row strides; query ebk_seqenc_uses_tma)");
   // Tensor-core modes: the weights are packed once per call (rounded to tf32, arranged in the GEMM's
   // shared-memory tile layout) and kept in the workspace for the backward pass.
   const bool tc = d->math != EBK_MATH_FP32;
@@ -403,7 +414,18 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
                               int training, uint64_t seed1, uint64_t seed2, void* workspace,
                               size_t workspace_bytes, const float* d_out, float* dWqkv, float* dattW,
                               float* dattb, float* dattq, float* d_table, float* d_x, void* stream) {
+  return ebk_seqenc_bwd_opts(d, nullptr, tok, table_or_x, Wqkv, attW, attb, attq, training, seed1, seed2, workspace,
+                             workspace_bytes, d_out, dWqkv, dattW, dattb, dattq, d_table, d_x, stream);
+}
+
+extern "C" int ebk_seqenc_bwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_opts* opts, const int32_t* tok,
+                                   const float* table_or_x, const float* Wqkv, const float* attW, const float* attb,
+                                   const float* attq, int training, uint64_t seed1, uint64_t seed2, void* workspace,
+                                   size_t workspace_bytes, const float* d_out, float* dWqkv, float* dattW,
+                                   float* dattb, float* dattq, float* d_table, float* d_x, void* stream) {
   EBK_TRY(check_desc(d));
+  const bool defer_wgrad = opts != nullptr && opts->defer_wgrad != 0;
+  cudaEvent_t table_grad_event = opts != nullptr ? (cudaEvent_t)opts->table_grad_event : nullptr;
   if (d->n_seq == 0) return EBK_OK;
   (void)attb;
   const bool pool = d->att > 0;   // att == 0: d_out is the gradient of the [n_seq*L, D] attention output
@@ -461,12 +483,9 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
                                      st, -1));
       if (tok && d_table) EBK_PROF(T_SCATTER, scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
     }
-    if (tok && g_table_grad_event) {
-      EBK_CUDA(cudaEventRecord(g_table_grad_event, st));
-      g_table_grad_event = nullptr;
-    }
+    if (tok && table_grad_event) EBK_CUDA(cudaEventRecord(table_grad_event, st));
     // dWqkv += X^T dQKV  (X = dropout1(gather)); deferred mode: on the side stream, behind the dgrad GEMM
-    if (g_defer_wgrad && tok != nullptr) {
+    if (defer_wgrad && tok != nullptr) {
       EBK_TRY(side_stream_init());
       EBK_CUDA(cudaEventRecord(g_ev_fork, st));
       EBK_CUDA(cudaStreamWaitEvent(g_side, g_ev_fork, 0));
@@ -535,10 +554,7 @@ extern "C" int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, cons
                                         3 * D, 0.0f, st, pk_qkv ? GEMM_B_PACKED : GEMM_B_RAW));
     if (tok && d_table) EBK_PROF(T_SCATTER, scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
   }
-  if (tok && g_table_grad_event) {
-    EBK_CUDA(cudaEventRecord(g_table_grad_event, st));
-    g_table_grad_event = nullptr;
-  }
+  if (tok && table_grad_event) EBK_CUDA(cudaEventRecord(table_grad_event, st));
   return EBK_OK;
 }
 

@@ -24,7 +24,8 @@ LOSS_BINARY_CE = 1        # hparams.loss "log_loss"
 
 SYMBOLS = [
     "ebk_last_error", "ebk_version", "ebk_device_ok",
-    "ebk_seqenc_workspace_bytes", "ebk_seqenc_fwd", "ebk_seqenc_bwd", "ebk_set_table_grad_event", "ebk_set_deferred_wgrad", "ebk_join_deferred", "ebk_ipc_export", "ebk_ipc_open", "ebk_set_peer_tables",
+    "ebk_seqenc_workspace_bytes", "ebk_seqenc_fwd", "ebk_seqenc_bwd", "ebk_seqenc_fwd_opts", "ebk_seqenc_bwd_opts",
+    "ebk_join_deferred", "ebk_seqenc_uses_tma", "ebk_ipc_export", "ebk_ipc_open",
     "ebk_score_softmax_ce", "ebk_score_loss", "ebk_score_sigmoid", "ebk_adam_keras_step",
     "ebk_embed_adam_workspace_bytes", "ebk_embed_adam_step",
     "ebk_dense_workspace_bytes", "ebk_dense_fwd", "ebk_dense_bwd", "ebk_sumsq_accum",
@@ -47,6 +48,12 @@ class SeqEncDesc(C.Structure):
         ("dh", C.c_int32), ("att", C.c_int32), ("V", C.c_int32), ("dropout", C.c_float),
         ("math", C.c_int32),
     ]
+
+
+class SeqEncOpts(C.Structure):
+    """Mirror of ebk_seqenc_opts (include/ebk.h): per-call options, nothing sticky."""
+    _fields_ = [("defer_wgrad", C.c_int32), ("table_grad_event", C.c_void_p), ("peer_tables", C.POINTER(C.c_void_p)),
+                ("peer_world", C.c_int32), ("peer_shard_floats", C.c_size_t)]
 
 
 class DenseDesc(C.Structure):
@@ -94,12 +101,14 @@ def lib() -> C.CDLL:
     l.ebk_seqenc_fwd.argtypes = [dp, vp, vp, vp, vp, vp, vp, C.c_int, u64, u64, vp, sz, vp, vp]
     l.ebk_seqenc_bwd.argtypes = [dp, vp, vp, vp, vp, vp, vp, C.c_int, u64, u64, vp, sz, vp,
                                  vp, vp, vp, vp, vp, vp, vp]
-    l.ebk_set_table_grad_event.argtypes = [vp]
-    l.ebk_set_deferred_wgrad.argtypes = [C.c_int]
+    op = C.POINTER(SeqEncOpts)
+    l.ebk_seqenc_fwd_opts.argtypes = [dp, op, vp, vp, vp, vp, vp, vp, C.c_int, u64, u64, vp, sz, vp, vp]
+    l.ebk_seqenc_bwd_opts.argtypes = [dp, op, vp, vp, vp, vp, vp, vp, C.c_int, u64, u64, vp, sz, vp,
+                                      vp, vp, vp, vp, vp, vp, vp]
     l.ebk_join_deferred.argtypes = [vp]
+    l.ebk_seqenc_uses_tma.argtypes = [dp]
     l.ebk_ipc_export.argtypes = [vp, vp, C.POINTER(sz)]
     l.ebk_ipc_open.argtypes = [vp, sz, C.POINTER(vp)]
-    l.ebk_set_peer_tables.argtypes = [C.POINTER(vp), i32, sz]
     ddp = C.POINTER(DenseDesc)
     l.ebk_dense_workspace_bytes.restype = sz
     l.ebk_dense_workspace_bytes.argtypes = [ddp]

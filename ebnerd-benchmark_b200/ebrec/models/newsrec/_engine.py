@@ -62,7 +62,9 @@ class FlatParams:
         for name, shape in spec:
             self.offsets[name] = off
             off += (int(np.prod(shape)) + _ALIGN - 1) // _ALIGN * _ALIGN
-        off = (off + 1023) // 1024 * 1024  # divisible into 16-byte aligned shards for any world size <= 64
+        # divisible into 16-byte aligned shards for every world size 1..8 (and 16, 32, 64, ...: powers of two up to
+        # 256): a multiple of 4 * lcm(1..8) = 3360 and of 1024; other world sizes fall back to an all-reduce
+        off = (off + 107519) // 107520 * 107520
         self.n = off
         self.theta = torch.zeros(off, dtype=torch.float32, device=device)
         self.grad = torch.zeros_like(self.theta)
@@ -185,18 +187,20 @@ class NRMSEngine:
         N = tok_all.shape[0]
         if Hh != self.H:
             raise ValueError(f"history length {Hh} != hparams.history_size {self.H}")
+        opts = None
         if training:
-            self._arm_peer_tables()
+            opts = self._peer_opts()     # rank-sharded table: gather rows from their owners over NVLink
         else:
             self._sync_table()
         dn = self._desc("news", N, training)
         wn = self._workspace("news", dn)
         n_all = self._buf("n_all", (N, self.D))
-        _ebk.check(lib.ebk_seqenc_fwd(C.byref(dn), _ebk.ptr(tok_all), _ebk.ptr(P.p("table")),
-                                      _ebk.ptr(P.p("news_Wqkv")), _ebk.ptr(P.p("news_attW")),
-                                      _ebk.ptr(P.p("news_attb")), _ebk.ptr(P.p("news_attq")),
-                                      int(training), seeds[0], seeds[1], _ebk.ptr(wn), wn.numel(),
-                                      _ebk.ptr(n_all), _ebk.stream()))
+        _ebk.check(lib.ebk_seqenc_fwd_opts(C.byref(dn), C.byref(opts) if opts is not None else None,
+                                           _ebk.ptr(tok_all), _ebk.ptr(P.p("table")),
+                                           _ebk.ptr(P.p("news_Wqkv")), _ebk.ptr(P.p("news_attW")),
+                                           _ebk.ptr(P.p("news_attb")), _ebk.ptr(P.p("news_attq")),
+                                           int(training), seeds[0], seeds[1], _ebk.ptr(wn), wn.numel(),
+                                           _ebk.ptr(n_all), _ebk.stream()))
         du = self._desc("user", B, training)
         wu = self._workspace("user", du)
         u = self._buf("u", (B, self.D))
@@ -361,10 +365,13 @@ class NRMSEngine:
         base = _mix(self.seed, self.step_count * self.world + self.rank)
         return _mix(base, 1), _mix(base, 2)
 
-    def loss_and_grads_dev(self, tok_all, labels, B, C_, training=True, seeds=None, sparse_table=False):
+    def loss_and_grads_dev(self, tok_all, labels, B, C_, training=True, seeds=None, sparse_table=False,
+                           defer_wgrad=False):
         """Forward + backward; gradients ACCUMULATE into params.grad.  Returns (loss_sum, probs).
         sparse_table: leave the table gradient as per-row gradients in the "dx" buffer (for apply_adam(sparse=...))
-        instead of scatter-adding it into params.grad."""
+        instead of scatter-adding it into params.grad.
+        defer_wgrad: the news encoder's QKV weight-gradient GEMM runs on the library's side stream; the caller joins
+        it with ebk_join_deferred (apply_adam(sparse=...) does)."""
         lib, P = _ebk.lib(), self.params
         seeds = self.step_seeds() if seeds is None else seeds
         n_all, news_c, u, (dn, wn, du, wu) = self.forward_logits_parts(tok_all, B, C_, training, seeds)
@@ -385,22 +392,23 @@ class NRMSEngine:
                                       _ebk.ptr(d_user), _ebk.ptr(P.g("user_Wqkv")), _ebk.ptr(P.g("user_attW")),
                                       _ebk.ptr(P.g("user_attb")), _ebk.ptr(P.g("user_attq")), None,
                                       _ebk.ptr(dn_all), _ebk.stream()))
+        opts = _ebk.SeqEncOpts(1 if defer_wgrad else 0, None, None, 0, 0)
         if self.world > 1:
             # the table gradient is final after the scatter inside this call: apply_adam starts its
             # reduce-scatter from that point, overlapping the weight-gradient GEMM that follows
             dp = self._dp_state()
             torch.cuda.current_stream().wait_event(dp["zeroed"])  # last step's clearing of the table gradient
-            lib.ebk_set_table_grad_event(C.c_void_p(dp["table_grad"].cuda_event))
+            opts.table_grad_event = C.c_void_p(dp["table_grad"].cuda_event)
             dp["armed"] = True
-        _ebk.check(lib.ebk_seqenc_bwd(C.byref(dn), _ebk.ptr(tok_all), _ebk.ptr(P.p("table")),
-                                      _ebk.ptr(P.p("news_Wqkv")), _ebk.ptr(P.p("news_attW")),
-                                      _ebk.ptr(P.p("news_attb")), _ebk.ptr(P.p("news_attq")), int(training),
-                                      seeds[0], seeds[1], _ebk.ptr(wn), wn.numel(), _ebk.ptr(dn_all),
-                                      _ebk.ptr(P.g("news_Wqkv")), _ebk.ptr(P.g("news_attW")),
-                                      _ebk.ptr(P.g("news_attb")), _ebk.ptr(P.g("news_attq")),
-                                      None if sparse_table else _ebk.ptr(P.g("table")),
-                                      _ebk.ptr(self._buf("dx", (N * self.T, self.E))) if sparse_table else None,
-                                      _ebk.stream()))
+        _ebk.check(lib.ebk_seqenc_bwd_opts(C.byref(dn), C.byref(opts), _ebk.ptr(tok_all), _ebk.ptr(P.p("table")),
+                                           _ebk.ptr(P.p("news_Wqkv")), _ebk.ptr(P.p("news_attW")),
+                                           _ebk.ptr(P.p("news_attb")), _ebk.ptr(P.p("news_attq")), int(training),
+                                           seeds[0], seeds[1], _ebk.ptr(wn), wn.numel(), _ebk.ptr(dn_all),
+                                           _ebk.ptr(P.g("news_Wqkv")), _ebk.ptr(P.g("news_attW")),
+                                           _ebk.ptr(P.g("news_attb")), _ebk.ptr(P.g("news_attq")),
+                                           None if sparse_table else _ebk.ptr(P.g("table")),
+                                           _ebk.ptr(self._buf("dx", (N * self.T, self.E))) if sparse_table else None,
+                                           _ebk.stream()))
         return loss, probs
 
     def apply_adam(self, sparse=None) -> None:
@@ -468,12 +476,18 @@ class NRMSEngine:
                                                self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
             if sharded:
                 # rank-sharded table: no all-gather -- the next forward's Embedding gather reads each chunk from its
-                # owner over NVLink (ebk_set_peer_tables).  A one-element all-reduce orders every rank's Adam
+                # owner over NVLink (ebk_seqenc_opts.peer_tables).  A one-element all-reduce orders every rank's Adam
                 # before any rank's next gather.
                 self._table_stale = True
                 dist.all_reduce(self._buf("dp_fence", (1,)))
             else:
                 w_ag.wait()
+            return
+        if P.n % (4 * self.world) != 0:
+            # world size that does not divide the buffer into aligned shards: plain all-reduce, replicated Adam
+            dist.all_reduce(P.grad)
+            _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(P.theta), _ebk.ptr(P.grad), _ebk.ptr(P.m), _ebk.ptr(P.v),
+                                               P.n, alpha, self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
             return
         shard = P.n // self.world
         lo = self.rank * shard
@@ -487,20 +501,24 @@ class NRMSEngine:
 
     def _peer_tables(self, tbl: int):
         """CUDA-IPC mappings of every rank's parameter buffer (data parallel on one NVSwitch box, world <= 8), or
-        None when the table cannot be sharded (EBK_DP_SHARDED_TABLE=0, world > 8, unaligned shard)."""
+        None when the table cannot be sharded: EBK_DP_SHARDED_TABLE=0, world > 8, unaligned shard, or a training
+        forward that does not run on the all-TMA path (math fp32 / 3xTF32, att % 4 != 0, no TMA encoder in the
+        driver) -- only that path gathers through the peer mappings, so anything else keeps replicated tables and the
+        all-gather of apply_adam."""
         import os
 
         if hasattr(self, "_peers"):
             return self._peers
         self._peers = None
         dist = torch.distributed
+        lib = _ebk.lib()
         ok = (os.environ.get("EBK_DP_SHARDED_TABLE", "1") != "0" and 1 < self.world <= 8 and tbl > 0
-              and tbl % (4 * self.world) == 0 and type(self) is NRMSEngine)
+              and tbl % (4 * self.world) == 0 and type(self) is NRMSEngine
+              and bool(lib.ebk_seqenc_uses_tma(C.byref(self._desc("news", 1, True)))))
         flag = torch.tensor([1 if ok else 0], device=self.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag) == 0:
             return None
-        lib = _ebk.lib()
         handle = (C.c_char * 64)()
         off = C.c_size_t(0)
         _ebk.check(lib.ebk_ipc_export(_ebk.ptr(self.params.theta), C.cast(handle, C.c_void_p), C.byref(off)))
@@ -519,16 +537,19 @@ class NRMSEngine:
         self._peers = {"ptrs": (C.c_void_p * self.world)(*ptrs), "shard": tbl // self.world}
         return self._peers
 
-    def _arm_peer_tables(self) -> None:
-        """Point the training forward's Embedding gather at the owners' table shards (no-op on one GPU)."""
-        if self.world <= 1:
-            return
+    def _peer_opts(self):
+        """Options of a TRAINING forward: gather table rows from the owners' shards while this rank's replica is
+        stale (after a sharded Adam step), else nothing (first step / after a sync: every replica is current)."""
+        forced = getattr(self, "_force_peer_opts", None)     # tests: exercise the peer gather on one GPU
+        if forced is not None:
+            ptrs, world, shard = forced
+            return _ebk.SeqEncOpts(0, None, ptrs, world, shard)
+        if self.world <= 1 or not getattr(self, "_table_stale", False):
+            return None
         pt = self._peer_tables(self.params.offsets.get("news_Wqkv", 0))
-        lib = _ebk.lib()
-        if pt is None or not getattr(self, "_table_stale", False):
-            lib.ebk_set_peer_tables(None, 0, 0)   # every replica is current (first step / after a sync)
-        else:
-            _ebk.check(lib.ebk_set_peer_tables(pt["ptrs"], self.world, pt["shard"]))
+        if pt is None:
+            return None
+        return _ebk.SeqEncOpts(0, None, pt["ptrs"], self.world, pt["shard"])
 
     def _sync_table(self) -> None:
         """Make this rank's replica of the table current (all-gather of the owners' shards); needed before any
@@ -541,8 +562,6 @@ class NRMSEngine:
             th = P.theta[self.rank * shard: (self.rank + 1) * shard]
             torch.distributed.all_gather_into_tensor(P.theta[:tbl], th)
             self._table_stale = False
-        if self.world > 1:
-            _ebk.lib().ebk_set_peer_tables(None, 0, 0)
 
     def sync_optimizer_state(self) -> None:
         """Data parallel: Adam's m / v of the table live only on the rank that owns each slice; gather them (and the
@@ -553,6 +572,8 @@ class NRMSEngine:
         P = self.params
         tbl = P.offsets.get("news_Wqkv", 0)
         n = tbl if (tbl > 0 and tbl % (4 * self.world) == 0 and type(self) is NRMSEngine) else P.n
+        if n % (4 * self.world) != 0:
+            return   # replicated Adam (see apply_adam): every rank already holds the full state
         shard = n // self.world
         lo = self.rank * shard
         for buf in (P.m, P.v):
@@ -581,33 +602,36 @@ class NRMSEngine:
             self.apply_adam()
             return loss, probs
         seeds = self.step_seeds()
-        lib = _ebk.lib()
-        defer = os.environ.get("EBK_DEFER_WGRAD", "1") != "0"
         # the QKV weight-gradient GEMM (tensor bound) overlaps the table's Adam pass (HBM bound): see ebk.h
-        lib.ebk_set_deferred_wgrad(1 if defer else 0)
-        try:
-            loss, probs = self.loss_and_grads_dev(tok_all, labels, B, C_, training=True, seeds=seeds, sparse_table=sparse)
-        finally:
-            lib.ebk_set_deferred_wgrad(0)
+        defer = os.environ.get("EBK_DEFER_WGRAD", "1") != "0"
+        loss, probs = self.loss_and_grads_dev(tok_all, labels, B, C_, training=True, seeds=seeds, sparse_table=sparse,
+                                              defer_wgrad=defer)
         self.apply_adam(sparse=(tok_all, seeds[0]) if sparse else None)
         return loss, probs
 
     # ------------------------------------------------------------------ host-array convenience
     def _h2d(self, key: str, arr: np.ndarray) -> torch.Tensor:
         """Host array -> device through a small ring of PINNED staging buffers (asynchronous copy: the host goes on
-        launching kernels while the DMA runs).  A slot is reused only after the copy that last read it finished."""
+        launching kernels while the DMA runs).  A slot is reused only after the copy that last read it finished.
+        The ring is keyed by (key, dtype) and sized by CAPACITY (grown geometrically), so eval-mode loaders whose
+        batches differ in length reuse the same four buffers instead of pinning new ones per shape."""
         ring = self.__dict__.setdefault("_pin_ring", {})
-        slots = ring.setdefault((key, arr.shape, arr.dtype.str), {"i": 0, "bufs": []})
+        slots = ring.setdefault((key, arr.dtype.str), {"i": 0, "bufs": []})
+        n = int(arr.size)
         if len(slots["bufs"]) < 4:
-            slots["bufs"].append([torch.empty(arr.shape, dtype=torch.from_numpy(arr).dtype).pin_memory(), None])
+            slots["bufs"].append([None, None])
             slot = slots["bufs"][-1]
         else:
             slot = slots["bufs"][slots["i"] % 4]
             slots["i"] += 1
             if slot[1] is not None:
                 slot[1].synchronize()
-        slot[0].numpy()[...] = arr
-        dev = slot[0].to(self.device, non_blocking=True)
+        if slot[0] is None or slot[0].numel() < n:
+            cap = max(1024, 1 << (max(n, 1) - 1).bit_length())
+            slot[0] = torch.empty(cap, dtype=torch.from_numpy(arr).dtype).pin_memory()
+        stage = slot[0][:n].view(arr.shape)
+        stage.numpy()[...] = arr
+        dev = stage.to(self.device, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         slot[1] = ev

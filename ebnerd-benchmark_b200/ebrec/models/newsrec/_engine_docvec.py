@@ -190,8 +190,35 @@ class DocVecEngine(NRMSEngine):
         self._mlp_bwd(ctx_c, dn_all[BH:], training, seeds[1], 0.0)
         return loss, probs
 
+    # ------------------------------------------------------------------ device-resident doc-vector matrix
+    def set_article_matrix(self, matrix: np.ndarray) -> None:
+        """Upload the [n_articles + 1, Ddoc] document-vector matrix of a dataloader once (row 0 = unknown article,
+        create_lookup_objects, _python.py:412-484); batches then carry article ROW INDICES.  The reference gathers
+        the float vectors on the host for every batch (dataloader.py:146-180) and ships [B, H+C, Ddoc] floats
+        (39 MB per step at BASELINE config 2); here a step moves B*(H+C) int32."""
+        m = np.ascontiguousarray(np.asarray(matrix), dtype=np.float32)
+        if m.ndim != 2 or m.shape[1] != self.Ddoc:
+            raise ValueError(f"doc-vector matrix must be [n_articles, title_size={self.Ddoc}], got {m.shape}")
+        self.article_matrix = torch.from_numpy(m).to(self.device)
+
+    def vectors_from_indices(self, his_idx, pred_idx) -> torch.Tensor:
+        """[B,H] + [B,C] article row indices -> [B*H + B*C, Ddoc] float rows on the device (history first)."""
+        if getattr(self, "article_matrix", None) is None:
+            raise ValueError("index batches need set_article_matrix(lookup_article_matrix) first")
+        idx = np.concatenate([np.asarray(his_idx).reshape(-1), np.asarray(pred_idx).reshape(-1)]).astype(np.int64)
+        n = self.article_matrix.shape[0]
+        if idx.size and (idx.min() < 0 or idx.max() >= n):
+            raise IndexError(f"article row index outside [0, {n})")
+        return self.article_matrix.index_select(0, self._h2d("idx", idx))
+
     # ------------------------------------------------------------------ host convenience
     def to_device_batch(self, his, pred, y=None):
+        if np.asarray(his).ndim == 2:   # article row indices of a device-feed loader
+            xd = self.vectors_from_indices(his, pred)
+            lab = None
+            if y is not None:
+                lab = self._h2d("lab", np.ascontiguousarray(y, dtype=np.float32))
+            return xd, lab
         his, pred = np.asarray(his, dtype=np.float32), np.asarray(pred, dtype=np.float32)
         B, H, Dd = his.shape
         C_ = pred.shape[1]

@@ -218,7 +218,34 @@ class NAMLEngine(NRMSEngine):
             out.append(np.ascontiguousarray(m if k < 2 else m.reshape(-1)))
         return out
 
+    def set_article_matrices(self, title_matrix: np.ndarray, body_matrix: np.ndarray) -> None:
+        """Device-resident batch feed: the [n+1, title_size] and [n+1, body_size] token matrices of a
+        NAMLDataLoaderDevice are uploaded once; batches then carry article row indices for the two text views."""
+        t = np.ascontiguousarray(np.asarray(title_matrix), dtype=np.int32)
+        b = np.ascontiguousarray(np.asarray(body_matrix), dtype=np.int32)
+        if t.ndim != 2 or t.shape[1] != self.T or b.ndim != 2 or b.shape[1] != self.Tb:
+            raise ValueError(f"token matrices must be [n, {self.T}] and [n, {self.Tb}], got {t.shape} and {b.shape}")
+        self.title_matrix, self.body_matrix = torch.from_numpy(t).to(self.device), torch.from_numpy(b).to(self.device)
+
     def to_device_batch(self, arrays, y=None):
+        if np.asarray(arrays[0]).ndim == 2:
+            # index feed: (his_title_idx [B,H], his_body_idx [B,H], his_vert [B,H,1], his_subvert [B,H,1], pred_...)
+            if getattr(self, "title_matrix", None) is None:
+                raise ValueError("index batches need set_article_matrices(title_matrix, body_matrix) first")
+            a = [np.asarray(v) for v in arrays]
+            rows = []
+            for k, mat in ((0, self.title_matrix), (1, self.body_matrix)):
+                idx = np.concatenate([a[k].reshape(-1), a[4 + k].reshape(-1)]).astype(np.int64)
+                if idx.size and (idx.min() < 0 or idx.max() >= mat.shape[0]):
+                    raise IndexError(f"article row index outside [0, {mat.shape[0]})")
+                rows.append(mat.index_select(0, torch.from_numpy(idx).to(self.device, non_blocking=True)))
+            cats = [torch.from_numpy(np.concatenate([a[k].reshape(-1), a[4 + k].reshape(-1)]).astype(np.int32)).to(
+                self.device, non_blocking=True) for k in (2, 3)]
+            x = (rows[0], rows[1], cats[0], cats[1])
+            lab = None
+            if y is not None:
+                lab = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).to(self.device, non_blocking=True)
+            return x, lab
         x = tuple(torch.from_numpy(m).to(self.device, non_blocking=True) for m in self.pack_inputs(arrays))
         lab = None
         if y is not None:

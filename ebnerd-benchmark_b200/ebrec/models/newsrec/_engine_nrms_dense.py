@@ -223,9 +223,24 @@ class NRMSDenseEngine(NRMSEngine):
     def encode_host(self, kind, x):
         x = np.asarray(x)
         if kind == "news":
+            # newsencoder.predict: Embedding -> SelfAttention -> Dense/BN stack (moving statistics) -> AttLayer2
+            lib, P = _ebk.lib(), self.params
             tok = torch.from_numpy(np.ascontiguousarray(x.reshape(-1, self.T), dtype=np.int32)).to(self.device)
-            # one "impression" of zero history is enough to reuse _encode: encode as candidates of a dummy batch
-            raise NotImplementedError("newsencoder.predict is not exposed for the dense-stack variant; use model.predict")
+            N = tok.shape[0]
+            dn = self._desc("news", N, False)
+            wn = self._workspace("news", dn)
+            y0 = self._buf("y0", (N * self.T, self.D))
+            _ebk.check(lib.ebk_seqenc_fwd(C.byref(dn), _ebk.ptr(tok), _ebk.ptr(P.p("table")), _ebk.ptr(P.p("news_Wqkv")),
+                                          None, None, None, 0, 0, 0, _ebk.ptr(wn), wn.numel(), _ebk.ptr(y0), _ebk.stream()))
+            z, _ = self._stack_fwd(2, y0, False, 0)
+            U = self.units[-1]
+            da = _ebk.AttLayerDesc(N, self.T, U, self.att, 0.0, self.math_infer)
+            wa = self._sized(("att", 2), lib.ebk_attlayer_workspace_bytes(C.byref(da)))
+            out = torch.empty((N, self.D), device=self.device)
+            _ebk.check(lib.ebk_attlayer_fwd(C.byref(da), _ebk.ptr(z.contiguous()), _ebk.ptr(P.p("news_attW")),
+                                            _ebk.ptr(P.p("news_attb")), _ebk.ptr(P.p("news_attq")), 0, 0, _ebk.ptr(wa),
+                                            wa.numel(), _ebk.ptr(out), self.D, _ebk.stream()))
+            return out.cpu().numpy()
         B = x.shape[0]
         tok = torch.from_numpy(np.ascontiguousarray(x.reshape(B * self.H, self.T), dtype=np.int32)).to(self.device)
         _, u, _ = self._encode(tok, B, self.H, False)

@@ -119,6 +119,24 @@ class _Prefetcher:
             yield item
 
 
+def shard_for_rank(order: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Data parallel: the batches (or samples) of one epoch that THIS rank trains on.  Every rank draws the same
+    shuffled `order` (same seed) and takes every world-th entry; the tail that cannot be split evenly is dropped
+    so that all ranks run the same number of optimizer steps (each step ends in a collective).  The reference has
+    no data parallelism; with world == 1 this is the identity."""
+    if world <= 1:
+        return order
+    n = (len(order) // world) * world
+    return order[:n][rank::world]
+
+
+def _unpack_xy(data):
+    """Keras accepts validation_data / x as (inputs, y): split such a pair, leave loaders and bare inputs alone."""
+    if isinstance(data, (tuple, list)) and len(data) == 2 and isinstance(data[0], (tuple, list)):
+        return tuple(data[0]), data[1]
+    return data, None
+
+
 def _is_sequence(x) -> bool:
     return hasattr(x, "__getitem__") and hasattr(x, "__len__") and not isinstance(x, (tuple, list, np.ndarray))
 
@@ -165,24 +183,47 @@ class KerasLikeModel:
         return self.get_weights()
 
     def save_weights(self, filepath, overwrite=True, **_):
+        """Checkpoint = {weights in Keras get_weights() order, Adam m / v / iteration, lr} as a torch.save file
+        (NOT Keras' h5 / TF-checkpoint format: there is no TensorFlow here; `get_weights()` arrays are in the
+        reference's order, so `reference_model.set_weights(model.get_weights())` moves weights across).
+        Data parallel: COLLECTIVE -- every rank calls it (ModelCheckpoint runs on all ranks); the rank-sharded
+        optimizer state is gathered, rank 0 alone writes, and a barrier follows."""
         import os
 
-        os.makedirs(os.path.dirname(str(filepath)) or ".", exist_ok=True)
         e = self._engine
+        world = getattr(e, "world", 1)
         if hasattr(e, "sync_optimizer_state"):
-            e.sync_optimizer_state()   # data parallel: every rank must call save_weights (collective)
-        state = {"weights": [torch.from_numpy(w) for w in e.get_weights()], "step_count": e.step_count,
-                 "adam_m": e.params.m.cpu(), "adam_v": e.params.v.cpu(), "lr": e.lr}
-        torch.save(state, str(filepath))
+            e.sync_optimizer_state()
+        weights = e.get_weights()
+        if world <= 1 or e.rank == 0:
+            os.makedirs(os.path.dirname(str(filepath)) or ".", exist_ok=True)
+            if not overwrite and os.path.exists(str(filepath)):
+                raise FileExistsError(str(filepath))
+            state = {"weights": [torch.from_numpy(np.ascontiguousarray(w)) for w in weights], "step_count": e.step_count,
+                     "adam_m": e.params.m.cpu(), "adam_v": e.params.v.cpu(), "lr": e.lr, "format": "ebk-1"}
+            tmp = f"{filepath}.tmp{os.getpid()}"
+            torch.save(state, tmp)
+            os.replace(tmp, str(filepath))
+        if world > 1:
+            torch.distributed.barrier()
 
     def load_weights(self, filepath, **_):
+        """Restores weights, Adam moments / iteration count and the learning rate.  A checkpoint whose optimizer
+        state does not fit this model (different vocabulary / widths) raises instead of silently dropping it."""
         e = self._engine
         state = torch.load(str(filepath), map_location="cpu", weights_only=True)
         e.set_weights([w.numpy() for w in state["weights"]])
-        if "adam_m" in state and state["adam_m"].numel() == e.params.m.numel():
+        if "adam_m" in state:
+            if state["adam_m"].numel() != e.params.m.numel():
+                raise ValueError(f"{filepath}: optimizer state of {state['adam_m'].numel()} parameters does not fit this "
+                                 f"model ({e.params.m.numel()})")
             e.params.m.copy_(state["adam_m"])
             e.params.v.copy_(state["adam_v"])
             e.step_count = int(state["step_count"])
+        if "lr" in state:
+            e.lr = float(state["lr"])
+        if hasattr(e, "_table_stale"):
+            e._table_stale = False   # every replica now holds the full table
 
     def summary(self, print_fn=print):
         e = self._engine
@@ -202,17 +243,24 @@ class KerasLikeModel:
     def _n_samples(x):
         return int(np.asarray(x[0]).shape[0])
 
-    def _batches(self, x, y, batch_size, shuffle, rng):
-        """Yield (inputs_tuple, y_or_None).  Arrays: Keras shuffles samples; Sequence: batch order."""
+    def _batches(self, x, y, batch_size, shuffle, rng, shard=False):
+        """Yield (inputs_tuple, y_or_None).  Arrays: Keras shuffles samples; Sequence: batch order.
+        shard (training under data parallel): this rank's share of every epoch, see shard_for_rank."""
         if _is_sequence(x):
-            if getattr(x, "device_feed", False) and hasattr(self._engine, "set_article_matrix"):
-                # device-resident feed: upload the loader's token matrix once, batches are row indices
+            if getattr(x, "device_feed", False):
+                # device-resident feed: upload the loader's lookup matrix (token ids, doc vectors) once; batches
+                # are article row indices
                 if getattr(self._engine, "_article_matrix_src", None) is not x.lookup_article_matrix:
-                    self._engine.set_article_matrix(x.lookup_article_matrix)
+                    if hasattr(x, "lookup_article_matrix_body"):      # NAML: title + body token matrices
+                        self._engine.set_article_matrices(x.lookup_article_matrix, x.lookup_article_matrix_body)
+                    else:
+                        self._engine.set_article_matrix(x.lookup_article_matrix)
                     self._engine._article_matrix_src = x.lookup_article_matrix
             order = np.arange(len(x))
             if shuffle:
                 rng.shuffle(order)
+            if shard:
+                order = shard_for_rank(order, self._engine.rank, self._engine.world)
 
             def fetch(i):
                 item = x[int(i)]
@@ -226,6 +274,15 @@ class KerasLikeModel:
         idx = np.arange(n)
         if shuffle:
             rng.shuffle(idx)
+        world = self._engine.world if shard else 1
+        if world > 1:
+            # a global step = world consecutive batches of bs samples, one per rank; the uneven tail is dropped
+            steps = n // (bs * world)
+            for g in range(steps):
+                lo = (g * world + self._engine.rank) * bs
+                sel = idx[lo: lo + bs]
+                yield tuple(a[sel] for a in xs), (None if y is None else np.asarray(y)[sel])
+            return
         for s in range(0, n, bs):
             sel = idx[s: s + bs]
             if not shuffle:
@@ -246,7 +303,11 @@ class KerasLikeModel:
         for cb in cbs:
             if hasattr(cb, "on_train_begin"):
                 cb.on_train_begin({})
-        rng = np.random.default_rng(self._engine.seed + 7919)
+        # the shuffle stream lives on the model: fit(epochs=1) called in a loop sees a new order every time
+        rng = self.__dict__.setdefault("_shuffle_rng", np.random.default_rng(self._engine.seed + 7919))
+        world = getattr(self._engine, "world", 1)
+        if y is None:
+            x, y = _unpack_xy(x)
         for epoch in range(initial_epoch, epochs):
             for cb in cbs:
                 if hasattr(cb, "on_epoch_begin"):
@@ -256,7 +317,7 @@ class KerasLikeModel:
             n_seen = 0
             ys, ps = [], []
             nb = 0
-            for inputs, yb in self._batches(x, y, batch_size, shuffle, rng):
+            for inputs, yb in self._batches(x, y, batch_size, shuffle, rng, shard=True):
                 loss_dev, probs_dev, bsz = self._train_batch(inputs, yb)
                 tot_loss += loss_dev * bsz  # stays on device: no per-step host sync
                 n_seen += bsz
@@ -264,9 +325,19 @@ class KerasLikeModel:
                 if "auc" in self._metrics:
                     ys.append(np.asarray(yb))
                     ps.append(probs_dev.clone())
-            logs = {"loss": float(tot_loss) / max(n_seen, 1)}
+            if world > 1:   # every rank logs the GLOBAL epoch mean (callbacks then decide identically on all ranks)
+                agg = torch.cat([tot_loss.double(), torch.tensor([float(n_seen)], device=tot_loss.device, dtype=torch.float64)])
+                torch.distributed.all_reduce(agg)
+                logs = {"loss": float(agg[0]) / max(float(agg[1]), 1.0)}
+            else:
+                logs = {"loss": float(tot_loss) / max(n_seen, 1)}
             if "auc" in self._metrics and ys:
-                logs["auc"] = keras_auc(np.concatenate(ys), torch.cat(ps).cpu().numpy())
+                yt, yp = np.concatenate(ys), torch.cat(ps).cpu().numpy()
+                if world > 1:
+                    parts = [None] * world
+                    torch.distributed.all_gather_object(parts, (yt, yp))
+                    yt, yp = np.concatenate([a for a, _ in parts]), np.concatenate([b for _, b in parts])
+                logs["auc"] = keras_auc(yt, yp)
             if validation_data is not None:
                 vlogs = self.evaluate(validation_data, verbose=0, return_dict=True)
                 logs.update({f"val_{k}": v for k, v in vlogs.items()})
@@ -287,6 +358,10 @@ class KerasLikeModel:
         return hist
 
     def evaluate(self, x=None, y=None, batch_size=None, verbose=0, return_dict=False, **_):
+        """Data parallel: every rank evaluates the WHOLE set (collective-free apart from the table sync), so all
+        ranks see identical val_* logs."""
+        if y is None:
+            x, y = _unpack_xy(x)
         tot, n_seen, ys, ps = 0.0, 0, [], []
         rng = np.random.default_rng(0)
         for inputs, yb in self._batches(x, y, batch_size, False, rng):

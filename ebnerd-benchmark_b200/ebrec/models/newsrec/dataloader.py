@@ -176,6 +176,13 @@ class NRMSDataLoaderDevice(NRMSDataLoader):
 
 
 @dataclass
+class NRMSDocVecDataLoaderDevice(NRMSDataLoaderDevice):
+    """Device-resident feed for NRMSDocVec: ``article_dict`` maps article ids
+    to 768-d document vectors, so ``lookup_article_matrix`` is the float [n_articles + 1, 768] matrix (386 MB for
+    ebnerd_large) -- uploaded to HBM once; batches are the same row-index tuples as NRMSDataLoaderDevice."""
+
+
+@dataclass
 class NRMSDataLoaderPretransform(NRMSDataLoader):
     """Reference: pre-transforms the whole frame in __post_init__ (dataloader.py:122-180).  Every loader
     of this build already does that, so this is the same class under the reference's name."""
@@ -218,6 +225,31 @@ class NAMLDataLoader(NewsrecDataLoader):
             np.array(self._hist_sub[sl])[:, :, np.newaxis],
             mt[np.array(self._inview_idx[sl])],
             mb[np.array(self._inview_body[sl])],
+            np.array(self._inview_cat[sl])[:, :, np.newaxis],
+            np.array(self._inview_sub[sl])[:, :, np.newaxis],
+        ), batch_y
+
+
+@dataclass(kw_only=True)
+class NAMLDataLoaderDevice(NAMLDataLoader):
+    """Device-resident feed for NAML: title / body token matrices live in HBM (uploaded once by the model), a batch
+    carries article row indices for the two text views and the category ids:
+    (his_title_idx [B,H], his_body_idx [B,H], his_vert [B,H,1], his_subvert [B,H,1], pred_title_idx [B,C], ...), y.
+    ``lookup_article_matrix[idx]`` / ``lookup_article_matrix_body[idx]`` reproduce NAMLDataLoader's batch exactly."""
+
+    device_feed = True
+
+    def __getitem__(self, idx):
+        sl = self._slice(idx)
+        batch_y = np.array(self.y[sl])
+        i32 = np.int32
+        return (
+            np.array(self._hist_idx[sl], dtype=i32),
+            np.array(self._hist_body[sl], dtype=i32),
+            np.array(self._hist_cat[sl])[:, :, np.newaxis],
+            np.array(self._hist_sub[sl])[:, :, np.newaxis],
+            np.array(self._inview_idx[sl], dtype=i32),
+            np.array(self._inview_body[sl], dtype=i32),
             np.array(self._inview_cat[sl])[:, :, np.newaxis],
             np.array(self._inview_sub[sl])[:, :, np.newaxis],
         ), batch_y

@@ -16,7 +16,7 @@ from ._engine import NRMSEngine
 from ._keraslike import KerasLikeModel
 
 
-def glorot_uniform(seed, shape, salt=0):
+def glorot_uniform(seed, shape):
     """keras GlorotUniform(seed)(shape).  Keras returns the SAME tensor for the same (seed, shape)
     (WQ == WK == WV at init); with seed=None draws are independent."""
     rng = np.random.default_rng(None if seed is None else [int(seed), int(shape[0]), int(shape[-1])])
@@ -121,23 +121,23 @@ class NRMSModel:
                                            att=A, units=units, l2=getattr(hp, "newsencoder_l2_regularization", 1e-4),
                                            dropout=hp.dropout, lr=hp.learning_rate, seed=self.seed,
                                            math=getattr(self, "_math", _ebk.MATH_TF32))
-            weights = [table, glorot_uniform(s, (E, D), 1), glorot_uniform(s, (E, D), 2), glorot_uniform(s, (E, D), 3)]
+            weights = [table, glorot_uniform(s, (E, D)), glorot_uniform(s, (E, D)), glorot_uniform(s, (E, D))]
             din = D
             for u in units:  # Keras: Dense kernel GlorotUniform (unseeded), bias 0; BN gamma 1, beta 0, mean 0, var 1
                 weights += [glorot_uniform(None, (din, u)), np.zeros((u,), np.float32), np.ones((u,), np.float32),
                             np.zeros((u,), np.float32), np.zeros((u,), np.float32), np.ones((u,), np.float32)]
                 din = u
-            weights += [glorot_uniform(s, (din, A), 4), np.zeros((A,), np.float32), glorot_uniform(s, (A, 1), 5)]
-            weights += [glorot_uniform(s, (D, D), 1), glorot_uniform(s, (D, D), 2), glorot_uniform(s, (D, D), 3),
-                        glorot_uniform(s, (D, A), 4), np.zeros((A,), np.float32), glorot_uniform(s, (A, 1), 5)]
+            weights += [glorot_uniform(s, (din, A)), np.zeros((A,), np.float32), glorot_uniform(s, (A, 1))]
+            weights += [glorot_uniform(s, (D, D)), glorot_uniform(s, (D, D)), glorot_uniform(s, (D, D)),
+                        glorot_uniform(s, (D, A)), np.zeros((A,), np.float32), glorot_uniform(s, (A, 1))]
         else:
             self._engine = NRMSEngine(V=V, E=E, T=hp.title_size, H=hp.history_size, nh=hp.head_num, dh=hp.head_dim,
                                       att=A, dropout=hp.dropout, lr=hp.learning_rate, seed=self.seed,
                                       math=getattr(self, "_math", _ebk.MATH_TF32))
             weights = [table]
             for din in (E, D):  # news encoder, then user encoder (Keras get_weights order)
-                weights += [glorot_uniform(s, (din, D), 1), glorot_uniform(s, (din, D), 2), glorot_uniform(s, (din, D), 3),
-                            glorot_uniform(s, (D, A), 4), np.zeros((A,), np.float32), glorot_uniform(s, (A, 1), 5)]
+                weights += [glorot_uniform(s, (din, D)), glorot_uniform(s, (din, D)), glorot_uniform(s, (din, D)),
+                            glorot_uniform(s, (D, A)), np.zeros((A,), np.float32), glorot_uniform(s, (A, 1))]
         self._engine.set_weights(weights)
         self._engine.loss_kind = (_ebk.LOSS_BINARY_CE if self._get_loss(hp.loss) == "binary_crossentropy"
                                   else _ebk.LOSS_CATEGORICAL_CE)

@@ -19,8 +19,9 @@ from .nrms import _EncoderView, glorot_uniform
 class _DocVecTrainModel(KerasLikeModel):
     def _pack(self, inputs, y=None):
         his, pred = (np.asarray(a) for a in inputs)
-        if his.ndim != 3 or pred.ndim != 3:
-            raise ValueError(f"expected his [B,H,Ddoc] and pred [B,C,Ddoc], got {his.shape} and {pred.shape}")
+        if his.ndim != pred.ndim or his.ndim not in (2, 3):
+            raise ValueError(f"expected his [B,H,Ddoc] and pred [B,C,Ddoc] (or [B,H] / [B,C] article indices of a "
+                             f"device-feed loader), got {his.shape} and {pred.shape}")
         x, lab = self._engine.to_device_batch(his, pred, y)
         return x, lab, pred.shape[0], pred.shape[1]
 

@@ -15,8 +15,11 @@
  *  - kernels never allocate: scratch and saved activations live in a caller-provided
  *    workspace whose size comes from the matching *_workspace_bytes() query;
  *    a forward and its backward must be given the SAME workspace;
- *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous, stateless
- *    and ordered only by the stream.
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous and ordered only by
+ *    the stream.  Entry points keep no modes between calls: per-call behaviour comes from the
+ *    descriptor / options structs.  (Process-wide state: the tensor-map cache, the measurement
+ *    hooks at the end of this header, and "a deferred weight gradient is outstanding", which
+ *    ebk_join_deferred clears.)
  */
 #ifndef EBK_H_
 #define EBK_H_
@@ -98,28 +101,50 @@ int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, const float* ta
                    float* dWqkv, float* dattW, float* dattb, float* dattq,
                    float* d_table, float* d_x, void* stream);
 
-/* Deferred weight gradient (single-GPU optimizer overlap).  After ebk_set_deferred_wgrad(1), ebk_seqenc_bwd calls
- * of this thread WITH token ids launch their QKV weight-gradient GEMM (tensor-pipe bound) on a library-owned side
- * stream, forked behind the input-gradient GEMM, and return without joining it: the caller may then enqueue work
- * that does not touch dWqkv or the call's workspace (the HBM-bound table pass of the optimizer) on its own stream
- * and MUST call ebk_join_deferred(stream) before anything that does (and before the next forward). */
-int ebk_set_deferred_wgrad(int on);
+/* Per-call options of the sequence encoder (NULL = all off).  They replace the thread-local setters of the first
+ * version of this ABI: nothing armed by one call can leak into the next.
+ *   defer_wgrad       backward WITH token ids: the QKV weight-gradient GEMM (tensor-pipe bound) is launched on a
+ *                     library-owned side stream, forked behind the input-gradient GEMM, and the call returns
+ *                     without joining it: the caller may then enqueue work that does not touch dWqkv or the call's
+ *                     workspace (the HBM-bound table pass of the optimizer) on its own stream and MUST call
+ *                     ebk_join_deferred(stream) before anything that does (and before the next forward).
+ *   table_grad_event  backward WITH token ids (data parallel): cudaEvent_t (as void*) recorded on the stream right
+ *                     after the embedding-gradient scatter -- the table gradient is then final, so its collective
+ *                     can start while the remaining backward kernels still run.
+ *   peer_tables       forward WITH token ids (data parallel, rank-sharded embedding table; all ranks on one NVSwitch
+ *                     box, <= 8): peer_tables[r] = this process's mapping of rank r's parameter buffer (own pointer
+ *                     for r == rank).  Every 16-byte chunk of a gathered table row is read from the rank that owns
+ *                     float index f (owner = f / peer_shard_floats) -- the all-gather of the updated table is fused
+ *                     into the Embedding gather (nrms.py:125-134) over NVLink.  Only the all-TMA path
+ *                     (ebk_seqenc_uses_tma(desc) == 1) gathers through peers; any other path returns
+ *                     EBK_ERR_INVALID rather than read a stale local shard. */
+typedef struct {
+  int32_t defer_wgrad;
+  void* table_grad_event;
+  const void* const* peer_tables;
+  int32_t peer_world;
+  size_t peer_shard_floats;
+} ebk_seqenc_opts;
+
+int ebk_seqenc_fwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_opts* opts, const int32_t* tok,
+                        const float* table_or_x, const float* Wqkv, const float* attW, const float* attb,
+                        const float* attq, int training, uint64_t seed1, uint64_t seed2, void* workspace,
+                        size_t workspace_bytes, float* out, void* stream);
+int ebk_seqenc_bwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_opts* opts, const int32_t* tok,
+                        const float* table_or_x, const float* Wqkv, const float* attW, const float* attb,
+                        const float* attq, int training, uint64_t seed1, uint64_t seed2, void* workspace,
+                        size_t workspace_bytes, const float* d_out, float* dWqkv, float* dattW, float* dattb,
+                        float* dattq, float* d_table, float* d_x, void* stream);
+/* joins the side stream of a defer_wgrad backward into `stream` (no-op when nothing is outstanding) */
 int ebk_join_deferred(void* stream);
+/* 1 when this descriptor runs on the all-TMA tcgen05 path (EBK_MATH_TF32, att % 4 == 0, TMA-encodable strides) */
+int ebk_seqenc_uses_tma(const ebk_seqenc_desc* d);
 
-/* Data parallel: arm a cudaEvent_t (as void*) that the NEXT ebk_seqenc_bwd call of this thread with token ids
- * records on its stream right after the embedding-gradient scatter -- the table gradient is then final, so its
- * collective can start while the remaining backward kernels still run.  NULL disarms. */
-int ebk_set_table_grad_event(void* cuda_event);
-
-/* Data parallel, rank-sharded embedding table (all ranks on one NVSwitch box, <= 8).  After
- * ebk_set_peer_tables the TRAINING forward of ebk_seqenc_fwd reads every 16-byte chunk of a gathered table row
- * from the rank that owns float index f (owner = f / shard_floats) through the peer mappings -- the all-gather of
- * the updated table is fused into the Embedding gather (nrms.py:125-134) over NVLink.  ebk_ipc_export /
- * ebk_ipc_open wrap cudaIpcGetMemHandle / cudaIpcOpenMemHandle (handle64: 64 bytes; offset of ptr inside its
- * allocation) so that the host code can exchange the mappings with any byte transport. */
+/* CUDA IPC plumbing for peer_tables: ebk_ipc_export / ebk_ipc_open wrap cudaIpcGetMemHandle / cudaIpcOpenMemHandle
+ * (handle64: 64 bytes; offset of ptr inside its allocation) so that the host code can exchange the mappings with any
+ * byte transport. */
 int ebk_ipc_export(const void* ptr, void* handle64, size_t* offset);
 int ebk_ipc_open(const void* handle64, size_t offset, void** out);
-int ebk_set_peer_tables(const void* const* tables, int32_t world, size_t shard_floats);
 
 /* ------------------------------------------------------------------------------------
  * Dense(+ReLU) -> [BatchNormalization] -> [Dropout] layer of the NRMSDocVec news encoder

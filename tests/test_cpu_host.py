@@ -319,3 +319,27 @@ def test_data_parallel_sharded_adam_equals_dense_gloo_world2(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
                         "127.0.0.1", "--master-port", "29519", str(script)], env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "DP_ADAM_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ---- data-parallel fit: which batches a rank trains on ---------------------------------------------------------
+def test_shard_for_rank_gives_disjoint_equal_shares():
+    from ebrec.models.newsrec._keraslike import _unpack_xy, shard_for_rank
+
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 8, 37):
+        order = rng.permutation(n)
+        assert np.array_equal(shard_for_rank(order, 0, 1), order)           # one GPU: identity
+        for world in (2, 3, 8):
+            shares = [shard_for_rank(order, r, world) for r in range(world)]
+            assert len({len(s) for s in shares}) == 1 and len(shares[0]) == n // world   # same number of steps
+            merged = np.concatenate(shares) if n >= world else np.array([], dtype=order.dtype)
+            assert len(set(merged.tolist())) == len(merged)                                # disjoint
+            assert set(merged.tolist()) == set(order[: (n // world) * world].tolist())     # only the uneven tail is dropped
+            # global step g = the batches order[g*world : (g+1)*world], one per rank
+            for g in range(n // world):
+                assert [int(s[g]) for s in shares] == order[g * world:(g + 1) * world].tolist()
+    # Keras-style (inputs, y) pairs are split; loaders and bare input tuples pass through
+    his, pred, y = np.zeros((2, 3, 4)), np.zeros((2, 5, 4)), np.zeros((2, 5))
+    x2, y2 = _unpack_xy(((his, pred), y))
+    assert x2[0] is his and y2 is y
+    assert _unpack_xy((his, pred)) == ((his, pred), None)

@@ -366,17 +366,21 @@ def test_peer_table_gather_paths_match_local_gather(monkeypatch):
             tbl = eng.params.offsets["news_Wqkv"]
             ptr = eng.params.theta.data_ptr()
             arr = (C.c_void_p * 2)(ptr, ptr)
-            _ebk.check(lib.ebk_set_peer_tables(arr, 2, (tbl // 2) // 4 * 4))
-        try:
-            loss, _ = eng.loss_and_grads_dev(tok, lab, B, C_, training=True, seeds=(11, 12))
-            torch.cuda.synchronize()
-        finally:
-            lib.ebk_set_peer_tables(None, 0, 0)
+            eng._force_peer_opts = (arr, 2, (tbl // 2) // 4 * 4)     # -> ebk_seqenc_opts.peer_tables of the forward
+        loss, _ = eng.loss_and_grads_dev(tok, lab, B, C_, training=True, seeds=(11, 12))
+        torch.cuda.synchronize()
         outs.append((float(loss), eng.params.grad.clone()))
     for l, g in outs[1:]:
         # loss and table gradient are summed with atomics (order noise); the gathered rows themselves are identical
         assert abs(l - outs[0][0]) < 1e-6 * abs(outs[0][0])
         assert float((g - outs[0][1]).abs().max()) < 1e-6
+    # a forward that is not on the all-TMA path must refuse peer tables instead of reading a stale local shard
+    eng = make_engine(P, V, E, T, H, nh, dh, att, 0.2, 1e-3, 0, seed=2)     # EBK_MATH_FP32
+    tok, lab = eng.to_device_batch(his, pred, y)
+    ptr = eng.params.theta.data_ptr()
+    eng._force_peer_opts = ((C.c_void_p * 2)(ptr, ptr), 2, (eng.params.offsets["news_Wqkv"] // 2) // 4 * 4)
+    with pytest.raises(_ebk.EbkError, match="peer tables need the all-TMA path"):
+        eng.loss_and_grads_dev(tok, lab, B, C_, training=True, seeds=(11, 12))
 
 
 def test_nrms_dummy_script_flow(capsys):
