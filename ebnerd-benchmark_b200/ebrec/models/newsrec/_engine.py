@@ -457,6 +457,9 @@ class NRMSEngine:
             shard = tbl // self.world
             lo = self.rank * shard
             gsh = self._buf("grad_shard", (shard,))
+            if getattr(self, "dp_prof", None) is not None:
+                self._apply_adam_dp_profiled(dp, tbl, shard, lo, gsh, alpha)
+                return
             side.wait_event(dp["table_grad"])
             with torch.cuda.stream(side):
                 w_rs = dist.reduce_scatter_tensor(gsh, P.grad[:tbl], async_op=True)
@@ -498,6 +501,40 @@ class NRMSEngine:
                                            self.beta1, self.beta2, self.eps, 0, _ebk.stream()))
         dist.all_gather_into_tensor(P.theta, th)
         P.grad.zero_()
+
+    def _apply_adam_dp_profiled(self, dp, tbl, shard, lo, gsh, alpha) -> None:
+        """Measurement variant of the data-parallel optimizer step (bench.py profile pass): the same collectives
+        and kernels, but SERIALISED on the main stream with CUDA events around every collective, so that each one's
+        own duration is visible (the production path overlaps them with the weight-gradient GEMM and the Adam
+        kernels).  Appends {name: (start_event, end_event)} to self.dp_prof."""
+        P, dist, lib = self.params, torch.distributed, _ebk.lib()
+        main = torch.cuda.current_stream()
+        rec = {}
+
+        def timed(name, fn):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(main)
+            fn()
+            b.record(main)
+            rec[name] = (a, b)
+
+        main.wait_event(dp["table_grad"])
+        timed("reduce_scatter_table_grad", lambda: dist.reduce_scatter_tensor(gsh, P.grad[:tbl]))
+        P.grad[:tbl].zero_()
+        dp["zeroed"].record(main)
+        timed("all_reduce_dense_grad", lambda: dist.all_reduce(P.grad[tbl:]))
+        th, m, v = P.theta[lo: lo + shard], P.m[lo: lo + shard], P.v[lo: lo + shard]
+        _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(th), _ebk.ptr(gsh), _ebk.ptr(m), _ebk.ptr(v), shard, alpha,
+                                           self.beta1, self.beta2, self.eps, 0, _ebk.stream()))
+        tt, tg, tm, tv = P.theta[tbl:], P.grad[tbl:], P.m[tbl:], P.v[tbl:]
+        _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(tt), _ebk.ptr(tg), _ebk.ptr(tm), _ebk.ptr(tv), P.n - tbl, alpha,
+                                           self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
+        if self._peer_tables(tbl) is not None:
+            self._table_stale = True
+            timed("fence_all_reduce", lambda: dist.all_reduce(self._buf("dp_fence", (1,))))
+        else:
+            timed("all_gather_table", lambda: dist.all_gather_into_tensor(P.theta[:tbl], th))
+        self.dp_prof.append(rec)
 
     def _peer_tables(self, tbl: int):
         """CUDA-IPC mappings of every rank's parameter buffer (data parallel on one NVSwitch box, world <= 8), or

@@ -205,7 +205,7 @@ class DocVecEngine(NRMSEngine):
         """[B,H] + [B,C] article row indices -> [B*H + B*C, Ddoc] float rows on the device (history first)."""
         if getattr(self, "article_matrix", None) is None:
             raise ValueError("index batches need set_article_matrix(lookup_article_matrix) first")
-        idx = np.concatenate([np.asarray(his_idx).reshape(-1), np.asarray(pred_idx).reshape(-1)]).astype(np.int64)
+        idx = np.concatenate([np.asarray(his_idx).reshape(-1), np.asarray(pred_idx).reshape(-1)]).astype(np.int32)
         n = self.article_matrix.shape[0]
         if idx.size and (idx.min() < 0 or idx.max() >= n):
             raise IndexError(f"article row index outside [0, {n})")
