@@ -397,9 +397,9 @@ def run_ours(args, w, wname):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = lib.ebk_launch_count()
+    l0 = eng.launch_count()      # direct launches + kernels inside CUDA-graph replays
     dev_ms = [timed(dev_step, args.steps) for _ in range(REPEATS)]
-    launches = (lib.ebk_launch_count() - l0) // REPEATS
+    launches = (eng.launch_count() - l0) // REPEATS
     clocks = sampler.stop() if rank == 0 else None
     ms_total = statistics.median(dev_ms)
 

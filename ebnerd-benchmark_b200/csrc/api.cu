@@ -233,6 +233,7 @@ extern "C" int ebk_prof_enable(int on) {
   }
   return EBK_OK;
 }
+extern "C" int ebk_prof_is_enabled(void) { return g_prof ? 1 : 0; }
 extern "C" int ebk_prof_num_tags(void) { return 2 * T_NUM_TAGS; }
 extern "C" const char* ebk_prof_tag_name(int slot) {
   static thread_local char buf[64];
@@ -301,8 +302,9 @@ extern "C" int ebk_seqenc_fwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
   EBK_TRY(ebk_join_deferred(stream));   // a forgotten deferred weight gradient may still read this workspace
   g_prof_user = tok == nullptr;
   const int R = d->n_seq * d->L, D = d->nh * d->dh;
-  Dropout drop1 = make_dropout(training != 0, d->dropout, seed1);
-  Dropout drop2 = make_dropout(training != 0, d->dropout, seed2);
+  const ebk_step_params* sp = opts != nullptr ? opts->step_dev : nullptr;   // device-resident seeds (CUDA graphs)
+  Dropout drop1 = make_dropout(training != 0, d->dropout, seed1, sp ? &sp->seed1 : nullptr);
+  Dropout drop2 = make_dropout(training != 0, d->dropout, seed2, sp ? &sp->seed2 : nullptr);
   const Dropout none = make_dropout(false, 0.0f, 0);
   if (tma_path(*d, ws)) {
     // ---- all-TMA path: every GEMM operand is materialised dense, masked and tf32-rounded by the layer
@@ -443,8 +445,9 @@ extern "C" int ebk_seqenc_bwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
   cudaStream_t st = (cudaStream_t)stream;
   g_prof_user = tok == nullptr;
   const int R = d->n_seq * d->L, D = d->nh * d->dh;
-  Dropout drop1 = make_dropout(training != 0, d->dropout, seed1);
-  Dropout drop2 = make_dropout(training != 0, d->dropout, seed2);
+  const ebk_step_params* sp = opts != nullptr ? opts->step_dev : nullptr;   // device-resident seeds (CUDA graphs)
+  Dropout drop1 = make_dropout(training != 0, d->dropout, seed1, sp ? &sp->seed1 : nullptr);
+  Dropout drop2 = make_dropout(training != 0, d->dropout, seed2, sp ? &sp->seed2 : nullptr);
   const Dropout none = make_dropout(false, 0.0f, 0);
 
   if (tma_path(*d, ws)) {

@@ -94,15 +94,25 @@ struct Dropout {
   uint64_t seed;
   uint32_t thr;   // 0 => disabled
   float scale;    // 1/(1-p)
+  // CUDA-graph replay: the seed of THIS step is read from device memory (ebk_step_params), so that a captured
+  // launch does not bake a seed in; NULL => `seed`
+  const uint64_t* seed_dev;
   __host__ __device__ bool on() const { return thr != 0; }
+  __device__ __forceinline__ uint64_t cur_seed() const {
+#ifdef __CUDA_ARCH__
+    return seed_dev != nullptr ? __ldg(reinterpret_cast<const unsigned long long*>(seed_dev)) : seed;
+#else
+    return seed;
+#endif
+  }
   // scale factor (0 or 1/(1-p)) of element idx
   __device__ __forceinline__ float factor(uint64_t idx) const {
-    return dropout_keep(seed, idx, thr) ? scale : 0.0f;
+    return dropout_keep(cur_seed(), idx, thr) ? scale : 0.0f;
   }
   // factors of the 4 elements of group g (elements 4g .. 4g+3)
   __device__ __forceinline__ float4 factor4_group(uint64_t g) const {
     uint32_t x, y;
-    dropout_group_bits(seed, g, x, y);
+    dropout_group_bits(cur_seed(), g, x, y);
     float4 f;
     f.x = ((x & 0xFFFFu) >= thr) ? scale : 0.0f;
     f.y = ((x >> 16) >= thr) ? scale : 0.0f;
@@ -113,9 +123,10 @@ struct Dropout {
   // factors of the 4 elements of an aligned group starting at idx (idx % 4 == 0)
   __device__ __forceinline__ float4 factor4(uint64_t idx) const { return factor4_group(idx >> 2); }
 };
-static inline Dropout make_dropout(bool training, float p, uint64_t seed) {
+static inline Dropout make_dropout(bool training, float p, uint64_t seed, const uint64_t* seed_dev = nullptr) {
   Dropout d;
   d.seed = seed;
+  d.seed_dev = seed_dev;
   if (training && p > 0.0f) {
     d.thr = dropout_threshold(p);
     d.scale = 1.0f / (1.0f - p);
@@ -214,7 +225,7 @@ bool attention_mma_supported(int L, int dh, const void* p0, const void* p1, cons
 // drop_out / round_out: store dropout(y) (mask and 1/(1-p) scale) and/or round it to tf32 -- what the
 // TMA GEMM of the following AttLayer2 consumes
 int attention_core_fwd_mma(int n_seq, int L, int nh, int dh, const float* qkv, float* y, cudaStream_t st,
-                           Dropout drop_out = Dropout{0, 0, 1.0f}, bool round_out = false);
+                           Dropout drop_out = Dropout{0, 0, 1.0f, nullptr}, bool round_out = false);
 int attention_core_bwd_mma(int n_seq, int L, int nh, int dh, const float* qkv, const float* dy, Dropout drop,
                            float* dqkv, bool round_out, cudaStream_t st, float* dqkv_packed = nullptr,
                            int packed_bn = 0);

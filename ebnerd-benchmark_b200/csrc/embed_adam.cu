@@ -108,7 +108,9 @@ __global__ void __launch_bounds__(256) embed_adam_kernel(int V, int E4, const in
                                                           const float4* __restrict__ dX, Dropout drop,
                                                           float4* __restrict__ d_table, float4* __restrict__ theta,
                                                           float4* __restrict__ m, float4* __restrict__ v, float alpha,
-                                                          float omb1, float omb2, float eps) {
+                                                          const float* __restrict__ alpha_dev, float omb1, float omb2,
+                                                          float eps) {
+  if (alpha_dev != nullptr) alpha = __ldg(alpha_dev);   // CUDA-graph replay: this step's alpha lives in device memory
   const int lane = threadIdx.x & 31;
   const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
   for (long row = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5; row < V; row += nwarps) {
@@ -197,6 +199,14 @@ extern "C" int ebk_embed_adam_step(int32_t R, int32_t E, int32_t V, const int32_
                                    uint64_t drop_seed, float* theta, float* d_table, float* m, float* v, float alpha,
                                    double beta1, double beta2, float eps, void* workspace, size_t workspace_bytes,
                                    void* stream) {
+  return ebk_embed_adam_step_p(R, E, V, tok, dX, drop_p, drop_seed, theta, d_table, m, v, alpha, nullptr, beta1, beta2, eps,
+                               workspace, workspace_bytes, stream);
+}
+
+extern "C" int ebk_embed_adam_step_p(int32_t R, int32_t E, int32_t V, const int32_t* tok, const float* dX, float drop_p,
+                                     uint64_t drop_seed, float* theta, float* d_table, float* m, float* v, float alpha,
+                                     const ebk_step_params* step_dev, double beta1, double beta2, float eps,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
   EBK_CHECK_ARG(R >= 0 && E >= 4 && E % 4 == 0 && E <= 1024 && V >= 1, "embed_adam: need E %% 4 == 0, E <= 1024 (E=%d)", E);
   EBK_CHECK_ARG((R == 0 || (tok && dX)) && theta && d_table && m && v && workspace, "embed_adam: null pointer");
   EBK_CHECK_ARG(((uintptr_t)theta % 16 == 0) && ((uintptr_t)d_table % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
@@ -212,7 +222,8 @@ extern "C" int ebk_embed_adam_step(int32_t R, int32_t E, int32_t V, const int32_
   int* total = cursor + V;
   int* offset = total + 64;
   int* perm = offset + V;
-  const Dropout drop = make_dropout(drop_p > 0.0f, drop_p, drop_seed);
+  const Dropout drop = make_dropout(drop_p > 0.0f, drop_p, drop_seed, step_dev ? &step_dev->seed1 : nullptr);
+  const float* alpha_dev = step_dev ? &step_dev->alpha : nullptr;
   const int E4 = E / 4;
   prof_set_group(0);
   if (prof_on()) prof_begin(T_SCATTER, st);
@@ -247,8 +258,8 @@ extern "C" int ebk_embed_adam_step(int32_t R, int32_t E, int32_t V, const int32_
 #define RUN(CH_)                                                                                                  \
   embed_adam_kernel<CH_><<<grid, 256, 0, st>>>(V, E4, count, offset, perm, reinterpret_cast<const float4*>(dX), drop, \
                                                reinterpret_cast<float4*>(d_table), reinterpret_cast<float4*>(theta),  \
-                                               reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), alpha, omb1, \
-                                               omb2, eps)
+                                               reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), alpha, alpha_dev, \
+                                               omb1, omb2, eps)
   if (ch == 1) RUN(1); else if (ch == 2) RUN(2); else if (ch == 3) RUN(3); else RUN(6);
 #undef RUN
   if (prof_on()) prof_end(T_ADAM, st);

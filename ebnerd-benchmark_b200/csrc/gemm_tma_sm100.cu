@@ -745,7 +745,7 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   const int cm = pair ? 2 : 1;
   TParams p;
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.alpha = alpha;
-  p.epi = epi ? *epi : GemmEpilogue{nullptr, nullptr, 0, 1, Dropout{0, 0, 1.0f}, 0, false};
+  p.epi = epi ? *epi : GemmEpilogue{nullptr, nullptr, 0, 1, Dropout{0, 0, 1.0f, nullptr}, 0, false};
   const bool has_epi = p.epi.rowscale != nullptr || p.epi.drop.on() || p.epi.round_out;
   EBK_CHECK_ARG(!has_epi || beta == 0.0f, "gemm_tma: a fused epilogue needs beta == 0");
   EBK_CHECK_ARG(!p.epi.drop.on() || p.epi.drop_ld % 4 == 0, "gemm_tma: dropout epilogue needs drop_ld %% 4 == 0");

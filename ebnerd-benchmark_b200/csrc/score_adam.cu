@@ -96,8 +96,9 @@ __global__ void score_sigmoid_kernel(long BC, int C, int D, const float* __restr
 // Keras-form Adam, 128-bit vectorised, grid-stride; pure HBM streaming (7 floats moved / param).
 __global__ void __launch_bounds__(256) adam_keras_kernel(float4* __restrict__ theta, float4* __restrict__ g,
                                                           float4* __restrict__ m, float4* __restrict__ v,
-                                                          size_t n4, float alpha, float omb1, float omb2,
-                                                          float eps, int zero_grad) {
+                                                          size_t n4, float alpha, const float* __restrict__ alpha_dev,
+                                                          float omb1, float omb2, float eps, int zero_grad) {
+  if (alpha_dev != nullptr) alpha = __ldg(alpha_dev);   // CUDA-graph replay: this step's alpha lives in device memory
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 th = theta[i], gg = g[i], mm = m[i], vv = v[i];
 #define UPD(c)                                  \
@@ -113,7 +114,9 @@ __global__ void __launch_bounds__(256) adam_keras_kernel(float4* __restrict__ th
   }
 }
 __global__ void adam_keras_tail_kernel(float* theta, float* g, float* m, float* v, size_t beg, size_t n,
-                                       float alpha, float omb1, float omb2, float eps, int zero_grad) {
+                                       float alpha, const float* alpha_dev, float omb1, float omb2, float eps,
+                                       int zero_grad) {
+  if (alpha_dev != nullptr) alpha = *alpha_dev;
   size_t i = beg + blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float gg = g[i];
@@ -175,7 +178,14 @@ extern "C" int ebk_score_sigmoid(int32_t B, int32_t C, int32_t D, const float* n
 
 extern "C" int ebk_adam_keras_step(float* theta, float* g, float* m, float* v, size_t n, float alpha,
                                    double beta1, double beta2, float eps, int zero_grad, void* stream) {
+  return ebk_adam_keras_step_p(theta, g, m, v, n, alpha, nullptr, beta1, beta2, eps, zero_grad, stream);
+}
+
+extern "C" int ebk_adam_keras_step_p(float* theta, float* g, float* m, float* v, size_t n, float alpha,
+                                     const ebk_step_params* step_dev, double beta1, double beta2, float eps,
+                                     int zero_grad, void* stream) {
   if (n == 0) return EBK_OK;
+  const float* alpha_dev = step_dev ? &step_dev->alpha : nullptr;
   EBK_CHECK_ARG(theta && g && m && v, "adam: null pointer");
   EBK_CHECK_ARG(((uintptr_t)theta % 16 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
                     ((uintptr_t)v % 16 == 0),
@@ -189,11 +199,11 @@ extern "C" int ebk_adam_keras_step(float* theta, float* g, float* m, float* v, s
     size_t cap = 148 * 16;
     adam_keras_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(
         reinterpret_cast<float4*>(theta), reinterpret_cast<float4*>(g), reinterpret_cast<float4*>(m),
-        reinterpret_cast<float4*>(v), n4, alpha, omb1, omb2, eps, zero_grad);
+        reinterpret_cast<float4*>(v), n4, alpha, alpha_dev, omb1, omb2, eps, zero_grad);
     EBK_LAUNCH_CHECK();
   }
   if (n4 * 4 < n) {
-    adam_keras_tail_kernel<<<1, 32, 0, st>>>(theta, g, m, v, n4 * 4, n, alpha, omb1, omb2, eps, zero_grad);
+    adam_keras_tail_kernel<<<1, 32, 0, st>>>(theta, g, m, v, n4 * 4, n, alpha, alpha_dev, omb1, omb2, eps, zero_grad);
     EBK_LAUNCH_CHECK();
   }
   if (prof_on()) prof_end(T_ADAM, st);

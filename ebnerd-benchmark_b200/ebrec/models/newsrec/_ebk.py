@@ -26,13 +26,14 @@ SYMBOLS = [
     "ebk_last_error", "ebk_version", "ebk_device_ok",
     "ebk_seqenc_workspace_bytes", "ebk_seqenc_fwd", "ebk_seqenc_bwd", "ebk_seqenc_fwd_opts", "ebk_seqenc_bwd_opts",
     "ebk_join_deferred", "ebk_seqenc_uses_tma", "ebk_ipc_export", "ebk_ipc_open",
-    "ebk_score_softmax_ce", "ebk_score_loss", "ebk_score_sigmoid", "ebk_adam_keras_step",
+    "ebk_score_softmax_ce", "ebk_score_loss", "ebk_score_sigmoid", "ebk_adam_keras_step", "ebk_adam_keras_step_p",
+    "ebk_embed_adam_step_p",
     "ebk_embed_adam_workspace_bytes", "ebk_embed_adam_step",
     "ebk_dense_workspace_bytes", "ebk_dense_fwd", "ebk_dense_bwd", "ebk_sumsq_accum",
     "ebk_attlayer_workspace_bytes", "ebk_attlayer_fwd", "ebk_attlayer_bwd",
     "ebk_conv1d_workspace_bytes", "ebk_conv1d_fwd", "ebk_conv1d_bwd",
     "ebk_catview_workspace_bytes", "ebk_catview_fwd", "ebk_catview_bwd",
-    "ebk_launch_count", "ebk_prof_enable", "ebk_prof_num_tags", "ebk_prof_tag_name", "ebk_prof_collect",
+    "ebk_launch_count", "ebk_prof_enable", "ebk_prof_is_enabled", "ebk_prof_num_tags", "ebk_prof_tag_name", "ebk_prof_collect",
     "ebk_gemm", "ebk_gemm_tma", "ebk_attention_core_fwd", "ebk_attention_core_bwd", "ebk_dropout_mask",
 ]
 
@@ -53,7 +54,7 @@ class SeqEncDesc(C.Structure):
 class SeqEncOpts(C.Structure):
     """Mirror of ebk_seqenc_opts (include/ebk.h): per-call options, nothing sticky."""
     _fields_ = [("defer_wgrad", C.c_int32), ("table_grad_event", C.c_void_p), ("peer_tables", C.POINTER(C.c_void_p)),
-                ("peer_world", C.c_int32), ("peer_shard_floats", C.c_size_t)]
+                ("peer_world", C.c_int32), ("peer_shard_floats", C.c_size_t), ("step_dev", C.c_void_p)]
 
 
 class DenseDesc(C.Structure):
@@ -132,6 +133,8 @@ def lib() -> C.CDLL:
     l.ebk_score_loss.argtypes = [i32, i32, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp]
     l.ebk_score_sigmoid.argtypes = [i32, i32, i32, vp, vp, vp, vp]
     l.ebk_adam_keras_step.argtypes = [vp, vp, vp, vp, sz, f32, f64, f64, f32, C.c_int, vp]
+    l.ebk_adam_keras_step_p.argtypes = [vp, vp, vp, vp, sz, f32, vp, f64, f64, f32, C.c_int, vp]
+    l.ebk_embed_adam_step_p.argtypes = [i32, i32, i32, vp, vp, f32, u64, vp, vp, vp, vp, f32, vp, f64, f64, f32, vp, sz, vp]
     l.ebk_embed_adam_workspace_bytes.restype = sz
     l.ebk_embed_adam_workspace_bytes.argtypes = [i32, i32]
     l.ebk_embed_adam_step.argtypes = [i32, i32, i32, vp, vp, f32, u64, vp, vp, vp, vp, f32, f64, f64, f32, vp, sz, vp]

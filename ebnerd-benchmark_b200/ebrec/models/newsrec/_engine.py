@@ -181,8 +181,9 @@ class NRMSEngine:
         return cur[:n].view(*shape)
 
     # ------------------------------------------------------------------ forward pieces
-    def _encode(self, tok_all: torch.Tensor, B: int, Hh: int, training: bool, seeds=(0, 0)):
-        """tok_all [B*Hh + B*C, T] int32 -> (n_all [N, D], u [B, D]); keeps descs/workspaces for backward."""
+    def _encode(self, tok_all: torch.Tensor, B: int, Hh: int, training: bool, seeds=(0, 0), step_dev=None):
+        """tok_all [B*Hh + B*C, T] int32 -> (n_all [N, D], u [B, D]); keeps descs/workspaces for backward.
+        step_dev: device tensor holding an ebk_step_params (CUDA-graph replay: seeds are read from it)."""
         lib, P = _ebk.lib(), self.params
         N = tok_all.shape[0]
         if Hh != self.H:
@@ -190,6 +191,9 @@ class NRMSEngine:
         opts = None
         if training:
             opts = self._peer_opts()     # rank-sharded table: gather rows from their owners over NVLink
+            if step_dev is not None:
+                opts = opts if opts is not None else _ebk.SeqEncOpts(0, None, None, 0, 0, None)
+                opts.step_dev = C.c_void_p(step_dev.data_ptr())
         else:
             self._sync_table()
         dn = self._desc("news", N, training)
@@ -239,8 +243,8 @@ class NRMSEngine:
         return out
 
     # ------------------------------------------------------------------ public steps (device tensors)
-    def forward_logits_parts(self, tok_all, B, C_, training=False, seeds=(0, 0)):
-        n_all, u, ctx = self._encode(tok_all, B, self.H, training, seeds)
+    def forward_logits_parts(self, tok_all, B, C_, training=False, seeds=(0, 0), step_dev=None):
+        n_all, u, ctx = self._encode(tok_all, B, self.H, training, seeds, step_dev)
         news_c = n_all[B * self.H:].view(B, C_, self.D)
         return n_all, news_c, u, ctx
 
@@ -366,7 +370,7 @@ class NRMSEngine:
         return _mix(base, 1), _mix(base, 2)
 
     def loss_and_grads_dev(self, tok_all, labels, B, C_, training=True, seeds=None, sparse_table=False,
-                           defer_wgrad=False):
+                           defer_wgrad=False, step_dev=None):
         """Forward + backward; gradients ACCUMULATE into params.grad.  Returns (loss_sum, probs).
         sparse_table: leave the table gradient as per-row gradients in the "dx" buffer (for apply_adam(sparse=...))
         instead of scatter-adding it into params.grad.
@@ -374,7 +378,7 @@ class NRMSEngine:
         it with ebk_join_deferred (apply_adam(sparse=...) does)."""
         lib, P = _ebk.lib(), self.params
         seeds = self.step_seeds() if seeds is None else seeds
-        n_all, news_c, u, (dn, wn, du, wu) = self.forward_logits_parts(tok_all, B, C_, training, seeds)
+        n_all, news_c, u, (dn, wn, du, wu) = self.forward_logits_parts(tok_all, B, C_, training, seeds, step_dev)
         N = n_all.shape[0]
         probs = self._buf("probs", (B, C_))
         loss = self._buf("loss", (1,))
@@ -392,7 +396,8 @@ class NRMSEngine:
                                       _ebk.ptr(d_user), _ebk.ptr(P.g("user_Wqkv")), _ebk.ptr(P.g("user_attW")),
                                       _ebk.ptr(P.g("user_attb")), _ebk.ptr(P.g("user_attq")), None,
                                       _ebk.ptr(dn_all), _ebk.stream()))
-        opts = _ebk.SeqEncOpts(1 if defer_wgrad else 0, None, None, 0, 0)
+        opts = _ebk.SeqEncOpts(1 if defer_wgrad else 0, None, None, 0, 0,
+                               C.c_void_p(step_dev.data_ptr()) if step_dev is not None else None)
         if self.world > 1:
             # the table gradient is final after the scatter inside this call: apply_adam starts its
             # reduce-scatter from that point, overlapping the weight-gradient GEMM that follows
@@ -411,7 +416,7 @@ class NRMSEngine:
                                            _ebk.stream()))
         return loss, probs
 
-    def apply_adam(self, sparse=None) -> None:
+    def apply_adam(self, sparse=None, step_dev=None) -> None:
         """One Keras-form Adam iteration over the whole flat buffer (clears grad in the same pass).
 
         sparse = (tok_all, dropout seed of the embedded tokens): the table rows are updated by
@@ -423,9 +428,27 @@ class NRMSEngine:
         theta/m/v only (the 5.4 GB/step optimizer traffic is divided by world instead of replicated), and an
         in-place all-gather republishes theta.  Wire volume equals one all-reduce."""
         P = self.params
+        lib = _ebk.lib()
+        if sparse is not None and step_dev is not None:
+            # CUDA-graph capture / replay: seeds and alpha come from the device-resident ebk_step_params; the
+            # optimizer iteration count is advanced by the caller once per replay
+            tok_all, _ = sparse
+            R = tok_all.numel()
+            sp = C.c_void_p(step_dev.data_ptr())
+            need = lib.ebk_embed_adam_workspace_bytes(R, self.V)
+            ws = self._buf("embed_adam_ws", (need,), dtype=torch.uint8)
+            _ebk.check(lib.ebk_embed_adam_step_p(R, self.E, self.V, _ebk.ptr(tok_all), _ebk.ptr(self._buf("dx", (R, self.E))),
+                                                 self.dropout, 0, _ebk.ptr(P.theta), _ebk.ptr(P.grad), _ebk.ptr(P.m),
+                                                 _ebk.ptr(P.v), 0.0, sp, self.beta1, self.beta2, self.eps, _ebk.ptr(ws),
+                                                 ws.numel(), _ebk.stream()))
+            _ebk.check(lib.ebk_join_deferred(_ebk.stream()))
+            lo = P.offsets["news_Wqkv"]
+            th, g, m, v = P.theta[lo:], P.grad[lo:], P.m[lo:], P.v[lo:]
+            _ebk.check(lib.ebk_adam_keras_step_p(_ebk.ptr(th), _ebk.ptr(g), _ebk.ptr(m), _ebk.ptr(v), P.n - lo, 0.0, sp,
+                                                 self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
+            return
         self.step_count += 1
         alpha = keras_adam_alpha(self.lr, self.step_count, self.beta1, self.beta2)
-        lib = _ebk.lib()
         if sparse is not None:
             tok_all, seed1 = sparse
             R = tok_all.numel()
@@ -580,13 +603,13 @@ class NRMSEngine:
         forced = getattr(self, "_force_peer_opts", None)     # tests: exercise the peer gather on one GPU
         if forced is not None:
             ptrs, world, shard = forced
-            return _ebk.SeqEncOpts(0, None, ptrs, world, shard)
+            return _ebk.SeqEncOpts(0, None, ptrs, world, shard, None)
         if self.world <= 1 or not getattr(self, "_table_stale", False):
             return None
         pt = self._peer_tables(self.params.offsets.get("news_Wqkv", 0))
         if pt is None:
             return None
-        return _ebk.SeqEncOpts(0, None, pt["ptrs"], self.world, pt["shard"])
+        return _ebk.SeqEncOpts(0, None, pt["ptrs"], self.world, pt["shard"], None)
 
     def _sync_table(self) -> None:
         """Make this rank's replica of the table current (all-gather of the owners' shards); needed before any
@@ -630,7 +653,8 @@ class NRMSEngine:
     def train_step_dev(self, tok_all, labels, B, C_):
         """One optimizer iteration.  Single GPU: the Embedding's row-sparse gradient never becomes a dense
         [V, E] buffer -- the backward leaves the per-row gradients dX and ebk_embed_adam_step sums them per
-        token inside the table's (dense, Keras-form) Adam pass.  Data parallel: dense gradient buffer +
+        token inside the table's (dense, Keras-form) Adam pass; the whole step (about 45 launches) is captured in
+        a CUDA graph per batch shape and replayed (see _graph_step).  Data parallel: dense gradient buffer +
         reduce-scatter (see apply_adam)."""
         # (subclasses with other graphs -- DocVec, NAML -- keep the dense path: they never set the flag)
         sparse = getattr(self, "sparse_table_grad", False) and self.world == 1 and self.E <= 1024
@@ -638,16 +662,112 @@ class NRMSEngine:
             loss, probs = self.loss_and_grads_dev(tok_all, labels, B, C_, training=True)
             self.apply_adam()
             return loss, probs
+        if self._graph_ok():
+            return self._graph_step(tok_all, labels, B, C_)
+        return self._eager_sparse_step(tok_all, labels, B, C_)
+
+    def _eager_sparse_step(self, tok_all, labels, B, C_, step_dev=None):
         seeds = self.step_seeds()
         # the QKV weight-gradient GEMM (tensor bound) overlaps the table's Adam pass (HBM bound): see ebk.h
         defer = os.environ.get("EBK_DEFER_WGRAD", "1") != "0"
-        loss, probs = self.loss_and_grads_dev(tok_all, labels, B, C_, training=True, seeds=seeds, sparse_table=sparse,
-                                              defer_wgrad=defer)
-        self.apply_adam(sparse=(tok_all, seeds[0]) if sparse else None)
+        loss, probs = self.loss_and_grads_dev(tok_all, labels, B, C_, training=True, seeds=seeds, sparse_table=True,
+                                              defer_wgrad=defer, step_dev=step_dev)
+        self.apply_adam(sparse=(tok_all, seeds[0]), step_dev=step_dev)
         return loss, probs
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the training step
+    def _graph_ok(self) -> bool:
+        """Graph replay is used on one GPU, on the all-TMA path, unless EBK_NO_GRAPH=1 or the library profiler
+        (per-kernel CUDA events) is recording."""
+        if os.environ.get("EBK_NO_GRAPH", "0") == "1" or type(self) is not NRMSEngine:
+            return False
+        if _ebk.lib().ebk_prof_is_enabled():
+            return False
+        ok = self.__dict__.get("_graph_path_ok")
+        if ok is None:
+            ok = bool(_ebk.lib().ebk_seqenc_uses_tma(C.byref(self._desc("news", 1, True))))
+            self._graph_path_ok = ok
+        return ok
+
+    def _graph_key(self, B, C_, tok_shape):
+        # everything a captured launch bakes in as a kernel ARGUMENT (lr, step count and seeds are not: ebk_step_params)
+        return (int(B), int(C_), tuple(int(d) for d in tok_shape), self.eps, self.dropout, self.beta1, self.beta2,
+                int(self.loss_kind), os.environ.get("EBK_DEFER_WGRAD", "1"))
+
+    def _write_step_params(self, st: dict) -> None:
+        """seed1 | seed2 | alpha of THIS step -> the graph's device-resident ebk_step_params (one 24-byte copy
+        from a pinned ring, ordered on the stream before the replay)."""
+        s1, s2 = self.step_seeds()
+        alpha = keras_adam_alpha(self.lr, self.step_count + 1, self.beta1, self.beta2)
+        raw = np.zeros(3, dtype=np.uint64)
+        raw[0], raw[1] = s1, s2
+        raw[2:].view(np.float32)[0] = alpha
+        self._h2d("step_params", raw.view(np.int64), out=st["step"])
+
+    def _graph_step(self, tok_all, labels, B, C_):
+        """Replay the captured train step on (tok_all, labels): inputs are copied into the graph's static buffers,
+        the per-step scalars (dropout seeds, Adam alpha) into its ebk_step_params.  First call per (B, C): one
+        eager step (allocates every workspace and warms the tensor-map cache), then capture."""
+        graphs = self.__dict__.setdefault("_graphs", {})
+        key = self._graph_key(B, C_, tok_all.shape)
+        st = graphs.get(key)
+        if st is None:
+            st = {"tok": torch.empty_like(tok_all), "lab": torch.empty_like(labels),
+                  "step": torch.zeros(3, dtype=torch.int64, device=self.device), "graph": None, "warm": 0}
+            graphs[key] = st
+        if st["graph"] is None:
+            if st["warm"] < 1:           # eager warm-up step(s) with the same shapes
+                st["warm"] += 1
+                return self._eager_sparse_step(tok_all, labels, B, C_)
+            st["tok"].copy_(tok_all)
+            st["lab"].copy_(labels)
+            self._write_step_params(st)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = _ebk.lib().ebk_launch_count()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                loss, probs = self.loss_and_grads_dev(st["tok"], st["lab"], B, C_, training=True, seeds=(0, 0),
+                                                      sparse_table=True,
+                                                      defer_wgrad=os.environ.get("EBK_DEFER_WGRAD", "1") != "0",
+                                                      step_dev=st["step"])
+                self.apply_adam(sparse=(st["tok"], 0), step_dev=st["step"])
+            st["graph"], st["loss"], st["probs"] = g, loss, probs
+            st["launches"] = int(_ebk.lib().ebk_launch_count() - l0)     # kernels of ours inside one replay
+            # (capture does not execute: the replay below runs this step)
+        else:
+            if tok_all.data_ptr() != st["tok"].data_ptr():
+                st["tok"].copy_(tok_all, non_blocking=True)
+            if labels.data_ptr() != st["lab"].data_ptr():
+                st["lab"].copy_(labels, non_blocking=True)
+            self._write_step_params(st)
+        st["graph"].replay()
+        self.step_count += 1
+        self.graph_steps = getattr(self, "graph_steps", 0) + 1
+        self.graph_launches = getattr(self, "graph_launches", 0) + st["launches"]
+        return st["loss"], st["probs"]
+
+    def launch_count(self) -> int:
+        """Kernels of libebk launched so far for this process: direct launches + those inside graph replays."""
+        return int(_ebk.lib().ebk_launch_count()) + int(getattr(self, "graph_launches", 0))
+
+    def train_step_host(self, his: np.ndarray, pred: np.ndarray, y: np.ndarray):
+        """train_on_batch / fit entry with HOST arrays: when the step is graph-replayed the pinned staging buffers
+        are copied straight into the graph's static inputs (no intermediate device tensors)."""
+        his, pred = np.asarray(his), np.asarray(pred)
+        B, C_ = pred.shape[0], pred.shape[1]
+        sparse = getattr(self, "sparse_table_grad", False) and self.world == 1 and self.E <= 1024
+        if sparse and his.ndim == 3 and self._graph_ok():
+            N = B * (his.shape[1] + C_)
+            st = self.__dict__.get("_graphs", {}).get(self._graph_key(B, C_, (N, self.T)))
+            if st is not None and st["graph"] is not None:
+                self._h2d("tok", self.pack_tokens(his, pred), out=st["tok"])
+                self._h2d("lab", np.ascontiguousarray(y, dtype=np.float32), out=st["lab"])
+                return self._graph_step(st["tok"], st["lab"], B, C_)
+        tok, lab = self.to_device_batch(his, pred, y)
+        return self.train_step_dev(tok, lab, B, C_)
+
     # ------------------------------------------------------------------ host-array convenience
-    def _h2d(self, key: str, arr: np.ndarray) -> torch.Tensor:
+    def _h2d(self, key: str, arr: np.ndarray, out: torch.Tensor | None = None) -> torch.Tensor:
         """Host array -> device through a small ring of PINNED staging buffers (asynchronous copy: the host goes on
         launching kernels while the DMA runs).  A slot is reused only after the copy that last read it finished.
         The ring is keyed by (key, dtype) and sized by CAPACITY (grown geometrically), so eval-mode loaders whose
@@ -668,7 +788,11 @@ class NRMSEngine:
             slot[0] = torch.empty(cap, dtype=torch.from_numpy(arr).dtype).pin_memory()
         stage = slot[0][:n].view(arr.shape)
         stage.numpy()[...] = arr
-        dev = stage.to(self.device, non_blocking=True)
+        if out is not None:      # straight into a static device buffer (CUDA-graph inputs)
+            out.view(arr.shape).copy_(stage, non_blocking=True)
+            dev = out
+        else:
+            dev = stage.to(self.device, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         slot[1] = ev

@@ -38,6 +38,10 @@ class _NRMSTrainModel(KerasLikeModel):
         return tok, lab, B, C_
 
     def _train_batch(self, inputs, y):
+        his, pred = (np.asarray(a) for a in inputs)
+        if his.ndim == 3 and pred.ndim == 3 and hasattr(self._engine, "train_step_host"):
+            loss, probs = self._engine.train_step_host(his, pred, y)   # graph-replayed step: H2D into its static inputs
+            return loss, probs, pred.shape[0]
         tok, lab, B, C_ = self._pack(inputs, y)
         loss, probs = self._engine.train_step_dev(tok, lab, B, C_)
         return loss, probs, B

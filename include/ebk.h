@@ -118,12 +118,23 @@ int ebk_seqenc_bwd(const ebk_seqenc_desc* d, const int32_t* tok, const float* ta
  *                     into the Embedding gather (nrms.py:125-134) over NVLink.  Only the all-TMA path
  *                     (ebk_seqenc_uses_tma(desc) == 1) gathers through peers; any other path returns
  *                     EBK_ERR_INVALID rather than read a stale local shard. */
+/* Per-step scalars kept in DEVICE memory so that a training step captured in a CUDA graph can be replayed with new
+ * values: the host writes the struct (one 24-byte copy) before every replay instead of passing seeds / alpha as
+ * kernel arguments.  seed1 / seed2: the two Dropout seeds of ebk_seqenc_*; alpha: Adam's
+ * lr*sqrt(1-b2^t)/(1-b1^t) of ebk_adam_keras_step_p / ebk_embed_adam_step_p (whose dropout seed is seed1). */
+typedef struct {
+  uint64_t seed1, seed2;
+  float alpha;
+  float reserved;
+} ebk_step_params;
+
 typedef struct {
   int32_t defer_wgrad;
   void* table_grad_event;
   const void* const* peer_tables;
   int32_t peer_world;
   size_t peer_shard_floats;
+  const ebk_step_params* step_dev; /* DEVICE pointer or NULL: when set, seed1 / seed2 come from it, not from the arguments */
 } ebk_seqenc_opts;
 
 int ebk_seqenc_fwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_opts* opts, const int32_t* tok,
@@ -285,6 +296,10 @@ int ebk_score_sigmoid(int32_t B, int32_t C, int32_t D, const float* news, const 
  * ---------------------------------------------------------------------------------- */
 int ebk_adam_keras_step(float* theta, float* g, float* m, float* v, size_t n, float alpha,
                         double beta1, double beta2, float eps, int zero_grad, void* stream);
+/* the same with alpha read from step_dev->alpha (device memory) when step_dev != NULL */
+int ebk_adam_keras_step_p(float* theta, float* g, float* m, float* v, size_t n, float alpha,
+                          const ebk_step_params* step_dev, double beta1, double beta2, float eps, int zero_grad,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Embedding table: IndexedSlices gradient + the same Keras-form Adam, fused (single-GPU training path).
@@ -298,6 +313,11 @@ int ebk_adam_keras_step(float* theta, float* g, float* m, float* v, size_t n, fl
  *   more than 32 times are pre-reduced into it).  E % 4 == 0, E <= 1024.
  * ---------------------------------------------------------------------------------- */
 size_t ebk_embed_adam_workspace_bytes(int32_t R, int32_t V);
+/* ebk_embed_adam_step with drop_seed / alpha read from step_dev->seed1 / ->alpha (device memory) when step_dev != NULL */
+int ebk_embed_adam_step_p(int32_t R, int32_t E, int32_t V, const int32_t* tok, const float* dX, float drop_p,
+                          uint64_t drop_seed, float* theta, float* d_table, float* m, float* v, float alpha,
+                          const ebk_step_params* step_dev, double beta1, double beta2, float eps, void* workspace,
+                          size_t workspace_bytes, void* stream);
 int ebk_embed_adam_step(int32_t R, int32_t E, int32_t V, const int32_t* tok, const float* dX, float drop_p,
                         uint64_t drop_seed, float* theta, float* d_table, float* m, float* v, float alpha,
                         double beta1, double beta2, float eps, void* workspace, size_t workspace_bytes, void* stream);
@@ -311,6 +331,7 @@ int ebk_embed_adam_step(int32_t R, int32_t E, int32_t V, const int32_t* tok, con
  * ---------------------------------------------------------------------------------- */
 long long ebk_launch_count(void);
 int ebk_prof_enable(int on);
+int ebk_prof_is_enabled(void);
 int ebk_prof_num_tags(void);
 const char* ebk_prof_tag_name(int slot);
 int ebk_prof_collect(double* ms_out, long long* count_out);

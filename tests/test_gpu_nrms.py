@@ -12,7 +12,10 @@ from oracle import nrms_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-FWD_TOL = {0: 1e-4, 1: 1e-3}
+FWD_TOL = {0: 1e-4, 1: 1e-3}      # inference arithmetic (fp32 / 3xTF32): the north-star click-score gate
+# training arithmetic (fp32 / single-pass TF32 on the TMA path): measured logit error 1.4e-3 ... 4.3e-3 of max|logit|
+# (tests/test_gpu_reference_golden.py::test_nrms_training_kernels_forward_error_measured); its gate is AUC parity
+TRAIN_TOL = {0: 1e-4, 1: 6e-3}
 BWD_TOL = {0: 2e-4, 1: 2e-2}
 
 
@@ -105,17 +108,17 @@ def test_loss_and_gradients(math, dropout, case):
     V, E, nh, dh, att, B, H, C, T = case
     rng = np.random.default_rng(sum(case) + 1)
     P, his, pred, y = make_case(rng, V, E, nh, dh, att, B, H, C, T, wv=CASE_WV[V])
-    zw = O.nrms_forward(his, pred, P, nh, dh)[0]
+    s1, s2 = 1234567, 7654321
+    zw = O.nrms_forward(his, pred, P, nh, dh, training=True, p_drop=dropout, seed1=s1, seed2=s2)[0]
     assert np.ptp(zw, axis=1).min() >= 1.0   # loss / probs carry signal
     zmax = max(1.0, float(np.abs(zw).max()))  # a relative logit error eps moves loss and probabilities by ~eps * max|z|
     eng = make_engine(P, V, E, T, H, nh, dh, att, dropout, 1e-4, math)
     tok, lab = eng.to_device_batch(his, pred, y)
-    s1, s2 = 1234567, 7654321
     eng.params.grad.zero_()
     loss, probs = eng.loss_and_grads_dev(tok, lab, B, C, training=True, seeds=(s1, s2))
     wl, wp, G = O.nrms_loss_and_grads(his, pred, y, P, nh, dh, training=True, p_drop=dropout, seed1=s1, seed2=s2)
-    assert abs(float(loss) - wl) < FWD_TOL[math] * zmax, (float(loss), wl)
-    assert rel(probs.cpu().numpy(), wp) < FWD_TOL[math] * 3 * zmax
+    assert abs(float(loss) - wl) < TRAIN_TOL[math] * zmax, (float(loss), wl)
+    assert rel(probs.cpu().numpy(), wp) < TRAIN_TOL[math] * 3 * zmax
     D = nh * dh
     got = {
         "table": eng.params.g("table").cpu().numpy(),
@@ -140,14 +143,14 @@ def test_loss_and_gradients(math, dropout, case):
     for k in O.NRMS_PARAM_ORDER:
         err = np.abs(got[k] - G[k]).max()
         noise = np.abs(G32[k].astype(np.float64) - G[k]).max()
-        allowed = BWD_TOL[math] * np.abs(G[k]).max() + 20.0 * amp * noise
+        allowed = BWD_TOL[math] * (zmax if math == 1 else 1.0) * np.abs(G[k]).max() + 20.0 * amp * noise
         report[k] = (err / (np.abs(G[k]).max() + 1e-30), err / allowed)
     print("gradient (rel err, err/allowed):", {k: (f"{a:.1e}", f"{b:.2f}") for k, (a, b) in report.items()})
     for k, (_, ratio) in report.items():
         assert ratio < 1.0, (k, report)
     # the well-conditioned gradients must be tight without the noise allowance
     for k in ("table", "news_WV", "user_WV"):
-        assert report[k][0] < BWD_TOL[math], (k, report)
+        assert report[k][0] < BWD_TOL[math] * (zmax if math == 1 else 1.0), (k, report)
 
 
 @pytest.mark.parametrize("math", [0, 1])
@@ -219,6 +222,38 @@ def test_fused_embedding_adam_matches_dense_path(V):
     for e in engs:
         assert float(e.params.grad.abs().max()) == 0.0
         assert float((e.params.m != 0).float().sum()) > 0
+
+
+def test_graph_replay_matches_eager_steps(monkeypatch):
+    """The single-GPU train step is captured in a CUDA graph (dropout seeds and Adam's alpha come from a
+    device-resident ebk_step_params written before every replay): 5 steps with a new batch, new masks and a new
+    alpha each -- eager warm-up, capture + replay, replays -- must follow the eager engine (EBK_NO_GRAPH=1)."""
+    V, E, nh, dh, att, B, H, C, T = 3000, 64, 4, 8, 24, 16, 10, 5, 12
+    rng = np.random.default_rng(5)
+    P, _, _, y = make_case(rng, V, E, nh, dh, att, B, H, C, T)
+    batches = [(rng.integers(0, V, (B, H, T)).astype(np.int32), rng.integers(0, V, (B, C, T)).astype(np.int32)) for _ in range(5)]
+    results = {}
+    for mode in ("graph", "eager"):
+        if mode == "eager":
+            monkeypatch.setenv("EBK_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("EBK_NO_GRAPH", raising=False)
+        eng = make_engine(P, V, E, T, H, nh, dh, att, 0.2, 1e-3, 1, seed=9)
+        eng.eps = 1e-3    # see test_fused_embedding_adam_matches_dense_path: keeps atomics-order noise un-amplified
+        losses = []
+        for i, (his, pred) in enumerate(batches):
+            if i == 3:
+                eng.lr = 5e-4                                   # ReduceLROnPlateau between steps: alpha is not baked in
+            loss, _ = eng.train_step_host(his, pred, y) if i % 2 else eng.train_step_dev(*eng.to_device_batch(his, pred, y), B, C)
+            losses.append(float(loss))
+        results[mode] = (losses, eng.get_weights(), getattr(eng, "graph_steps", 0), eng.step_count)
+    (lg, wg, ng, tg), (le, we, ne, te) = results["graph"], results["eager"]
+    assert ng == 4 and ne == 0 and tg == te == 5                # step 0 eager (warm-up), steps 1-4 replayed
+    assert np.allclose(lg, le, rtol=0, atol=5e-5 * max(1.0, max(abs(x) for x in le)))
+    for k, a, b in zip(O.NRMS_PARAM_ORDER, wg, we):
+        diff = np.abs(a - b)
+        assert diff.mean() < 2e-7, (k, diff.mean())
+        assert (diff > 1e-5).mean() < 1e-3, (k, (diff > 1e-5).mean())
 
 
 def test_scorer_dedup_matches_plain_predict():

