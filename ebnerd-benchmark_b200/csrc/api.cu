@@ -113,6 +113,7 @@ struct SeqWs {
   // TMA path (EBK_MATH_TF32): dense tf32-rounded operands
   float *xd;                           //   dropout(gather(table, tok)) or the dense input, [R, Din]
   float *wqkv_r, *attw_r;              //   rounded copies of the weights
+  float *wqkv_p;                       //   head-major permuted + rounded Wqkv (fused projection + attention forward)
   float *colpart, *colsum2;            //   per-sequence column-sum partials [n_seq, 2 att] and their reduction scratch
   size_t bytes;
 };
@@ -128,7 +129,13 @@ SeqWs seq_layout(const ebk_seqenc_desc& d0, void* base) {
     return p;
   };
   SeqWs w;
-  w.qkv = take(R * 3 * D);
+  // Q|K|V of the forward: [R, 3D] rows, or the zero-padded per-(sequence, head) tiles of the fused forward
+  size_t qkv_floats = R * 3 * D;
+  if (d.dh == 16 || d.dh == 20 || d.dh == 24 || d.dh == 32) {
+    const size_t tiled = qkv_tiles_floats(d.n_seq, d.nh, d.dh);
+    if (tiled > qkv_floats) qkv_floats = tiled;
+  }
+  w.qkv = take(qkv_floats);
   w.y0 = take(R * D);
   w.hbuf = take(R * d.att);
   w.w = take(R);
@@ -148,10 +155,21 @@ SeqWs seq_layout(const ebk_seqenc_desc& d0, void* base) {
   w.xd = take(R * (size_t)d.Din + 64);  // + 64: TMA boxes of the last row may touch (zero-filled) columns past it
   w.wqkv_r = take((size_t)d.Din * 3 * D + 64);
   w.attw_r = take(D * (size_t)d.att + 64);
+  w.wqkv_p = take((size_t)d.Din * 3 * D + 64);
   w.colpart = take((size_t)d.n_seq * 2 * d.att);
   w.colsum2 = take(colsum_partial_floats(d.n_seq, 2 * d.att));
   w.bytes = off;
   return w;
+}
+
+// Fused SelfAttention forward (QKV projection with the attention in its epilogue): the forward and the backward of a
+// call decide it from the same descriptor + workspace, because it fixes the layout of the saved Q|K|V.
+bool fused_attn(const ebk_seqenc_desc& d, const SeqWs& ws) {
+  // (read per call: tests and experiments flip these between calls)
+  const char* e1 = getenv("EBK_FUSED_ATTN");
+  const char* e2 = getenv("EBK_DP_CHUNKED_GATHER");
+  const bool on = !(e1 && atoi(e1) == 0) && !(e2 && atoi(e2) != 0);
+  return on && qkv_attn_fused_supported(d.L, d.dh, d.Din, ws.xd, ws.wqkv_p, ws.y0);
 }
 
 // The all-TMA GEMM path: tf32 tensor-core math, every row stride a multiple of 16 bytes.
@@ -343,6 +361,18 @@ extern "C" int ebk_seqenc_fwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
         EBK_PROF(T_QKV_FWD, gemm_tma(ws.xd + (size_t)r0 * d->Din, d->Din, false, ws.wqkv_r, 3 * D, false,
                                      ws.qkv + (size_t)r0 * 3 * D, 3 * D, rows, 3 * D, d->Din, 0.0f, 1.0f, st, -1, &round_epi));
       }
+    } else if (fused_attn(*d, ws)) {
+      // ---- north-star kernel: gather -> [QKV projection + per-head softmax(QK^T/sqrt(dh))^T V in ONE tcgen05 kernel]:
+      // the accumulator tile is whole sequences x whole heads (weights permuted head-major), the attention runs in the
+      // GEMM epilogue from TMEM through shared memory, Q|K|V reach HBM only as the tiles the backward needs
+      EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st,
+                                          remote ? &peers : nullptr));
+      EBK_TRY(permute_round_wqkv(ws.wqkv_p, Wqkv, d->Din, d->nh, d->dh, st));
+      float* y0f = pool ? ws.y0 : out;
+      EBK_PROF(T_QKV_FWD, qkv_attn_fused(ws.xd, d->Din, ws.wqkv_p, d->n_seq, d->L, d->nh, d->dh, ws.qkv, y0f,
+                                         pool ? drop2 : none, st));
+      if (!pool) return EBK_OK;
+      goto attlayer;
     } else {
       EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st,
                                           remote ? &peers : nullptr));
@@ -350,6 +380,7 @@ extern "C" int ebk_seqenc_fwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
       EBK_PROF(T_QKV_FWD, gemm_tma(ws.xd, d->Din, false, ws.wqkv_r, 3 * D, false, ws.qkv, 3 * D, R, 3 * D, d->Din, 0.0f,
                                    1.0f, st, -1, &round_epi));
     }
+    {
     // (2) attention core; its output is stored as tf32(dropout2(Y0)) -- the only form AttLayer2 reads
     float* y0 = pool ? ws.y0 : out;
     const Dropout dropy = pool ? drop2 : none;
@@ -362,7 +393,9 @@ extern "C" int ebk_seqenc_fwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
       EBK_PROF(T_ATTN_FWD, attention_core_fwd(d->n_seq, d->L, d->nh, d->dh, ws.qkv, y0, st));
       if (pool) EBK_TRY(round_tf32_copy(y0, y0, (size_t)R * D, st));
     }
+    }
     if (!pool) return EBK_OK;
+  attlayer:
     // (3) pre-activation of AttLayer2                                nrms.py:153-156, layers.py:65
     EBK_PROF(T_ATT_GEMM_FWD, gemm_tma(ws.y0, D, false, ws.attw_r, d->att, false, ws.hbuf, d->att, R, d->att, D, 0.0f,
                                       1.0f, st, -1));
@@ -472,7 +505,8 @@ extern "C" int ebk_seqenc_bwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
     }
     // SelfAttention core backward
     if (attention_pre_supported(d->L, d->dh, ws.qkv, ws.dy, ws.dqkv)) {
-      EBK_PROF(T_ATTN_BWD, attention_core_bwd_pre(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, ws.dqkv, st));
+      const bool tiled = fused_attn(*d, ws);   // the fused forward saved Q|K|V as per-(sequence, head) tiles
+      EBK_PROF(T_ATTN_BWD, attention_core_bwd_pre(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, ws.dqkv, st, tiled));
     } else if (attention_mma_supported(d->L, d->dh, ws.qkv, ws.dy, ws.dqkv)) {
       EBK_PROF(T_ATTN_BWD, attention_core_bwd_mma(d->n_seq, d->L, d->nh, d->dh, ws.qkv, ws.dy, none, ws.dqkv, true, st));
     } else {

@@ -16,228 +16,13 @@
 #include <stdlib.h>
 
 #include "ebk_common.cuh"
+#include "attention_tiles.cuh"
 
 namespace ebk {
 namespace {
 
 constexpr int WARPS = 4;
-constexpr int LP = 32;   // padded sequence length
-constexpr int PS = 40;   // stride of the 32x32 score-shaped tile
-
-template <int DH> struct Cfg {
-  static constexpr int ST = (DH == 20) ? 20 : DH + 4;
-  static constexpr int KF = DH / 8;            // full k-steps over the head dim
-  static constexpr bool KH = (DH % 8) != 0;    // plus one half k-step (4 columns)
-  static constexpr int NT = (DH + 7) / 8;      // n-tiles over the head dim
-  static constexpr int MAT = LP * ST;          // floats per staged matrix
-};
-
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-__device__ __forceinline__ uint32_t u(float x) { return __float_as_uint(x); }
-__device__ __forceinline__ uint32_t ur(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }  // tf32 round
-// 16-byte async copy; bytes == 0 writes zeros (the source is not read)
-__device__ __forceinline__ void cp16(float* dst, const float* src, uint32_t bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// issue the cp.async copies of NM [L, DH] slices (global row strides ld[m]) into dst + m * MAT; every
-// 16-byte chunk of the [32][ST] tiles is written (rows >= L and columns >= DH with zeros)
-template <int DH, int NM>
-__device__ __forceinline__ void stage_async(float* dst, const float* const (&src)[NM], const long (&ld)[NM], int L, int lane) {
-  constexpr int ST = Cfg<DH>::ST, CPR = ST / 4, MAT = Cfg<DH>::MAT;
-#pragma unroll
-  for (int it = 0; it < LP * CPR / 32; ++it) {
-    const int i = lane + it * 32;
-    const int t = i / CPR, j = i - t * CPR;
-    const bool ok = t < L && j * 4 < DH;
-#pragma unroll
-    for (int m = 0; m < NM; ++m)
-      cp16(dst + m * MAT + t * ST + j * 4, ok ? src[m] + (long)t * ld[m] + j * 4 : src[m], ok ? 16u : 0u);
-  }
-}
-
-// acc (32x32 fragments) = X Y^T over the head dim; X, Y staged row-major with stride ST
-template <int DH>
-__device__ __forceinline__ void gemm_xyT(float (&acc)[2][4][4], const float* X, const float* Y, int g, int t) {
-  constexpr int ST = Cfg<DH>::ST;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.0f;
-#pragma unroll
-  for (int ks = 0; ks < Cfg<DH>::KF + (Cfg<DH>::KH ? 1 : 0); ++ks) {
-    const bool half = ks >= Cfg<DH>::KF;  // compile-time after unrolling: only columns ks*8 .. ks*8+3 exist
-    uint32_t a[2][4], b[4][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const float* p = X + (mt * 16 + g) * ST + ks * 8 + t;
-      a[mt][0] = u(p[0]);
-      a[mt][1] = u(p[8 * ST]);
-      a[mt][2] = half ? 0u : u(p[4]);
-      a[mt][3] = half ? 0u : u(p[8 * ST + 4]);
-    }
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const float* p = Y + (nt * 8 + g) * ST + ks * 8 + t;
-      b[nt][0] = u(p[0]);
-      b[nt][1] = half ? 0u : u(p[4]);
-    }
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[mt][nt], a[mt], b[nt]);
-  }
-}
-
-// out[32 x DH] (fragments o[mt][nt]) = P M, P given as accumulator fragments (rounded here), M staged
-// [key][d] with stride ST.  k-slot permutation: slot t <-> key 8ks+2t, slot t+4 <-> key 8ks+2t+1.
-template <int DH>
-__device__ __forceinline__ void gemm_regP(float (&o)[2][Cfg<DH>::NT][4], const float (&P)[2][4][4], const float* M, int g,
-                                          int t) {
-  constexpr int ST = Cfg<DH>::ST, NT = Cfg<DH>::NT;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.0f;
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    uint32_t a[2][4], b[NT][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      a[mt][0] = ur(P[mt][ks][0]);
-      a[mt][1] = ur(P[mt][ks][2]);
-      a[mt][2] = ur(P[mt][ks][1]);
-      a[mt][3] = ur(P[mt][ks][3]);
-    }
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const float* p = M + (ks * 8 + 2 * t) * ST + nt * 8 + g;
-      b[nt][0] = u(p[0]);
-      b[nt][1] = u(p[ST]);
-    }
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) mma_tf32(o[mt][nt], a[mt], b[nt]);
-  }
-}
-
-// out[32 x DH] = T^T M, T a 32x32 tile in shared memory (stride PS, already tf32), M staged [q][d] (stride ST)
-template <int DH>
-__device__ __forceinline__ void gemm_smemT(float (&o)[2][Cfg<DH>::NT][4], const float* T, const float* M, int g, int t) {
-  constexpr int ST = Cfg<DH>::ST, NT = Cfg<DH>::NT;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.0f;
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    uint32_t a[2][4], b[NT][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const float* p = T + (ks * 8 + t) * PS + mt * 16 + g;   // A(row, col) = T[col][row]
-      a[mt][0] = u(p[0]);
-      a[mt][1] = u(p[8]);
-      a[mt][2] = u(p[4 * PS]);
-      a[mt][3] = u(p[4 * PS + 8]);
-    }
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      const float* p = M + (ks * 8 + t) * ST + nt * 8 + g;
-      b[nt][0] = u(p[0]);
-      b[nt][1] = u(p[4 * ST]);
-    }
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) mma_tf32(o[mt][nt], a[mt], b[nt]);
-  }
-}
-
-// in-register row softmax of S*inv over the first L columns (fragment layout); masked columns -> 0
-__device__ __forceinline__ void softmax_rows(float (&acc)[2][4][4], float inv, int L, int t) {
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      float mx = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int col = nt * 8 + 2 * t + e;
-          float s = acc[mt][nt][hf * 2 + e] * inv;
-          s = col < L ? s : -INFINITY;
-          acc[mt][nt][hf * 2 + e] = s;
-          mx = fmaxf(mx, s);
-        }
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      float sum = 0.0f;
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float ex = __expf(acc[mt][nt][hf * 2 + e] - mx);
-          acc[mt][nt][hf * 2 + e] = ex;
-          sum += ex;
-        }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      const float r = 1.0f / sum;
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) acc[mt][nt][hf * 2 + e] *= r;
-    }
-}
-
-// store a 32x32 accumulator-fragment matrix to smem [32][PS], rounded to tf32
-__device__ __forceinline__ void store_frag(float* P, const float (&acc)[2][4][4], int g, int t) {
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int col = nt * 8 + 2 * t;
-      *reinterpret_cast<uint2*>(P + (mt * 16 + g) * PS + col) = make_uint2(ur(acc[mt][nt][0]), ur(acc[mt][nt][1]));
-      *reinterpret_cast<uint2*>(P + (mt * 16 + g + 8) * PS + col) = make_uint2(ur(acc[mt][nt][2]), ur(acc[mt][nt][3]));
-    }
-}
-
-// write a [32 x DH] fragment matrix (rows = tokens) to out[(row0 + r) * ld + col0 + c], rounded to tf32
-template <int DH>
-__device__ __forceinline__ void store_rows(const float (&acc)[2][Cfg<DH>::NT][4], float scale, float* __restrict__ out,
-                                           long row0, int ld, int col0, int L, int g, int t) {
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < Cfg<DH>::NT; ++nt) {
-      const int col = nt * 8 + 2 * t;
-      if (col >= DH) continue;
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const int r = mt * 16 + g + hf * 8;
-        if (r >= L) continue;
-        const uint2 v = make_uint2(ur(acc[mt][nt][hf * 2] * scale), ur(acc[mt][nt][hf * 2 + 1] * scale));
-        *reinterpret_cast<uint2*>(out + (row0 + r) * ld + col0 + col) = v;
-      }
-    }
-}
+using namespace att;
 
 template <int DH, int STAGES>
 __global__ void __launch_bounds__(WARPS * 32, 5) attn_fwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
@@ -318,7 +103,8 @@ __global__ void __launch_bounds__(WARPS * 32, 5) attn_fwd_pre_kernel(int n_seq, 
 
 template <int DH, int STAGES, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) attn_bwd_pre_kernel(int n_seq, int L, int nh, const float* __restrict__ qkv,
-                                                                  const float* __restrict__ dy, float* __restrict__ dqkv) {
+                                                                  const float* __restrict__ dy, float* __restrict__ dqkv,
+                                                                  int tiled) {
   extern __shared__ __align__(16) float smem[];
   constexpr int MAT = Cfg<DH>::MAT;
   constexpr int PER_WARP = STAGES * 4 * MAT;
@@ -331,9 +117,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) attn_bwd_pre_kernel(int n_se
   long item = (long)blockIdx.x * WARPS + warp;
   auto issue = [&](long it, int buf) {
     const int n = (int)(it / nh), h = (int)(it - (long)n * nh);
-    const float* b = qkv + (long)n * L * 3 * D + h * DH;
-    const float* const src[4] = {b, b + D, b + 2 * D, dy + (long)n * L * D + h * DH};
-    const long ld[4] = {3L * D, 3L * D, 3L * D, (long)D};
+    // rows of the [n_seq*L, 3D] projection buffer, or the zero-padded [32][ST] tiles saved by the fused forward
+    const float* b = tiled ? qkv + (long)it * 3 * MAT : qkv + (long)n * L * 3 * D + h * DH;
+    const long qs = tiled ? (long)Cfg<DH>::ST : 3L * D, step = tiled ? (long)MAT : (long)D;
+    const float* const src[4] = {b, b + step, b + 2 * step, dy + (long)n * L * D + h * DH};
+    const long ld[4] = {qs, qs, qs, (long)D};
     stage_async<DH, 4>(base_s + buf * 4 * MAT, src, ld, L, lane);
     cp_commit();
   };
@@ -463,7 +251,7 @@ int attention_core_fwd_pre(int n_seq, int L, int nh, int dh, const float* qkv, f
 }
 
 int attention_core_bwd_pre(int n_seq, int L, int nh, int dh, const float* qkv, const float* dy, float* dqkv,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool tiled) {
   if (n_seq <= 0) return EBK_OK;
   EBK_CHECK_ARG(attention_pre_supported(L, dh, qkv, dy, dqkv), "attention_pre: unsupported shape L=%d dh=%d", L, dh);
   const long total = (long)n_seq * nh;
@@ -473,10 +261,10 @@ int attention_core_bwd_pre(int n_seq, int L, int nh, int dh, const float* qkv, c
     const size_t smem = (size_t)WARPS * (ST_ * 4 * Cfg<DH_>::MAT) * sizeof(float) + 64; /* n-tile overhang */ \
     if (att_minb() == 4) {                                                                        \
       EBK_TRY(cfg(attn_bwd_pre_kernel<DH_, ST_, 4>, smem, total, &grid));                         \
-      attn_bwd_pre_kernel<DH_, ST_, 4><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, qkv, dy, dqkv); \
+      attn_bwd_pre_kernel<DH_, ST_, 4><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, qkv, dy, dqkv, tiled ? 1 : 0); \
     } else {                                                                                      \
       EBK_TRY(cfg(attn_bwd_pre_kernel<DH_, ST_, 3>, smem, total, &grid));                         \
-      attn_bwd_pre_kernel<DH_, ST_, 3><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, qkv, dy, dqkv); \
+      attn_bwd_pre_kernel<DH_, ST_, 3><<<grid, WARPS * 32, smem, st>>>(n_seq, L, nh, qkv, dy, dqkv, tiled ? 1 : 0); \
     }                                                                                             \
   }
 #define RUN(DH_) { if (att_stages() == 2) RUN2(DH_, 2) else RUN2(DH_, 1) }

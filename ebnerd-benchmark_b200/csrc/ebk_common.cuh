@@ -208,6 +208,15 @@ bool gemm_tma_eligible(const float* A, int lda, const float* B, int ldb, int M, 
 int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool transB, float* C, int ldc, int M,
              int N, int K, float beta, float alpha, cudaStream_t st, int tall = 0, const GemmEpilogue* epi = nullptr,
              int cluster = 0);
+// Fused SelfAttention forward on the all-TMA path (gemm_tma_sm100.cu): QKV projection with the per-head
+// softmax(QK^T/sqrt(dh))^T V computed in the GEMM epilogue (accumulator tile = whole sequences x whole heads).
+//   wp = permute_round_wqkv(W): [Din, (head, Q|K|V, d)] tf32 copy of Wqkv [Din, (Q|K|V, head, d)]
+//   qkv_t (nullable): Q | K | V saved as [n_seq, nh, 3, 32, ST] zero-padded tiles for attention_core_bwd_pre(tiled)
+bool qkv_attn_fused_supported(int L, int dh, int Din, const float* xd, const float* wp, const float* y);
+size_t qkv_tiles_floats(int n_seq, int nh, int dh);
+int permute_round_wqkv(float* wp, const float* W, int Din, int nh, int dh, cudaStream_t st);
+int qkv_attn_fused(const float* xd, int Din, const float* wp, int n_seq, int L, int nh, int dh, float* qkv_t, float* y,
+                   Dropout drop, cudaStream_t st);
 // hi[i] = tf32(src[i]) (round to nearest), lo[i] = src[i] - hi[i]
 int split_tf32_copy(float* hi, float* lo, const float* src, size_t n, cudaStream_t st);
 // dst[i] = round-to-nearest-tf32(src[i])  (so that the tensor core's truncation is exact)
@@ -234,8 +243,9 @@ int attention_core_bwd_mma(int n_seq, int L, int nh, int dh, const float* qkv, c
 // cp.async double-buffered staging, register-resident A / dS.  fwd stores tf32(dropout(y)); bwd stores tf32(dqkv).
 bool attention_pre_supported(int L, int dh, const void* p0, const void* p1, const void* p2);
 int attention_core_fwd_pre(int n_seq, int L, int nh, int dh, const float* qkv, float* y, Dropout drop_out, cudaStream_t st);
+// tiled: qkv is the [n_seq, nh, 3, 32, ST] tile layout written by qkv_attn_fused instead of [n_seq*L, 3D] rows
 int attention_core_bwd_pre(int n_seq, int L, int nh, int dh, const float* qkv, const float* dy, float* dqkv,
-                           cudaStream_t st);
+                           cudaStream_t st, bool tiled = false);
 
 // AttLayer2 pieces
 int attpool_fwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop, float* hbuf /*[R,att] in: pre-act, out: tanh*/,

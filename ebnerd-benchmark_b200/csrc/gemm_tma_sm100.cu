@@ -41,6 +41,7 @@
 
 #include <unordered_map>
 
+#include "attention_tiles.cuh"
 #include "ebk_common.cuh"
 
 namespace ebk {
@@ -68,6 +69,25 @@ struct TParams {
   GemmEpilogue epi;    // optional fused epilogue (out_mode 0 only)
   int rv_smem;         // 1: the rowvec rows of each epilogue warp are staged in shared memory (L >= 16)
   int c_tma;           // 1: C has a tensor map -> the epilogue stores through shared memory + TMA
+  int tile_rows;       // matrix rows between consecutive m-tiles of one CTA (BM * MT; fused attention: spt * L <= 128)
+  // ---- fused QKV projection + attention epilogue (ADH > 0): the tile is spt whole sequences x HPT whole heads
+  int att_L, att_spt, att_nh, att_nseq;
+  float* att_qkv_t;    // [n_seq, nh, 3, 32, ST] tf32 Q|K|V tiles saved for the backward pass (NULL: inference)
+  float* att_y;        // [n_seq * L, nh * DH] attention output (dropout-masked, tf32-rounded)
+  Dropout att_drop;
+};
+// fused-attention geometry for head dim DH: HR heads are processed per epilogue round, HPT heads per tile
+template <int DH> struct AttGeo {
+  static constexpr int HPT = (DH <= 20) ? 4 : 2;
+  static constexpr int HR = 2;
+  static constexpr int ROUNDS = HPT / HR;
+  static constexpr int BN = HPT * 3 * DH;                 // 240 (dh 20), 192 (16), 144 (24), 192 (32)
+  static constexpr int RCOLS = HR * 3 * DH;               // accumulator columns per round (multiple of 8)
+  static constexpr int MAT = att::Cfg<DH>::MAT;
+  static constexpr int SPT_MAX = 4;                       // sequences per 128-row tile handled (one per epilogue warp)
+  static constexpr uint32_t TILE_BYTES = SPT_MAX * HR * 3 * MAT * 4;
+  static constexpr uint32_t P_BYTES = 4 * att::LP * att::PS * 4;
+  static constexpr uint32_t SMEM = TILE_BYTES + P_BYTES;
 };
 constexpr uint32_t STG_BYTES = 4u * 2u * 4096u;  // store staging: 4 epilogue warps x 2 x [32][128 B]
 constexpr int RV_ART = 4;                   // articles a warp's 32 rows can span when L >= 16
@@ -220,6 +240,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+
 // Walks this CTA's work items (m-tile, n-tile, k-split; n fastest so the CTAs that run at the same
 // time share the A rows in L2) k-step by k-step.
 template <int MT, bool PAIR>
@@ -230,7 +261,7 @@ struct Cursor {
     const int per_m = p.tiles_n * p.splitk;
     const int tm = item / per_m, rem = item - tm * per_m;
     const int tn = rem / p.splitk, sp = rem - tn * p.splitk;
-    m0 = (tm * (PAIR ? 2 : 1) + rm) * BM * MT;
+    m0 = (tm * (PAIR ? 2 : 1) + rm) * p.tile_rows;
     n0 = tn * p.BN;
     ks = sp * p.ksteps_per_split;
     ks_end = min(p.ksteps_total, ks + p.ksteps_per_split);
@@ -337,7 +368,7 @@ __device__ __forceinline__ void store16_direct(const TParams& p, float* crow, co
   }
 }
 
-template <bool A_MN, bool B_MN, int MT, bool PAIR>
+template <bool A_MN, bool B_MN, int MT, bool PAIR, int ADH>
 __global__ void __launch_bounds__(THREADS, 1)
     gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const TParams p) {
@@ -509,6 +540,126 @@ __global__ void __launch_bounds__(THREADS, 1)
     Cursor<MT, PAIR> cu;
     cu.init(p, first_item, n_items, rm);
     int t = 0;
+    if constexpr (ADH > 0) {
+      // ============ fused attention epilogue (north star: projection -> per-head softmax(QK^T/sqrt(dh))^T V) ============
+      // The accumulator tile is spt whole sequences x HPT whole heads, columns ordered (head, Q|K|V, d) by the
+      // permuted weight operand.  Per round of HR heads: every epilogue warp moves its 32 accumulator rows
+      // TMEM -> registers -> [seq][head][Q|K|V][32 tok][ST] tiles in shared memory (tf32-rounded), then warp w runs the
+      // attention of sequence w on mma.sync and writes dropout(Y) rows; when training, the Q|K|V tiles go to global
+      // memory as they are (one 3*MAT bulk copy per (sequence, head)) for the backward kernel.
+      using G = AttGeo<ADH>;
+      using AC = att::Cfg<ADH>;
+      static_assert(MT == 1, "fused attention uses 128-row tiles with a double-buffered accumulator");
+      constexpr int DH = ADH, ST = AC::ST, MAT = AC::MAT;
+      const int lane_g = lane >> 2, lane_t = lane & 3;
+      const int L = p.att_L, spt = p.att_spt, nh = p.att_nh, D = nh * DH;
+      float* tiles = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)S * stage_bytes);
+      float* Pw = tiles + G::TILE_BYTES / 4 + (warp - 2) * (att::LP * att::PS);
+      const float inv = rsqrtf((float)DH);
+      const int etid = (warp - 2) * 32 + lane;
+      for (int i = etid; i < (int)(G::TILE_BYTES / 16); i += EPI_THREADS)   // zero rows past L (and all padding) once
+        reinterpret_cast<float4*>(tiles)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int r_loc = ew * 32 + lane;                      // accumulator row of this thread inside the tile
+      const int seq_loc = r_loc / L, tok = r_loc - seq_loc * L;
+      const bool row_ok = seq_loc < spt;
+      int nbulk = 0;
+      while (cu.valid(n_items)) {
+        const int buf = t & 1, use = t >> 1;
+        const int seq0 = cu.m0 / L;                          // first sequence of this CTA's tile
+        const int head0 = cu.n0 / (3 * DH);
+        mbar_wait_backoff(smem_u32(&tfull_bar[buf]), (uint32_t)(use & 1));
+        tc_fence_after();
+        const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * 256u;
+#pragma unroll 1
+        for (int rd = 0; rd < G::ROUNDS; ++rd) {
+          if (nbulk > 0) {   // the bulk copies of the previous round must have read the tiles
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
+          epi_bar_sync();   // previous round's attention is done with the tiles in every warp
+          float* rowbase = tiles + (size_t)seq_loc * (G::HR * 3 * MAT) + tok * ST;
+#pragma unroll
+          for (int c = 0; c < G::RCOLS / 8; ++c) {
+            float v[8];
+            tmem_ld8(tbase + (uint32_t)(rd * G::RCOLS + c * 8), v);   // warp-collective
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int col = c * 8 + j * 4;                 // compile-time after unrolling
+                const int hh = col / (3 * DH), rem = col - hh * 3 * DH, m = rem / DH, d = rem - m * DH;
+                float4 o = make_float4(round_tf32_bits(v[j * 4] * p.alpha), round_tf32_bits(v[j * 4 + 1] * p.alpha),
+                                       round_tf32_bits(v[j * 4 + 2] * p.alpha), round_tf32_bits(v[j * 4 + 3] * p.alpha));
+                *reinterpret_cast<float4*>(rowbase + (hh * 3 + m) * MAT + d) = o;
+              }
+            }
+          }
+          if (rd == G::ROUNDS - 1) {
+            // every accumulator column of this tile has been read: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+            else mbar_arrive(smem_u32(&tempty_bar[buf]));
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // tiles are read by bulk copies below
+          epi_bar_sync();   // all rows of every sequence are in place
+          const int s_loc = warp - 2;                            // this warp's sequence of the tile
+          const long seq = (long)seq0 + s_loc;
+          if (s_loc < spt && seq < p.att_nseq) {
+#pragma unroll 1
+            for (int hh = 0; hh < G::HR; ++hh) {
+              const int head = head0 + rd * G::HR + hh;
+              if (head >= nh) break;
+              float* Qs = tiles + (size_t)(s_loc * G::HR + hh) * 3 * MAT;
+              const float* Ks = Qs + MAT;
+              const float* Vs = Ks + MAT;
+              if (p.att_qkv_t != nullptr && lane == 0) {
+                float* dst = p.att_qkv_t + ((size_t)seq * nh + head) * 3 * MAT;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(Qs)),
+                             "r"((uint32_t)(3 * MAT * 4))
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+              if (p.att_qkv_t != nullptr) ++nbulk;
+              float acc[2][4][4];
+              att::gemm_xyT<DH>(acc, Qs, Ks, lane_g, lane_t);
+              att::softmax_rows(acc, inv, L, lane_t);
+              att::store_frag(Pw, acc, lane_g, lane_t);
+              __syncwarp();
+              float o[2][AC::NT][4];
+              att::gemm_smemT<DH>(o, Pw, Vs, lane_g, lane_t);   // O[k, d] = sum_q P[q, k] V[q, d]
+              float* out = p.att_y + seq * L * D + head * DH;
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < AC::NT; ++nt) {
+                  const int col = nt * 8 + 2 * lane_t;
+                  if (col >= DH) continue;
+#pragma unroll
+                  for (int hf = 0; hf < 2; ++hf) {
+                    const int r = mt * 16 + lane_g + hf * 8;
+                    if (r >= L) continue;
+                    float2 v = make_float2(o[mt][nt][hf * 2], o[mt][nt][hf * 2 + 1]);
+                    if (p.att_drop.on()) {  // AttLayer2 only ever reads dropout(y): store it masked and scaled
+                      const uint64_t idx = (uint64_t)(seq * L + r) * (uint64_t)D + (uint64_t)(head * DH + col);
+                      const float4 f = p.att_drop.factor4_group(idx >> 2);
+                      v.x *= (idx & 2ull) ? f.z : f.x;
+                      v.y *= (idx & 2ull) ? f.w : f.y;
+                    }
+                    *reinterpret_cast<uint2*>(out + (long)r * D + col) =
+                        make_uint2(__float_as_uint(round_tf32_bits(v.x)), __float_as_uint(round_tf32_bits(v.y)));
+                  }
+                }
+              __syncwarp();   // Pw is rewritten by the next head
+            }
+          }
+        }
+        cu.next_item(p, n_items, item_stride);
+        ++t;
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    } else {
     const bool vec_base = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     const bool vec8_base = vec_base && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 31) == 0) && p.out_mode == 0;
     uint8_t* tail = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)S * stage_bytes;   // behind the stage ring
@@ -617,6 +768,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging must outlive its readers
     __syncwarp();
+    }   // plain GEMM epilogue
   }
   tc_fence_before();
   __syncthreads();
@@ -755,6 +907,10 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   const int bn_cta = pair ? p.BN / 2 : p.BN;                       // B columns staged by one CTA
   p.b_rows = b_mn ? ((bn_cta + 31) & ~31) : bn_cta;
   p.tiles_m = ceil_div(M, BM * MT * cm);
+  p.tile_rows = BM * MT;
+  p.att_L = p.att_spt = p.att_nh = p.att_nseq = 0;
+  p.att_qkv_t = p.att_y = nullptr;
+  p.att_drop = Dropout{0, 0, 1.0f, nullptr};
   p.ksteps_total = ceil_div(K, BK);
   const size_t stage_bytes = (size_t)MT * BM * BK * 4 + (size_t)p.b_rows * BK * 4;
   p.rv_smem = (p.epi.rowscale != nullptr && p.epi.L >= 16) ? 1 : 0;
@@ -810,9 +966,9 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   cfg.numAttrs = csize > 1 ? 1 : 0;
 #define LAUNCH4(AMN_, BMN_, MT_, PAIR_)                                                                          \
   {                                                                                                                \
-    EBK_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<AMN_, BMN_, MT_, PAIR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    EBK_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<AMN_, BMN_, MT_, PAIR_, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)smem));                                                                     \
-    EBK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tma_kernel<AMN_, BMN_, MT_, PAIR_>, tmA, tmB, tmC, p));                  \
+    EBK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tma_kernel<AMN_, BMN_, MT_, PAIR_, 0>, tmA, tmB, tmC, p));               \
   }
 #define LAUNCH3(AMN_, BMN_, MT_)                   \
   {                                                \
@@ -831,6 +987,115 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
 #undef LAUNCH2
 #undef LAUNCH3
 #undef LAUNCH4
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+
+// ---- fused QKV projection + attention (the forward of SelfAttention, layers.py:214-252, in ONE kernel) -------------
+namespace {
+// wp[k, (h, m, d)] = tf32(W[k, m * D + h * dh + d]): head-major column order, so that an accumulator tile of
+// AttGeo::BN columns holds Q | K | V of whole heads
+__global__ void permute_round_wqkv_kernel(const float* __restrict__ W, float* __restrict__ wp, int Din, int nh, int dh) {
+  const int D = nh * dh, N = 3 * D;
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)Din * N) return;
+  const int k = (int)(i / N), c = (int)(i - (long)k * N);
+  const int h = c / (3 * dh), rem = c - h * 3 * dh, m = rem / dh, d = rem - m * dh;
+  wp[i] = round_tf32_bits(W[(long)k * N + m * D + h * dh + d]);
+}
+}  // namespace
+
+int permute_round_wqkv(float* wp, const float* W, int Din, int nh, int dh, cudaStream_t st) {
+  const long n = (long)Din * 3 * nh * dh;
+  permute_round_wqkv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, wp, Din, nh, dh);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+bool qkv_attn_fused_supported(int L, int dh, int Din, const float* xd, const float* wp, const float* y) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return L >= 1 && L <= 32 && (dh == 16 || dh == 20 || dh == 24 || dh == 32) && Din % 4 == 0 && al(xd) && al(wp) && al(y) &&
+         encode_fn() != nullptr;
+}
+size_t qkv_tiles_floats(int n_seq, int nh, int dh) {
+  const int st = (dh == 20) ? 20 : dh + 4;
+  return (size_t)n_seq * nh * 3 * 32 * st;
+}
+
+// xd [n_seq * L, Din] (tf32 values), wp [Din, nh * 3 * dh] head-major (permute_round_wqkv) ->
+//   y [n_seq * L, nh * dh] = tf32(dropout(attention output)), qkv_t (nullable) = the Q | K | V tiles for the backward
+int qkv_attn_fused(const float* xd, int Din, const float* wp, int n_seq, int L, int nh, int dh, float* qkv_t, float* y,
+                   Dropout drop, cudaStream_t st) {
+  if (n_seq <= 0) return EBK_OK;
+  EBK_CHECK_ARG(qkv_attn_fused_supported(L, dh, Din, xd, wp, y), "qkv_attn_fused: unsupported shape L=%d dh=%d Din=%d", L, dh, Din);
+  if (g_sms == 0) {
+    int dev = 0;
+    EBK_CUDA(cudaGetDevice(&dev));
+    EBK_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int hpt = dh <= 20 ? 4 : 2, BN = hpt * 3 * dh, Ntot = nh * 3 * dh;
+  const int spt = (128 / L) < 4 ? (128 / L) : 4;          // whole sequences per 128-row tile, one per epilogue warp
+  const long M = (long)n_seq * L;
+  const int n_row_tiles = ceil_div(n_seq, spt);
+  const int env_pair = getenv("EBK_FUSED_PAIR") ? atoi(getenv("EBK_FUSED_PAIR")) : -1;   // experiments / tests
+  const bool pair = env_pair >= 0 ? env_pair != 0 : (n_row_tiles >= 2 * (g_sms / 2));
+  const int cm = pair ? 2 : 1;
+  TParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = nullptr; p.ldc = 0; p.M = (int)M; p.N = Ntot; p.K = Din; p.alpha = 1.0f;
+  p.epi = GemmEpilogue{nullptr, nullptr, 0, 1, Dropout{0, 0, 1.0f, nullptr}, 0, false};
+  p.BN = BN;
+  p.tiles_n = ceil_div(nh, hpt);
+  const int bn_cta = pair ? BN / 2 : BN;
+  p.b_rows = (bn_cta + 31) & ~31;                             // MN-major operand: padded groups of 32 columns
+  p.tiles_m = ceil_div(n_row_tiles, cm);
+  p.tile_rows = spt * L;
+  p.ksteps_total = ceil_div(Din, BK);
+  p.ksteps_per_split = p.ksteps_total;
+  p.splitk = 1;
+  p.out_mode = 0;
+  p.rv_smem = 0;
+  p.c_tma = 0;
+  p.att_L = L; p.att_spt = spt; p.att_nh = nh; p.att_nseq = n_seq;
+  p.att_qkv_t = qkv_t; p.att_y = y; p.att_drop = drop;
+  const size_t stage_bytes = (size_t)BM * BK * 4 + (size_t)p.b_rows * BK * 4;
+  const size_t att_smem = dh == 16 ? AttGeo<16>::SMEM : dh == 20 ? AttGeo<20>::SMEM : dh == 24 ? AttGeo<24>::SMEM : AttGeo<32>::SMEM;
+  const size_t budget = 226 * 1024 - 1024 - att_smem;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  EBK_CHECK_ARG(stages >= 2, "qkv_attn_fused: shared memory budget (stage %zu B, attention %zu B)", stage_bytes, att_smem);
+  p.stages = stages;
+  CUtensorMap tmA, tmB;
+  EBK_TRY(get_map(xd, Din, (int)M, Din, BM, false, &tmA));          // storage [M, K], box {32 k, 128 rows}
+  EBK_TRY(get_map(wp, Ntot, Din, Ntot, 32, true, &tmB));            // storage [K, N], boxes {32 n, 32 k}
+  const long n_items = (long)p.tiles_m * p.tiles_n;
+  const int max_clusters = g_sms / cm;
+  const int grid = (int)(n_items < max_clusters ? n_items : max_clusters) * cm;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + att_smem;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cm;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cm > 1 ? 1 : 0;
+#define FUSED_LAUNCH(PAIR_, DH_)                                                                                       \
+  {                                                                                                                   \
+    EBK_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<false, true, 1, PAIR_, DH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smem));                                                                        \
+    EBK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tma_kernel<false, true, 1, PAIR_, DH_>, tmA, tmB, tmA, p));                 \
+  }
+#define FUSED_DH(DH_) { if (pair) FUSED_LAUNCH(true, DH_) else FUSED_LAUNCH(false, DH_) }
+  if (dh == 16) FUSED_DH(16) else if (dh == 20) FUSED_DH(20) else if (dh == 24) FUSED_DH(24) else FUSED_DH(32)
+#undef FUSED_DH
+#undef FUSED_LAUNCH
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

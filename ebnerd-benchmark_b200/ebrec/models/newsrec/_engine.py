@@ -712,8 +712,14 @@ class NRMSEngine:
         key = self._graph_key(B, C_, tok_all.shape)
         st = graphs.get(key)
         if st is None:
-            st = {"tok": torch.empty_like(tok_all), "lab": torch.empty_like(labels),
-                  "step": torch.zeros(3, dtype=torch.int64, device=self.device), "graph": None, "warm": 0}
+            # ONE device block [ebk_step_params (64 B) | labels | token ids], so that a host batch is a single H2D copy
+            lab_off, lab_bytes = 64, labels.numel() * 4
+            tok_off = lab_off + (lab_bytes + 63) // 64 * 64
+            inbuf = torch.zeros(tok_off + tok_all.numel() * 4, dtype=torch.uint8, device=self.device)
+            st = {"inbuf": inbuf, "lab_off": lab_off, "tok_off": tok_off,
+                  "step": inbuf[:24].view(torch.int64),
+                  "lab": inbuf[lab_off: lab_off + lab_bytes].view(torch.float32).view(labels.shape),
+                  "tok": inbuf[tok_off:].view(torch.int32).view(tok_all.shape), "graph": None, "warm": 0}
             graphs[key] = st
         if st["graph"] is None:
             if st["warm"] < 1:           # eager warm-up step(s) with the same shapes
@@ -751,30 +757,45 @@ class NRMSEngine:
         return int(_ebk.lib().ebk_launch_count()) + int(getattr(self, "graph_launches", 0))
 
     def train_step_host(self, his: np.ndarray, pred: np.ndarray, y: np.ndarray):
-        """train_on_batch / fit entry with HOST arrays: when the step is graph-replayed the pinned staging buffers
-        are copied straight into the graph's static inputs (no intermediate device tensors)."""
+        """train_on_batch / fit entry with HOST arrays.  When the step is graph-replayed, token ids, labels and the
+        per-step scalars are written straight into ONE pinned staging block laid out like the graph's device input
+        block and moved with a single asynchronous copy (no intermediate arrays or device tensors)."""
         his, pred = np.asarray(his), np.asarray(pred)
         B, C_ = pred.shape[0], pred.shape[1]
         sparse = getattr(self, "sparse_table_grad", False) and self.world == 1 and self.E <= 1024
         if sparse and his.ndim == 3 and self._graph_ok():
-            N = B * (his.shape[1] + C_)
+            Hh = his.shape[1]
+            N = B * (Hh + C_)
             st = self.__dict__.get("_graphs", {}).get(self._graph_key(B, C_, (N, self.T)))
             if st is not None and st["graph"] is not None:
-                self._h2d("tok", self.pack_tokens(his, pred), out=st["tok"])
-                self._h2d("lab", np.ascontiguousarray(y, dtype=np.float32), out=st["lab"])
-                return self._graph_step(st["tok"], st["lab"], B, C_)
+                if Hh != self.H:
+                    raise ValueError(f"history length {Hh} != hparams.history_size {self.H}")
+                stage, done = self._pin_slot("graph_in", st["inbuf"].numel())
+                hv = stage.numpy()
+                s1, s2 = self.step_seeds()
+                hv[:16].view(np.uint64)[:] = (s1, s2)
+                hv[16:20].view(np.float32)[0] = keras_adam_alpha(self.lr, self.step_count + 1, self.beta1, self.beta2)
+                hv[st["lab_off"]: st["lab_off"] + B * C_ * 4].view(np.float32).reshape(B, C_)[...] = y
+                tokv = hv[st["tok_off"]:].view(np.int32).reshape(N, self.T)
+                tokv[: B * Hh] = his.reshape(B * Hh, self.T)
+                tokv[B * Hh:] = pred.reshape(B * C_, self.T)
+                st["inbuf"].copy_(stage[: st["inbuf"].numel()], non_blocking=True)
+                done()
+                st["graph"].replay()
+                self.step_count += 1
+                self.graph_steps = getattr(self, "graph_steps", 0) + 1
+                self.graph_launches = getattr(self, "graph_launches", 0) + st["launches"]
+                return st["loss"], st["probs"]
         tok, lab = self.to_device_batch(his, pred, y)
         return self.train_step_dev(tok, lab, B, C_)
 
     # ------------------------------------------------------------------ host-array convenience
-    def _h2d(self, key: str, arr: np.ndarray, out: torch.Tensor | None = None) -> torch.Tensor:
-        """Host array -> device through a small ring of PINNED staging buffers (asynchronous copy: the host goes on
-        launching kernels while the DMA runs).  A slot is reused only after the copy that last read it finished.
-        The ring is keyed by (key, dtype) and sized by CAPACITY (grown geometrically), so eval-mode loaders whose
-        batches differ in length reuse the same four buffers instead of pinning new ones per shape."""
+    def _pin_slot(self, key, nbytes: int, dtype=torch.uint8):
+        """-> (pinned 1-D staging tensor of >= nbytes elements of `dtype`, done()): a small ring of PINNED buffers per
+        key, sized by capacity (grown geometrically).  A slot is handed out again only after the copy that last read
+        it has finished; call done() right after enqueueing the copy that reads the slot."""
         ring = self.__dict__.setdefault("_pin_ring", {})
-        slots = ring.setdefault((key, arr.dtype.str), {"i": 0, "bufs": []})
-        n = int(arr.size)
+        slots = ring.setdefault((key, str(dtype)), {"i": 0, "bufs": []})
         if len(slots["bufs"]) < 4:
             slots["bufs"].append([None, None])
             slot = slots["bufs"][-1]
@@ -783,19 +804,29 @@ class NRMSEngine:
             slots["i"] += 1
             if slot[1] is not None:
                 slot[1].synchronize()
-        if slot[0] is None or slot[0].numel() < n:
-            cap = max(1024, 1 << (max(n, 1) - 1).bit_length())
-            slot[0] = torch.empty(cap, dtype=torch.from_numpy(arr).dtype).pin_memory()
-        stage = slot[0][:n].view(arr.shape)
+        if slot[0] is None or slot[0].numel() < nbytes:
+            cap = max(1024, 1 << (max(int(nbytes), 1) - 1).bit_length())
+            slot[0] = torch.empty(cap, dtype=dtype).pin_memory()
+
+        def done():
+            ev = torch.cuda.Event()
+            ev.record()
+            slot[1] = ev
+        return slot[0], done
+
+    def _h2d(self, key: str, arr: np.ndarray, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Host array -> device through the pinned staging ring (asynchronous copy: the host goes on launching
+        kernels while the DMA runs); `out`: copy straight into this static device buffer."""
+        n = int(arr.size)
+        buf, done = self._pin_slot(key, n, torch.from_numpy(arr).dtype)
+        stage = buf[:n].view(arr.shape)
         stage.numpy()[...] = arr
-        if out is not None:      # straight into a static device buffer (CUDA-graph inputs)
+        if out is not None:
             out.view(arr.shape).copy_(stage, non_blocking=True)
             dev = out
         else:
             dev = stage.to(self.device, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        slot[1] = ev
+        done()
         return dev
 
     def to_device_batch(self, his: np.ndarray, pred: np.ndarray, y: np.ndarray | None = None):
