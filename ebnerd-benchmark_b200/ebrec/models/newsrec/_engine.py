@@ -776,7 +776,7 @@ class NRMSEngine:
                 hv[:16].view(np.uint64)[:] = (s1, s2)
                 hv[16:20].view(np.float32)[0] = keras_adam_alpha(self.lr, self.step_count + 1, self.beta1, self.beta2)
                 hv[st["lab_off"]: st["lab_off"] + B * C_ * 4].view(np.float32).reshape(B, C_)[...] = y
-                tokv = hv[st["tok_off"]:].view(np.int32).reshape(N, self.T)
+                tokv = hv[st["tok_off"]: st["tok_off"] + N * self.T * 4].view(np.int32).reshape(N, self.T)
                 tokv[: B * Hh] = his.reshape(B * Hh, self.T)
                 tokv[B * Hh:] = pred.reshape(B * C_, self.T)
                 st["inbuf"].copy_(stage[: st["inbuf"].numel()], non_blocking=True)
