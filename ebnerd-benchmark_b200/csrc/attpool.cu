@@ -2,6 +2,8 @@
 //   h = tanh(X W + b); a = h q; e = exp(a) (NO max subtraction); w = e/(sum e + 1e-7); y = sum_t w_t X_t
 // X = dropout2(Y0) is recomputed from the saved attention output and the counter-based mask.
 // One CTA per sequence; also the column-sum and embedding-row scatter helpers.
+#include <stdlib.h>
+
 #include "ebk_common.cuh"
 
 namespace ebk {
@@ -73,6 +75,72 @@ __global__ void __launch_bounds__(PT) attpool_fwd_kernel(int L, int D, int att, 
   }
 }
 
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// TMA-path forward (y0 already holds dropout(Y0)): every HBM read of the sequence is issued up front -- the [L, D]
+// rows of y0 go to shared memory with cp.async while the tanh / q-dot pass streams the [L, att] rows of h -- so the
+// pooling pass reads shared memory instead of waiting on 30 dependent global loads per thread.
+__global__ void __launch_bounds__(PT) attpool_fwd_fast_kernel(int L, int D, int att, const float* __restrict__ y0,
+                                                               float* __restrict__ hbuf, const float* __restrict__ attb,
+                                                               const float* __restrict__ attq, float* __restrict__ w,
+                                                               float* __restrict__ out, int out_ld) {
+  extern __shared__ __align__(16) float y_s[];   // [L, D]
+  __shared__ float a_s[64];
+  __shared__ float w_s[64];
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = PT / 32;
+  const int D4 = D >> 2, A4 = att >> 2;
+  const float4* ysrc = reinterpret_cast<const float4*>(y0 + (long)n * L * D);
+  for (int i = threadIdx.x; i < L * D4; i += PT) cp_async16(reinterpret_cast<float4*>(y_s) + i, ysrc + i);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int t = warp; t < L; t += nwarp) {
+    float4* hrow = reinterpret_cast<float4*>(hbuf + ((long)n * L + t) * att);
+    float acc = 0.0f;
+    for (int j = lane; j < A4; j += 32) {
+      float4 h = hrow[j];
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(attb) + j), qq = __ldg(reinterpret_cast<const float4*>(attq) + j);
+      h.x = tanhf(h.x + bb.x); h.y = tanhf(h.y + bb.y); h.z = tanhf(h.z + bb.z); h.w = tanhf(h.w + bb.w);
+      hrow[j] = h;
+      acc = fmaf(h.x, qq.x, fmaf(h.y, qq.y, fmaf(h.z, qq.z, fmaf(h.w, qq.w, acc))));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) a_s[t] = acc;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    float s = 0.0f;
+    for (int t = lane; t < L; t += 32) {
+      float e = expf(a_s[t]);  // layers.py:70-71: plain exp
+      w_s[t] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    float r = 1.0f / (s + K_EPS);  // layers.py:75-77
+    for (int t = lane; t < L; t += 32) {
+      float ww = w_s[t] * r;
+      w_s[t] = ww;
+      w[(long)n * L + t] = ww;
+    }
+  }
+  __syncthreads();
+  for (int d4 = threadIdx.x; d4 < D4; d4 += PT) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < L; ++t) {
+      const float4 x = reinterpret_cast<const float4*>(y_s)[t * D4 + d4];
+      const float ww = w_s[t];
+      acc.x = fmaf(ww, x.x, acc.x); acc.y = fmaf(ww, x.y, acc.y); acc.z = fmaf(ww, x.z, acc.z); acc.w = fmaf(ww, x.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(out + (long)n * out_ld + d4 * 4) = acc;
+  }
+}
+
 // dy[r,:] = w_r * d_out[n,:]   (the dpre.W^T term is added afterwards by a beta=1 GEMM)
 // da[r]   = w_r (dw_r - sum_j w_j dw_j),  dw_r = X_r . d_out[n]
 // dpre[r,j] = da_r q_j (1 - h_rj^2)
@@ -132,13 +200,19 @@ __global__ void __launch_bounds__(PT) attpool_bwd_fused_kernel(int L, int D, int
                                                                 const float* __restrict__ w,
                                                                 const float* __restrict__ d_out, int dout_ld,
                                                                 float* __restrict__ da, float* __restrict__ dpre,
-                                                                float* __restrict__ colpart) {
+                                                                float* __restrict__ colpart, int h_in_smem) {
+  extern __shared__ __align__(16) float h_s[];   // [L, att] (when launched with shared memory: att % 4 == 0)
   __shared__ float dw_s[64];
   __shared__ float da_s[64];
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = PT / 32;
   const float4* g4 = reinterpret_cast<const float4*>(d_out + (long)n * dout_ld);
   const int D4 = D >> 2;
+  if (h_in_smem) {   // issue the h rows now: they arrive while the X.g pass streams y0
+    const float4* hsrc = reinterpret_cast<const float4*>(hbuf + (long)n * L * att);
+    for (int i = threadIdx.x; i < L * (att >> 2); i += PT) cp_async16(reinterpret_cast<float4*>(h_s) + i, hsrc + i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (int t = warp; t < L; t += nwarp) {
     const float4* x4 = reinterpret_cast<const float4*>(y0 + ((long)n * L + t) * D);
     float acc = 0.0f;
@@ -160,13 +234,14 @@ __global__ void __launch_bounds__(PT) attpool_bwd_fused_kernel(int L, int D, int
       da[(long)n * L + t] = v;
     }
   }
+  if (h_in_smem) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   for (int j = threadIdx.x; j < att; j += PT) {
     const float qj = attq[j];
     float sb = 0.0f, sq = 0.0f;
     for (int t = 0; t < L; ++t) {
       const long r = (long)n * L + t;
-      const float h = hbuf[r * att + j];
+      const float h = h_in_smem ? h_s[t * att + j] : hbuf[r * att + j];
       const float v = round_tf32_bits(da_s[t] * qj * (1.0f - h * h));
       dpre[r * att + j] = v;
       sb += v;
@@ -280,7 +355,19 @@ int attpool_fwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop,
                 const float* attq, float* w, float* out, cudaStream_t st, int out_ld) {
   if (n_seq <= 0) return EBK_OK;
   EBK_CHECK_ARG(L <= 64, "attpool: L=%d > 64", L);
-  attpool_fwd_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, drop, hbuf, attb, attq, w, out, out_ld > 0 ? out_ld : D);
+  const int old = out_ld > 0 ? out_ld : D;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const size_t ysm = (size_t)L * D * sizeof(float);
+  static const bool fast_on = !(getenv("EBK_ATTPOOL_FAST") && atoi(getenv("EBK_ATTPOOL_FAST")) == 0);
+  if (fast_on && !drop.on() && D % 4 == 0 && att % 4 == 0 && old % 4 == 0 && ysm <= 96 * 1024 && al(y0) && al(hbuf) &&
+      al(attb) && al(attq) && al(out)) {
+    if (ysm > 48 * 1024)
+      EBK_CUDA(cudaFuncSetAttribute(attpool_fwd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attpool_fwd_fast_kernel<<<n_seq, PT, ysm, st>>>(L, D, att, y0, hbuf, attb, attq, w, out, old);
+    EBK_LAUNCH_CHECK();
+    return EBK_OK;
+  }
+  attpool_fwd_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, drop, hbuf, attb, attq, w, out, old);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }
@@ -303,7 +390,11 @@ int attpool_bwd_fused(int n_seq, int L, int D, int att, const float* y0, const f
   if (dout_ld <= 0) dout_ld = D;
   EBK_CHECK_ARG(L <= 64 && D % 4 == 0 && dout_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0,
                 "attpool: L=%d > 64, or D=%d / dout_ld=%d not multiples of 4", L, D, dout_ld);
-  attpool_bwd_fused_kernel<<<n_seq, PT, 0, st>>>(L, D, att, y0, hbuf, attq, w, d_out, dout_ld, da, dpre, colpart);
+  const size_t hsm = (size_t)L * att * sizeof(float);
+  static const bool fast_on = !(getenv("EBK_ATTPOOL_FAST") && atoi(getenv("EBK_ATTPOOL_FAST")) == 0);
+  const bool h_smem = fast_on && att % 4 == 0 && hsm <= 48 * 1024 && (reinterpret_cast<uintptr_t>(hbuf) & 15) == 0;
+  attpool_bwd_fused_kernel<<<n_seq, PT, h_smem ? hsm : 0, st>>>(L, D, att, y0, hbuf, attq, w, d_out, dout_ld, da, dpre, colpart,
+                                                                h_smem ? 1 : 0);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

@@ -53,6 +53,10 @@ constexpr int UMMA_K = 8;
 constexpr int MAX_STAGES = 8;
 constexpr int THREADS = 192;       // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 constexpr int EPI_THREADS = 128;
+// fused-attention variant: 8 epilogue warps (two per TMEM lane quarter) -- the per-(sequence, head) attention is a long
+// dependent chain of mma.sync / shuffles / exp, so its latency is hidden by running 8 of them per CTA at a time
+constexpr int ATT_EPI_WARPS = 8;
+constexpr int ATT_THREADS = 64 + 32 * ATT_EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
 
@@ -86,8 +90,8 @@ template <int DH> struct AttGeo {
   static constexpr int MAT = att::Cfg<DH>::MAT;
   static constexpr int SPT_MAX = 4;                       // sequences per 128-row tile handled (one per epilogue warp)
   static constexpr uint32_t TILE_BYTES = SPT_MAX * HR * 3 * MAT * 4;
-  static constexpr uint32_t P_BYTES = 4 * att::LP * att::PS * 4;
-  static constexpr uint32_t SMEM = TILE_BYTES + P_BYTES;
+  static constexpr uint32_t SMEM = TILE_BYTES;             // (the 32x32 probability tile overlays the unit's own Q | K)
+  static_assert(2 * MAT >= att::LP * att::PS, "the score tile overlays Q and K");
 };
 constexpr uint32_t STG_BYTES = 4u * 2u * 4096u;  // store staging: 4 epilogue warps x 2 x [32][128 B]
 constexpr int RV_ART = 4;                   // articles a warp's 32 rows can span when L >= 16
@@ -249,7 +253,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+__device__ __forceinline__ void epi_bar_sync() {   // the epilogue warps of the fused-attention variant
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * ATT_EPI_WARPS) : "memory");
+}
 
 // Walks this CTA's work items (m-tile, n-tile, k-split; n fastest so the CTAs that run at the same
 // time share the A rows in L2) k-step by k-step.
@@ -369,7 +375,7 @@ __device__ __forceinline__ void store16_direct(const TParams& p, float* crow, co
 }
 
 template <bool A_MN, bool B_MN, int MT, bool PAIR, int ADH>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : THREADS, 1)
     gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const TParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -399,7 +405,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tfull_bar[b]), 1);
-      mbar_init(smem_u32(&tempty_bar[b]), EPI_THREADS * csize);  // PAIR: both CTAs' epilogues release the leader
+      // PAIR: both CTAs' epilogues release the leader
+      mbar_init(smem_u32(&tempty_bar[b]), (ADH > 0 ? 32 * ATT_EPI_WARPS : EPI_THREADS) * csize);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -554,15 +561,17 @@ __global__ void __launch_bounds__(THREADS, 1)
       const int lane_g = lane >> 2, lane_t = lane & 3;
       const int L = p.att_L, spt = p.att_spt, nh = p.att_nh, D = nh * DH;
       float* tiles = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)S * stage_bytes);
-      float* Pw = tiles + G::TILE_BYTES / 4 + (warp - 2) * (att::LP * att::PS);
       const float inv = rsqrtf((float)DH);
+      const int eg = (warp - 2) >> 2;                          // 0 / 1: the two warps of a TMEM lane quarter
       const int etid = (warp - 2) * 32 + lane;
-      for (int i = etid; i < (int)(G::TILE_BYTES / 16); i += EPI_THREADS)   // zero rows past L (and all padding) once
+      for (int i = etid; i < (int)(G::TILE_BYTES / 16); i += 32 * ATT_EPI_WARPS)   // zero rows past L (and all padding) once
         reinterpret_cast<float4*>(tiles)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       const int r_loc = ew * 32 + lane;                      // accumulator row of this thread inside the tile
       const int seq_loc = r_loc / L, tok = r_loc - seq_loc * L;
       const bool row_ok = seq_loc < spt;
-      int nbulk = 0;
+      const int s_loc = (warp - 2) & 3;                      // compute: this warp's sequence of the tile ...
+      const int my_hh = eg;                                  // ... and head of the round (HR == 2)
+      static_assert(G::HR == 2 && ATT_EPI_WARPS == 8, "one (sequence, head) unit per epilogue warp and round");
       while (cu.valid(n_items)) {
         const int buf = t & 1, use = t >> 1;
         const int seq0 = cu.m0 / L;                          // first sequence of this CTA's tile
@@ -572,21 +581,17 @@ __global__ void __launch_bounds__(THREADS, 1)
         const uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * 256u;
 #pragma unroll 1
         for (int rd = 0; rd < G::ROUNDS; ++rd) {
-          if (nbulk > 0) {   // the bulk copies of the previous round must have read the tiles
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
-          }
-          epi_bar_sync();   // previous round's attention is done with the tiles in every warp
+          epi_bar_sync();   // previous round's attention (and its bulk copies) are done with the tiles in every warp
           float* rowbase = tiles + (size_t)seq_loc * (G::HR * 3 * MAT) + tok * ST;
+          // the two warps of a lane quarter split the round's columns in 8-column chunks (even / odd)
 #pragma unroll
           for (int c = 0; c < G::RCOLS / 8; ++c) {
+            if ((c & 1) != eg) continue;                       // warp-uniform
             float v[8];
             tmem_ld8(tbase + (uint32_t)(rd * G::RCOLS + c * 8), v);   // warp-collective
             if (row_ok) {
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
-                constexpr int dummy = 0;
-                (void)dummy;
                 const int col = c * 8 + j * 4;                 // compile-time after unrolling
                 const int hh = col / (3 * DH), rem = col - hh * 3 * DH, m = rem / DH, d = rem - m * DH;
                 float4 o = make_float4(round_tf32_bits(v[j * 4] * p.alpha), round_tf32_bits(v[j * 4 + 1] * p.alpha),
@@ -603,54 +608,57 @@ __global__ void __launch_bounds__(THREADS, 1)
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // tiles are read by bulk copies below
           epi_bar_sync();   // all rows of every sequence are in place
-          const int s_loc = warp - 2;                            // this warp's sequence of the tile
           const long seq = (long)seq0 + s_loc;
-          if (s_loc < spt && seq < p.att_nseq) {
-#pragma unroll 1
-            for (int hh = 0; hh < G::HR; ++hh) {
-              const int head = head0 + rd * G::HR + hh;
-              if (head >= nh) break;
-              float* Qs = tiles + (size_t)(s_loc * G::HR + hh) * 3 * MAT;
-              const float* Ks = Qs + MAT;
-              const float* Vs = Ks + MAT;
-              if (p.att_qkv_t != nullptr && lane == 0) {
-                float* dst = p.att_qkv_t + ((size_t)seq * nh + head) * 3 * MAT;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(Qs)),
-                             "r"((uint32_t)(3 * MAT * 4))
-                             : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-              }
-              if (p.att_qkv_t != nullptr) ++nbulk;
-              float acc[2][4][4];
-              att::gemm_xyT<DH>(acc, Qs, Ks, lane_g, lane_t);
-              att::softmax_rows(acc, inv, L, lane_t);
-              att::store_frag(Pw, acc, lane_g, lane_t);
-              __syncwarp();
-              float o[2][AC::NT][4];
-              att::gemm_smemT<DH>(o, Pw, Vs, lane_g, lane_t);   // O[k, d] = sum_q P[q, k] V[q, d]
-              float* out = p.att_y + seq * L * D + head * DH;
+          const int head = head0 + rd * G::HR + my_hh;
+          if (s_loc < spt && seq < p.att_nseq && head < nh) {
+            float* Qs = tiles + (size_t)(s_loc * G::HR + my_hh) * 3 * MAT;
+            const float* Ks = Qs + MAT;
+            const float* Vs = Ks + MAT;
+            const bool save = p.att_qkv_t != nullptr;
+            if (save && lane == 0) {   // Q | K | V tiles of this (sequence, head) -> HBM for the backward pass
+              float* dst = p.att_qkv_t + ((size_t)seq * nh + head) * 3 * MAT;
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(Qs)),
+                           "r"((uint32_t)(3 * MAT * 4))
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            float acc[2][4][4];
+            att::gemm_xyT<DH>(acc, Qs, Ks, lane_g, lane_t);
+            att::softmax_rows(acc, inv, L, lane_t);
+            if (save && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();   // every lane is done reading Q / K, and the bulk copy has read them
+            float* Ps = Qs;  // the probabilities overlay Q and K
+            att::store_frag(Ps, acc, lane_g, lane_t);
+            __syncwarp();
+            float o[2][AC::NT][4];
+            att::gemm_smemT<DH>(o, Ps, Vs, lane_g, lane_t);   // O[k, d] = sum_q P[q, k] V[q, d]
+            float* out = p.att_y + seq * L * D + head * DH;
 #pragma unroll
-              for (int mt = 0; mt < 2; ++mt)
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < AC::NT; ++nt) {
-                  const int col = nt * 8 + 2 * lane_t;
-                  if (col >= DH) continue;
+              for (int nt = 0; nt < AC::NT; ++nt) {
+                const int col = nt * 8 + 2 * lane_t;
+                if (col >= DH) continue;
 #pragma unroll
-                  for (int hf = 0; hf < 2; ++hf) {
-                    const int r = mt * 16 + lane_g + hf * 8;
-                    if (r >= L) continue;
-                    float2 v = make_float2(o[mt][nt][hf * 2], o[mt][nt][hf * 2 + 1]);
-                    if (p.att_drop.on()) {  // AttLayer2 only ever reads dropout(y): store it masked and scaled
-                      const uint64_t idx = (uint64_t)(seq * L + r) * (uint64_t)D + (uint64_t)(head * DH + col);
-                      const float4 f = p.att_drop.factor4_group(idx >> 2);
-                      v.x *= (idx & 2ull) ? f.z : f.x;
-                      v.y *= (idx & 2ull) ? f.w : f.y;
-                    }
-                    *reinterpret_cast<uint2*>(out + (long)r * D + col) =
-                        make_uint2(__float_as_uint(round_tf32_bits(v.x)), __float_as_uint(round_tf32_bits(v.y)));
+                for (int hf = 0; hf < 2; ++hf) {
+                  const int r = mt * 16 + lane_g + hf * 8;
+                  if (r >= L) continue;
+                  float2 v = make_float2(o[mt][nt][hf * 2], o[mt][nt][hf * 2 + 1]);
+                  if (p.att_drop.on()) {  // AttLayer2 only ever reads dropout(y): store it masked and scaled
+                    const uint64_t idx = (uint64_t)(seq * L + r) * (uint64_t)D + (uint64_t)(head * DH + col);
+                    const float4 f = p.att_drop.factor4_group(idx >> 2);
+                    v.x *= (idx & 2ull) ? f.z : f.x;
+                    v.y *= (idx & 2ull) ? f.w : f.y;
                   }
+                  *reinterpret_cast<uint2*>(out + (long)r * D + col) =
+                      make_uint2(__float_as_uint(round_tf32_bits(v.x)), __float_as_uint(round_tf32_bits(v.y)));
                 }
-              __syncwarp();   // Pw is rewritten by the next head
+              }
+            // rows past L of the overlaid Q / K tiles must read as zero in the next round (V rows are never touched)
+            __syncwarp();
+            for (int i = lane; i < (att::LP - L) * ST; i += 32) {
+              Qs[L * ST + i] = 0.0f;
+              Qs[MAT + L * ST + i] = 0.0f;
             }
           }
         }
@@ -1076,7 +1084,7 @@ int qkv_attn_fused(const float* xd, int Din, const float* wp, int n_seq, int L, 
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(ATT_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
