@@ -492,8 +492,7 @@ extern "C" int ebk_seqenc_bwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
     EBK_PROF(T_POOL_BWD, attpool_bwd_fused(d->n_seq, d->L, D, d->att, ws.y0, ws.hbuf, attq, ws.w, d_out, ws.da, ws.dpre,
                                            ws.colpart, st));
     // db += sum_r dpre_r ; dq += sum_r h_r da_r   (second, deterministic stage over the per-sequence partials)
-    EBK_PROF(T_COLSUM, colsum_accum_ws(d->n_seq, d->att, ws.colpart, 2 * d->att, nullptr, dattb, ws.colsum2, st));
-    EBK_PROF(T_COLSUM, colsum_accum_ws(d->n_seq, d->att, ws.colpart + d->att, 2 * d->att, nullptr, dattq, ws.colsum2, st));
+    EBK_PROF(T_COLSUM, colsum_accum2_ws(d->n_seq, 2 * d->att, d->att, ws.colpart, 2 * d->att, dattb, dattq, ws.colsum2, st));
     // dW += X^T dpre
     EBK_PROF(T_ATT_WGRAD, gemm_tma(ws.y0, D, true, ws.dpre, d->att, false, dattW, d->att, D, d->att, R, 1.0f, 1.0f, st, -1));
     // dY0 = tf32(dropout2'(w_t d_out + dpre W^T)): pooling term, dropout backward and the rounding for the

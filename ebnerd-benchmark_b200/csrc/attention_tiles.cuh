@@ -229,5 +229,106 @@ __device__ __forceinline__ void store_rows(const float (&acc)[2][Cfg<DH>::NT][4]
     }
 }
 
+
+// ---- half-unit variants: ONE 16-row m-tile `mt` of the 32x32 products, so that two warps can share a
+// (sequence, head) unit (fused attention epilogue of gemm_tma_sm100.cu: halves the dependent chain per warp) ----
+template <int DH>
+__device__ __forceinline__ void gemm_xyT_half(float (&acc)[4][4], const float* X, const float* Y, int mt, int g, int t) {
+  constexpr int ST = Cfg<DH>::ST;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.0f;
+#pragma unroll
+  for (int ks = 0; ks < Cfg<DH>::KF + (Cfg<DH>::KH ? 1 : 0); ++ks) {
+    const bool half = ks >= Cfg<DH>::KF;
+    uint32_t a[4], b[4][2];
+    const float* p = X + (mt * 16 + g) * ST + ks * 8 + t;
+    a[0] = u(p[0]);
+    a[1] = u(p[8 * ST]);
+    a[2] = half ? 0u : u(p[4]);
+    a[3] = half ? 0u : u(p[8 * ST + 4]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float* q = Y + (nt * 8 + g) * ST + ks * 8 + t;
+      b[nt][0] = u(q[0]);
+      b[nt][1] = half ? 0u : u(q[4]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], a, b[nt]);
+  }
+}
+
+__device__ __forceinline__ void softmax_rows_half(float (&acc)[4][4], float inv, int L, int t) {
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = nt * 8 + 2 * t + e;
+        float s = acc[nt][hf * 2 + e] * inv;
+        s = col < L ? s : -INFINITY;
+        acc[nt][hf * 2 + e] = s;
+        mx = fmaxf(mx, s);
+      }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.0f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float ex = __expf(acc[nt][hf * 2 + e] - mx);
+        acc[nt][hf * 2 + e] = ex;
+        sum += ex;
+      }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float r = 1.0f / sum;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) acc[nt][hf * 2 + e] *= r;
+  }
+}
+
+__device__ __forceinline__ void store_frag_half(float* P, const float (&acc)[4][4], int mt, int g, int t) {
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int col = nt * 8 + 2 * t;
+    *reinterpret_cast<uint2*>(P + (mt * 16 + g) * PS + col) = make_uint2(ur(acc[nt][0]), ur(acc[nt][1]));
+    *reinterpret_cast<uint2*>(P + (mt * 16 + g + 8) * PS + col) = make_uint2(ur(acc[nt][2]), ur(acc[nt][3]));
+  }
+}
+
+// rows mt*16 .. mt*16+15 of out[32 x DH] = T^T M
+template <int DH>
+__device__ __forceinline__ void gemm_smemT_half(float (&o)[Cfg<DH>::NT][4], const float* T, const float* M, int mt, int g, int t) {
+  constexpr int ST = Cfg<DH>::ST, NT = Cfg<DH>::NT;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[nt][e] = 0.0f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4], b[NT][2];
+    const float* p = T + (ks * 8 + t) * PS + mt * 16 + g;   // A(row, col) = T[col][row]
+    a[0] = u(p[0]);
+    a[1] = u(p[8]);
+    a[2] = u(p[4 * PS]);
+    a[3] = u(p[4 * PS + 8]);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const float* q = M + (ks * 8 + t) * ST + nt * 8 + g;
+      b[nt][0] = u(q[0]);
+      b[nt][1] = u(q[4 * ST]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) mma_tf32(o[nt], a, b[nt]);
+  }
+}
+
 }  // namespace att
 }  // namespace ebk

@@ -275,6 +275,17 @@ __global__ void colsum_final_kernel(int nblk, int Ncols, const float* __restrict
   out[j] += acc;
 }
 
+// the same with the columns split between two outputs (db | dq partials of AttLayer2): out0[j] for j < n0, out1[j - n0] after
+__global__ void colsum_final2_kernel(int nblk, int Ncols, int n0, const float* __restrict__ partial, float* __restrict__ out0,
+                                     float* __restrict__ out1) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Ncols) return;
+  float acc = 0.0f;
+  for (int b = 0; b < nblk; ++b) acc += partial[(long)b * Ncols + j];
+  if (j < n0) out0[j] += acc;
+  else out1[j - n0] += acc;
+}
+
 __global__ void round_tf32_copy_kernel(float4* __restrict__ dst, const float4* __restrict__ src, size_t n4) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
@@ -410,6 +421,18 @@ int colsum_accum_ws(int R, int Ncols, const float* X, int ldx, const float* coef
   colsum_partial_kernel<<<grid, 128, 0, st>>>(R, Ncols, X, ldx, coef, partial);
   EBK_LAUNCH_CHECK();
   colsum_final_kernel<<<ceil_div(Ncols, 128), 128, 0, st>>>(nblk, Ncols, partial, out);
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+// out0[j] += sum_r X[r, j] (j < n0), out1[j - n0] += sum_r X[r, j] (n0 <= j < Ncols): one launch pair for both
+int colsum_accum2_ws(int R, int Ncols, int n0, const float* X, int ldx, float* out0, float* out1, float* partial,
+                     cudaStream_t st) {
+  if (R <= 0 || Ncols <= 0) return EBK_OK;
+  int nblk = ceil_div(R, CS_ROWS);
+  dim3 grid(ceil_div(Ncols, 128), nblk);
+  colsum_partial_kernel<<<grid, 128, 0, st>>>(R, Ncols, X, ldx, nullptr, partial);
+  EBK_LAUNCH_CHECK();
+  colsum_final2_kernel<<<ceil_div(Ncols, 128), 128, 0, st>>>(nblk, Ncols, n0, partial, out0, out1);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

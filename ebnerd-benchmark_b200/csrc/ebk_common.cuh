@@ -264,6 +264,8 @@ int attpool_bwd_fused(int n_seq, int L, int D, int att, const float* y0, const f
 // two-stage reduction through `partial` (colsum_partial_floats(R, Ncols) floats of scratch)
 int colsum_accum_ws(int R, int Ncols, const float* X, int ldx, const float* coef, float* out, float* partial,
                     cudaStream_t st);
+int colsum_accum2_ws(int R, int Ncols, int n0, const float* X, int ldx, float* out0, float* out1, float* partial,
+                     cudaStream_t st);
 size_t colsum_partial_floats(int R, int Ncols);
 
 // z = act(z + b) in place (n = rows*U elements, U % 4 == 0);  dz = dy * dropout' * relu'(y)

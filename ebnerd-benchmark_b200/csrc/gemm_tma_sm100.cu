@@ -53,9 +53,10 @@ constexpr int UMMA_K = 8;
 constexpr int MAX_STAGES = 8;
 constexpr int THREADS = 192;       // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 constexpr int EPI_THREADS = 128;
-// fused-attention variant: 8 epilogue warps (two per TMEM lane quarter) -- the per-(sequence, head) attention is a long
-// dependent chain of mma.sync / shuffles / exp, so its latency is hidden by running 8 of them per CTA at a time
-constexpr int ATT_EPI_WARPS = 8;
+// fused-attention variant: 16 epilogue warps (four per TMEM lane quarter).  The per-(sequence, head) attention is a long
+// dependent chain of mma.sync / shuffles / exp (measured ~12k cycles per unit on one warp), so 8 units run per CTA at a
+// time and each unit is split between TWO warps (one 16-row half of the 32x32 products each).
+constexpr int ATT_EPI_WARPS = 16;
 constexpr int ATT_THREADS = 64 + 32 * ATT_EPI_WARPS;
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
@@ -562,16 +563,17 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : THREADS, 1)
       const int L = p.att_L, spt = p.att_spt, nh = p.att_nh, D = nh * DH;
       float* tiles = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)S * stage_bytes);
       const float inv = rsqrtf((float)DH);
-      const int eg = (warp - 2) >> 2;                          // 0 / 1: the two warps of a TMEM lane quarter
+      const int eg = (warp - 2) >> 2;                          // 0..3: the four warps of a TMEM lane quarter
       const int etid = (warp - 2) * 32 + lane;
       for (int i = etid; i < (int)(G::TILE_BYTES / 16); i += 32 * ATT_EPI_WARPS)   // zero rows past L (and all padding) once
         reinterpret_cast<float4*>(tiles)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       const int r_loc = ew * 32 + lane;                      // accumulator row of this thread inside the tile
       const int seq_loc = r_loc / L, tok = r_loc - seq_loc * L;
       const bool row_ok = seq_loc < spt;
-      const int s_loc = (warp - 2) & 3;                      // compute: this warp's sequence of the tile ...
-      const int my_hh = eg;                                  // ... and head of the round (HR == 2)
-      static_assert(G::HR == 2 && ATT_EPI_WARPS == 8, "one (sequence, head) unit per epilogue warp and round");
+      // compute: unit = (sequence s_loc of the tile, head my_hh of the round), shared by the two warps half = 0 / 1
+      const int s_loc = (warp - 2) & 3, my_hh = eg & 1, half = eg >> 1;
+      const int pair_bar = 2 + s_loc * 2 + my_hh;              // named barrier of the unit's two warps (ids 2..9)
+      static_assert(G::HR == 2 && ATT_EPI_WARPS == 16, "two warps per (sequence, head) unit and round");
       while (cu.valid(n_items)) {
         const int buf = t & 1, use = t >> 1;
         const int seq0 = cu.m0 / L;                          // first sequence of this CTA's tile
@@ -583,10 +585,10 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : THREADS, 1)
         for (int rd = 0; rd < G::ROUNDS; ++rd) {
           epi_bar_sync();   // previous round's attention (and its bulk copies) are done with the tiles in every warp
           float* rowbase = tiles + (size_t)seq_loc * (G::HR * 3 * MAT) + tok * ST;
-          // the two warps of a lane quarter split the round's columns in 8-column chunks (even / odd)
+          // the four warps of a lane quarter split the round's columns in 8-column chunks (c mod 4)
 #pragma unroll
           for (int c = 0; c < G::RCOLS / 8; ++c) {
-            if ((c & 1) != eg) continue;                       // warp-uniform
+            if ((c & 3) != eg) continue;                       // warp-uniform
             float v[8];
             tmem_ld8(tbase + (uint32_t)(rd * G::RCOLS + c * 8), v);   // warp-collective
             if (row_ok) {
@@ -614,7 +616,7 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : THREADS, 1)
             float* Qs = tiles + (size_t)(s_loc * G::HR + my_hh) * 3 * MAT;
             const float* Ks = Qs + MAT;
             const float* Vs = Ks + MAT;
-            const bool save = p.att_qkv_t != nullptr;
+            const bool save = p.att_qkv_t != nullptr && half == 0;
             if (save && lane == 0) {   // Q | K | V tiles of this (sequence, head) -> HBM for the backward pass
               float* dst = p.att_qkv_t + ((size_t)seq * nh + head) * 3 * MAT;
               asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(Qs)),
@@ -622,44 +624,39 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : THREADS, 1)
                            : "memory");
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
-            float acc[2][4][4];
-            att::gemm_xyT<DH>(acc, Qs, Ks, lane_g, lane_t);
-            att::softmax_rows(acc, inv, L, lane_t);
+            float acc[4][4];
+            att::gemm_xyT_half<DH>(acc, Qs, Ks, half, lane_g, lane_t);   // query rows half*16 .. +15
+            att::softmax_rows_half(acc, inv, L, lane_t);
             if (save && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();   // every lane is done reading Q / K, and the bulk copy has read them
-            float* Ps = Qs;  // the probabilities overlay Q and K
-            att::store_frag(Ps, acc, lane_g, lane_t);
-            __syncwarp();
-            float o[2][AC::NT][4];
-            att::gemm_smemT<DH>(o, Ps, Vs, lane_g, lane_t);   // O[k, d] = sum_q P[q, k] V[q, d]
+            // both warps are done reading Q / K, and the bulk copy has read them: the probabilities overlay them
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            float* Ps = Qs;
+            att::store_frag_half(Ps, acc, half, lane_g, lane_t);
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            float o[AC::NT][4];
+            att::gemm_smemT_half<DH>(o, Ps, Vs, half, lane_g, lane_t);   // O[k, d] = sum_q P[q, k] V[q, d], k rows half*16 ..
             float* out = p.att_y + seq * L * D + head * DH;
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+            for (int nt = 0; nt < AC::NT; ++nt) {
+              const int col = nt * 8 + 2 * lane_t;
+              if (col >= DH) continue;
 #pragma unroll
-              for (int nt = 0; nt < AC::NT; ++nt) {
-                const int col = nt * 8 + 2 * lane_t;
-                if (col >= DH) continue;
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                  const int r = mt * 16 + lane_g + hf * 8;
-                  if (r >= L) continue;
-                  float2 v = make_float2(o[mt][nt][hf * 2], o[mt][nt][hf * 2 + 1]);
-                  if (p.att_drop.on()) {  // AttLayer2 only ever reads dropout(y): store it masked and scaled
-                    const uint64_t idx = (uint64_t)(seq * L + r) * (uint64_t)D + (uint64_t)(head * DH + col);
-                    const float4 f = p.att_drop.factor4_group(idx >> 2);
-                    v.x *= (idx & 2ull) ? f.z : f.x;
-                    v.y *= (idx & 2ull) ? f.w : f.y;
-                  }
-                  *reinterpret_cast<uint2*>(out + (long)r * D + col) =
-                      make_uint2(__float_as_uint(round_tf32_bits(v.x)), __float_as_uint(round_tf32_bits(v.y)));
+              for (int hf = 0; hf < 2; ++hf) {
+                const int r = half * 16 + lane_g + hf * 8;
+                if (r >= L) continue;
+                float2 v = make_float2(o[nt][hf * 2], o[nt][hf * 2 + 1]);
+                if (p.att_drop.on()) {  // AttLayer2 only ever reads dropout(y): store it masked and scaled
+                  const uint64_t idx = (uint64_t)(seq * L + r) * (uint64_t)D + (uint64_t)(head * DH + col);
+                  const float4 f = p.att_drop.factor4_group(idx >> 2);
+                  v.x *= (idx & 2ull) ? f.z : f.x;
+                  v.y *= (idx & 2ull) ? f.w : f.y;
                 }
+                *reinterpret_cast<uint2*>(out + (long)r * D + col) =
+                    make_uint2(__float_as_uint(round_tf32_bits(v.x)), __float_as_uint(round_tf32_bits(v.y)));
               }
-            // rows past L of the overlaid Q / K tiles must read as zero in the next round (V rows are never touched)
-            __syncwarp();
-            for (int i = lane; i < (att::LP - L) * ST; i += 32) {
-              Qs[L * ST + i] = 0.0f;
-              Qs[MAT + L * ST + i] = 0.0f;
             }
+            // (rows past L of the overlaid Q / K tiles now hold probabilities: finite values, which is all the
+            // masked softmax columns and the zero V rows need; the backward re-zeroes them when it loads the tiles)
           }
         }
         cu.next_item(p, n_items, item_stride);

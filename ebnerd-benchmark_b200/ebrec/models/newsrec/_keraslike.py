@@ -317,9 +317,13 @@ class KerasLikeModel:
             n_seen = 0
             ys, ps = [], []
             nb = 0
+            loss_host = self.__dict__.get("_loss_host")
+            if loss_host is None:   # pinned ring the per-step losses are copied to (what a progress bar reads)
+                loss_host = self._loss_host = torch.zeros(64, dtype=torch.float32).pin_memory()
             for inputs, yb in self._batches(x, y, batch_size, shuffle, rng, shard=True):
                 loss_dev, probs_dev, bsz = self._train_batch(inputs, yb)
                 tot_loss += loss_dev * bsz  # stays on device: no per-step host sync
+                loss_host[nb % 64: nb % 64 + 1].copy_(loss_dev.reshape(-1)[:1], non_blocking=True)   # async D2H, 4 bytes
                 n_seen += bsz
                 nb += 1
                 if "auc" in self._metrics:
