@@ -53,6 +53,11 @@ constexpr int UMMA_K = 8;
 constexpr int MAX_STAGES = 8;
 constexpr int THREADS = 192;       // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 constexpr int EPI_THREADS = 128;
+// GEMMs with a heavy fused epilogue (dropout hash + pooling term + rounding) run 8 epilogue warps, two per TMEM lane
+// quarter splitting the tile's 32-column chunks: one warp alone on its scheduler is latency-bound (ncu: 20k cycles per
+// 128x208 tile against a 5k-cycle main loop with 4 warps)
+constexpr int MAX_EPI_WARPS = 8;
+constexpr int MAX_THREADS = 64 + 32 * MAX_EPI_WARPS;
 // fused-attention variant: 16 epilogue warps (four per TMEM lane quarter).  The per-(sequence, head) attention is a long
 // dependent chain of mma.sync / shuffles / exp (measured ~12k cycles per unit on one warp), so 8 units run per CTA at a
 // time and each unit is split between TWO warps (one 16-row half of the 32x32 products each).
@@ -75,6 +80,7 @@ struct TParams {
   int rv_smem;         // 1: the rowvec rows of each epilogue warp are staged in shared memory (L >= 16)
   int c_tma;           // 1: C has a tensor map -> the epilogue stores through shared memory + TMA
   int tile_rows;       // matrix rows between consecutive m-tiles of one CTA (BM * MT; fused attention: spt * L <= 128)
+  int epi_warps;       // epilogue warps of the plain GEMM: 4, or 8 (two per TMEM lane quarter)
   // ---- fused QKV projection + attention epilogue (ADH > 0): the tile is spt whole sequences x HPT whole heads
   int att_L, att_spt, att_nh, att_nseq;
   float* att_qkv_t;    // [n_seq, nh, 3, 32, ST] tf32 Q|K|V tiles saved for the backward pass (NULL: inference)
@@ -94,7 +100,7 @@ template <int DH> struct AttGeo {
   static constexpr uint32_t SMEM = TILE_BYTES;             // (the 32x32 probability tile overlays the unit's own Q | K)
   static_assert(2 * MAT >= att::LP * att::PS, "the score tile overlays Q and K");
 };
-constexpr uint32_t STG_BYTES = 4u * 2u * 4096u;  // store staging: 4 epilogue warps x 2 x [32][128 B]
+constexpr uint32_t STG_WARP_BYTES = 2u * 4096u;  // store staging per epilogue warp: 2 x [32][128 B]
 constexpr int RV_ART = 4;                   // articles a warp's 32 rows can span when L >= 16
 constexpr int RV_WARP_FLOATS = RV_ART * 256; // per warp, per m-subtile
 
@@ -376,7 +382,7 @@ __device__ __forceinline__ void store16_direct(const TParams& p, float* crow, co
 }
 
 template <bool A_MN, bool B_MN, int MT, bool PAIR, int ADH>
-__global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : THREADS, 1)
+__global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : MAX_THREADS, 1)
     gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const TParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -407,7 +413,7 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : THREADS, 1)
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tfull_bar[b]), 1);
       // PAIR: both CTAs' epilogues release the leader
-      mbar_init(smem_u32(&tempty_bar[b]), (ADH > 0 ? 32 * ATT_EPI_WARPS : EPI_THREADS) * csize);
+      mbar_init(smem_u32(&tempty_bar[b]), (uint32_t)((ADH > 0 ? 32 * ATT_EPI_WARPS : 32 * p.epi_warps) * csize));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -669,7 +675,8 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : THREADS, 1)
     const bool vec8_base = vec_base && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 31) == 0) && p.out_mode == 0;
     uint8_t* tail = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)S * stage_bytes;   // behind the stage ring
     // rowvec slab of this warp: [MT][RV_ART][BN] floats
-    float* rv_s = reinterpret_cast<float*>(tail + STG_BYTES) + (size_t)(warp - 2) * MT * RV_WARP_FLOATS;
+    const int EG = p.epi_warps >> 2, eg = (warp - 2) >> 2;   // warps per TMEM lane quarter, this warp's index among them
+    float* rv_s = reinterpret_cast<float*>(tail + (size_t)p.epi_warps * STG_WARP_BYTES) + (size_t)(warp - 2) * MT * RV_WARP_FLOATS;
     // store staging of this warp: 2 x [32 rows][128 B], SWIZZLE_128B
     const uint32_t stg = smem_base + (uint32_t)S * stage_bytes + (uint32_t)(warp - 2) * 2u * 4096u;
     int nstore = 0;  // TMA stores issued by this warp (lane 0 tracks the bulk groups)
@@ -718,6 +725,7 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : THREADS, 1)
         int c0 = 0;
         if (p.c_tma) {
           for (; c0 + 32 <= BN && n0 + c0 < p.N; c0 += 32) {
+            if (((c0 >> 5) % EG) != eg) continue;   // the warps of a lane quarter take the 32-column chunks in turn
             float v[32];
             tmem_ld16(tbase + (uint32_t)c0, v);
             tmem_ld16(tbase + (uint32_t)c0 + 16u, v + 16);
@@ -755,6 +763,7 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : THREADS, 1)
         float* crow = p.C + (long)row * p.ldc + n0;
         for (; c0 < BN; c0 += 16) {
           if (n0 + c0 >= p.N) break;  // warp-uniform
+          if (((c0 >> 4) % EG) != eg) continue;
           float v[16];
           tmem_ld16(tbase + (uint32_t)c0, v);  // warp-collective
           if (row < p.M) {
@@ -919,7 +928,11 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   p.ksteps_total = ceil_div(K, BK);
   const size_t stage_bytes = (size_t)MT * BM * BK * 4 + (size_t)p.b_rows * BK * 4;
   p.rv_smem = (p.epi.rowscale != nullptr && p.epi.L >= 16) ? 1 : 0;
-  const size_t rv_bytes = p.rv_smem ? (size_t)4 * MT * RV_WARP_FLOATS * sizeof(float) : 0;
+  static const int env_ew = getenv("EBK_GEMM_EPI_WARPS") ? atoi(getenv("EBK_GEMM_EPI_WARPS")) : 0;   // experiments
+  p.epi_warps = (env_ew == 4 || env_ew == 8) ? env_ew
+                : ((p.epi.rowscale != nullptr || p.epi.drop.on()) && MT == 1 && !pair) ? 8 : 4;
+  const size_t STG_BYTES = (size_t)p.epi_warps * STG_WARP_BYTES;
+  const size_t rv_bytes = p.rv_smem ? (size_t)p.epi_warps * MT * RV_WARP_FLOATS * sizeof(float) : 0;
   p.c_tma = (ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
   const size_t budget = 226 * 1024 - 1024 - STG_BYTES - rv_bytes;   // 227 KB per CTA minus barriers / alignment slack
   int stages = (int)(budget / stage_bytes);
@@ -959,7 +972,7 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(64 + 32 * p.epi_warps);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
