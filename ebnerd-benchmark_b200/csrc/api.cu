@@ -491,10 +491,9 @@ extern "C" int ebk_seqenc_bwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
     } else {
     EBK_PROF(T_POOL_BWD, attpool_bwd_fused(d->n_seq, d->L, D, d->att, ws.y0, ws.hbuf, attq, ws.w, d_out, ws.da, ws.dpre,
                                            ws.colpart, st));
-    // db += sum_r dpre_r ; dq += sum_r h_r da_r   (second, deterministic stage over the per-sequence partials)
-    EBK_PROF(T_COLSUM, colsum_accum2_ws(d->n_seq, 2 * d->att, d->att, ws.colpart, 2 * d->att, dattb, dattq, ws.colsum2, st));
-    // dW += X^T dpre
-    EBK_PROF(T_ATT_WGRAD, gemm_tma(ws.y0, D, true, ws.dpre, d->att, false, dattW, d->att, D, d->att, R, 1.0f, 1.0f, st, -1));
+    // (the AttLayer2 parameter gradients -- db, dq, dW -- only need y0 / dpre / colpart, which stay valid: they are
+    // computed at the END of this call, behind the table-gradient scatter, so that under data parallel they overlap the
+    // table gradient's reduce-scatter together with the QKV weight gradient)
     // dY0 = tf32(dropout2'(w_t d_out + dpre W^T)): pooling term, dropout backward and the rounding for the
     // attention kernel all happen in the GEMM epilogue
     const GemmEpilogue dy_epi{ws.w, d_out, D, d->L, drop2, D, true};
@@ -520,6 +519,12 @@ extern "C" int ebk_seqenc_bwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
       if (tok && d_table) EBK_PROF(T_SCATTER, scatter_rows_add(R, d->Din, d->V, tok, dx, drop1, d_table, st));
     }
     if (tok && table_grad_event) EBK_CUDA(cudaEventRecord(table_grad_event, st));
+    if (pool) {
+      // db += sum_r dpre_r ; dq += sum_r h_r da_r   (second, deterministic stage over the per-sequence partials)
+      EBK_PROF(T_COLSUM, colsum_accum2_ws(d->n_seq, 2 * d->att, d->att, ws.colpart, 2 * d->att, dattb, dattq, ws.colsum2, st));
+      // dW += X^T dpre
+      EBK_PROF(T_ATT_WGRAD, gemm_tma(ws.y0, D, true, ws.dpre, d->att, false, dattW, d->att, D, d->att, R, 1.0f, 1.0f, st, -1));
+    }
     // dWqkv += X^T dQKV  (X = dropout1(gather)); deferred mode: on the side stream, behind the dgrad GEMM
     if (defer_wgrad && tok != nullptr) {
       EBK_TRY(side_stream_init());

@@ -36,8 +36,11 @@ class hp(hparams_nrms):
 
 
 rng = np.random.default_rng(0)
-beh, articles = synthetic_frames(rng, 32 * 4 * world + 40)        # 4 global steps per epoch + a tail that is dropped
-n_train = 32 * 4 * world + 8
+# 4 global steps per epoch + ONE more full batch that cannot be shared out and is dropped.  (All batches are full: the
+# per-rank loss scale 1/(B*world) makes the summed gradient the global-batch mean only when every rank's B is the same;
+# a ragged batch inside a global step would be weighted like a full one.)
+beh, articles = synthetic_frames(rng, 32 * (4 * world + 1) + 40)
+n_train = 32 * (4 * world + 1)
 tr = {k: v[:n_train] for k, v in beh.items()}
 va = {k: v[n_train:] for k, v in beh.items()}
 kw = dict(article_dict=articles, history_column="hist", unknown_representation="zeros", batch_size=32)
@@ -63,20 +66,25 @@ ok = True
 all_seen = [None] * world
 dist.all_gather_object(all_seen, seen)
 per_epoch = (len(train) // world)
-ok &= all(len(s) == 2 * per_epoch for s in all_seen)
+checks = {}
+checks["shares_len"] = all(len(s) == 2 * per_epoch for s in all_seen)
+ok &= checks["shares_len"]
 for e in range(2):
     got = sorted(i for s in all_seen for i in s[e * per_epoch:(e + 1) * per_epoch])
-    ok &= len(set(got)) == len(got) == per_epoch * world
+    checks[f"disjoint_epoch{e}"] = len(set(got)) == len(got) == per_epoch * world
+    ok &= checks[f"disjoint_epoch{e}"]
 # (2) identical logs
 logs = [None] * world
 dist.all_gather_object(logs, hist.history)
-ok &= all(l == logs[0] for l in logs)
+checks["logs_identical"] = all(l == logs[0] for l in logs)
+ok &= checks["logs_identical"]
 # (3) identical weights
 w = m.model.get_weights()
 flat = torch.from_numpy(np.concatenate([a.ravel() for a in w])).cuda()
 others = [torch.empty_like(flat) for _ in range(world)]
 dist.all_gather(others, flat)
-ok &= all(bool(torch.equal(others[0], o)) for o in others)
+checks["weights_identical"] = all(bool(torch.equal(others[0], o)) for o in others)
+ok &= checks["weights_identical"]
 msg = ""
 if rank == 0:
     # (4) single-GPU run over the merged batches
@@ -96,16 +104,19 @@ if rank == 0:
             y = np.concatenate([p[1] for p in parts])
             solo.model.train_on_batch((his, pred), y)
     dev = max(float(np.abs(a - b).mean()) for a, b in zip(w, solo.model.get_weights()))
-    ok &= dev < 2e-6
+    checks["solo_match"] = dev < 2e-6
+    ok &= checks["solo_match"]
     # (5) the DP checkpoint restores a complete single-GPU model
     back = NRMSModel(hp, word2vec_embedding=table.copy(), seed=3)
     back._engine.world, back._engine.rank = 1, 0
     back.model.load_weights(ck.filepath)
-    ok &= all(np.array_equal(a, b) for a, b in zip(w, back.model.get_weights()))
-    ok &= back._engine.step_count == 2 * per_epoch and float(back._engine.params.m.abs().sum()) > 0
+    checks["ckpt_weights"] = all(np.array_equal(a, b) for a, b in zip(w, back.model.get_weights()))
+    checks["ckpt_adam"] = back._engine.step_count == 2 * per_epoch and float(back._engine.params.m.abs().sum()) > 0
     nz = float((back._engine.params.v[: 300 * 32] != 0).float().mean())     # gathered from BOTH shards
-    ok &= nz > 0.5
-    msg = f"mean|dp - solo| {dev:.2e}, adam-v coverage {nz:.2f}, loss {hist.history['loss']}, val_auc {hist.history['val_auc']}"
+    checks["ckpt_adam_coverage"] = nz > 0.5
+    ok &= checks["ckpt_weights"] and checks["ckpt_adam"] and checks["ckpt_adam_coverage"]
+    msg = f"checks {checks} mean|dp - solo| {dev:.2e}, adam-v coverage {nz:.2f}, loss {hist.history['loss']}, val_auc {hist.history['val_auc']}"
+print(f"rank {rank}: ok={ok} {checks if rank else msg}", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
