@@ -471,6 +471,32 @@ def run_ours(args, w, wname):
     os.environ.pop("EBK_NO_GRAPH", None)
     sync_all()
 
+    # ---- scorer path (model.scorer.predict over eval-mode batches, reference ebnerd_nrms.py:287-348): the loader
+    # repeats the history once per candidate; distinct articles / histories are encoded once, 3xTF32 arithmetic ----
+    scorer = None
+    if world == 1 and w["kind"] == "nrms":     # (single GPU only: inference after sharded training is a collective)
+        srng = np.random.default_rng(SEED + 99)
+        n_imp, inview, pool_n = 64, 11, 20000
+        pool = srng.integers(0, w["V"], (pool_n, w["T"]), dtype=np.int32)
+        eval_batches = []
+        for _ in range(4):
+            hist = pool[srng.integers(0, pool_n, (n_imp, w["H"]))]                      # [n_imp, H, T]
+            his = np.repeat(hist, inview, axis=0)                                       # eval mode: [sumN, H, T]
+            pred = pool[srng.integers(0, pool_n, n_imp * inview)][:, None, :]            # [sumN, 1, T]
+            eval_batches.append((his, pred))
+        for b in eval_batches[:2]:
+            model.scorer.predict_on_batch(b)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_calls = 12
+        for i in range(n_calls):
+            model.scorer.predict_on_batch(eval_batches[i % 4])     # host arrays in, numpy scores out
+        dt = time.perf_counter() - t0
+        scorer = {"candidates_per_s": n_calls * n_imp * inview / dt, "impressions_per_s": n_calls * n_imp / dt,
+                  "ms_per_batch": 1e3 * dt / n_calls, "batch": {"impressions": n_imp, "inview": inview, "rows": n_imp * inview},
+                  "note": "model.scorer.predict_on_batch on eval-mode host batches (history repeated per candidate by the "
+                          "loader, encoded once here), wall clock incl. H2D of ids and D2H of scores"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and w["kind"] == "nrms":
         r = cpu_port_run(w, 2, 1, B)
@@ -524,6 +550,7 @@ def run_ours(args, w, wname):
             "kernel_roofline_frac": {k: round(kernel_roofline(k, prof, models, pk, step_prof_ms, world)["frac"], 3)
                                      for k in prof if k in models},
             "cpu_baseline": cpu,
+            "scorer": scorer,
         }
         if world > 1:
             line["comm_ms_exposed"] = round(ms_step - step_prof_ms, 4)

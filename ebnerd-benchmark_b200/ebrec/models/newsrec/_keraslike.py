@@ -346,6 +346,12 @@ class KerasLikeModel:
                 vlogs = self.evaluate(validation_data, verbose=0, return_dict=True)
                 logs.update({f"val_{k}": v for k, v in vlogs.items()})
             logs["lr"] = float(self._engine.lr)
+            if world > 1:
+                # every rank evaluated the validation set itself; atomics-order noise in the last bits must not let
+                # callbacks (EarlyStopping, ReduceLROnPlateau) decide differently per rank: rank 0's logs are THE logs
+                box = [logs]
+                torch.distributed.broadcast_object_list(box, src=0)
+                logs = box[0]
             if verbose:
                 dt = time.time() - t0
                 msg = " - ".join(f"{k}: {v:.4f}" for k, v in logs.items() if k != "lr")
