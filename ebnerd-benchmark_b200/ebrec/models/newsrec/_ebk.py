@@ -27,7 +27,7 @@ SYMBOLS = [
     "ebk_seqenc_workspace_bytes", "ebk_seqenc_fwd", "ebk_seqenc_bwd", "ebk_seqenc_fwd_opts", "ebk_seqenc_bwd_opts",
     "ebk_join_deferred", "ebk_seqenc_uses_tma", "ebk_ipc_export", "ebk_ipc_open",
     "ebk_score_softmax_ce", "ebk_score_loss", "ebk_score_sigmoid", "ebk_adam_keras_step", "ebk_adam_keras_step_p",
-    "ebk_embed_adam_step_p",
+    "ebk_embed_adam_step_p", "ebk_dp_token_flags", "ebk_adam_pull_step",
     "ebk_embed_adam_workspace_bytes", "ebk_embed_adam_step",
     "ebk_dense_workspace_bytes", "ebk_dense_fwd", "ebk_dense_bwd", "ebk_sumsq_accum",
     "ebk_attlayer_workspace_bytes", "ebk_attlayer_fwd", "ebk_attlayer_bwd",
@@ -135,6 +135,8 @@ def lib() -> C.CDLL:
     l.ebk_adam_keras_step.argtypes = [vp, vp, vp, vp, sz, f32, f64, f64, f32, C.c_int, vp]
     l.ebk_adam_keras_step_p.argtypes = [vp, vp, vp, vp, sz, f32, vp, f64, f64, f32, C.c_int, vp]
     l.ebk_embed_adam_step_p.argtypes = [i32, i32, i32, vp, vp, f32, u64, vp, vp, vp, vp, f32, vp, f64, f64, f32, vp, sz, vp]
+    l.ebk_dp_token_flags.argtypes = [i32, i32, vp, vp, sz, vp]
+    l.ebk_adam_pull_step.argtypes = [vp, vp, vp, C.POINTER(vp), vp, sz, i32, i32, i32, sz, sz, f32, vp, f64, f64, f32, vp]
     l.ebk_embed_adam_workspace_bytes.restype = sz
     l.ebk_embed_adam_workspace_bytes.argtypes = [i32, i32]
     l.ebk_embed_adam_step.argtypes = [i32, i32, i32, vp, vp, f32, u64, vp, vp, vp, vp, f32, f64, f64, f32, vp, sz, vp]

@@ -405,6 +405,11 @@ class NRMSEngine:
             torch.cuda.current_stream().wait_event(dp["zeroed"])  # last step's clearing of the table gradient
             opts.table_grad_event = C.c_void_p(dp["table_grad"].cuda_event)
             dp["armed"] = True
+            if self._dp_pull():
+                # which table rows this rank's gradient touches (one byte per row): the owners pull only those
+                fl = self._dp_flags()
+                _ebk.check(lib.ebk_dp_token_flags(tok_all.numel(), self.V, _ebk.ptr(tok_all), _ebk.ptr(fl["local"]),
+                                                  fl["v_pad"], _ebk.stream()))
         _ebk.check(lib.ebk_seqenc_bwd_opts(C.byref(dn), C.byref(opts), _ebk.ptr(tok_all), _ebk.ptr(P.p("table")),
                                            _ebk.ptr(P.p("news_Wqkv")), _ebk.ptr(P.p("news_attW")),
                                            _ebk.ptr(P.p("news_attb")), _ebk.ptr(P.p("news_attq")), int(training),
@@ -483,6 +488,35 @@ class NRMSEngine:
             if getattr(self, "dp_prof", None) is not None:
                 self._apply_adam_dp_profiled(dp, tbl, shard, lo, gsh, alpha)
                 return
+            if self._dp_pull():
+                # Gradient reduction fused into the Adam pass over NVLink peer memory (csrc/dp_pull.cu): no
+                # reduce-scatter.  Side stream: [all-gather of the touched-row flags (250 KB per rank; it also orders
+                # every rank's scatter before any pull)] -> [pull + Adam on this rank's shard]; main stream meanwhile:
+                # the weight-gradient GEMMs, then all-reduce + dense Adam of the small parameters.
+                pt, fl = self._peer_tables(tbl), self._dp_flags()
+                side.wait_event(dp["table_grad"])
+                with torch.cuda.stream(side):
+                    dist.all_gather_into_tensor(fl["all"].view(-1), fl["local"])
+                    _ebk.check(lib.ebk_adam_pull_step(_ebk.ptr(P.theta), _ebk.ptr(P.m), _ebk.ptr(P.v), pt["grad_ptrs"],
+                                                      _ebk.ptr(fl["all"]), fl["v_pad"], self.world, self.rank, self.E, lo,
+                                                      shard, alpha, None, self.beta1, self.beta2, self.eps,
+                                                      C.c_void_p(side.cuda_stream)))
+                    dp["pulled"].record(side)
+                w_ar = dist.all_reduce(P.grad[tbl:], async_op=True)
+                w_ar.wait()
+                tt, tg, tm, tv = P.theta[tbl:], P.grad[tbl:], P.m[tbl:], P.v[tbl:]
+                _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(tt), _ebk.ptr(tg), _ebk.ptr(tm), _ebk.ptr(tv), P.n - tbl, alpha,
+                                                   self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
+                main.wait_event(dp["pulled"])
+                # orders every rank's pull + Adam before any rank's next gather AND before any rank clears the
+                # gradient buffer its peers have been reading
+                self._table_stale = True
+                dist.all_reduce(self._buf("dp_fence", (1,)))
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    P.grad[:tbl].zero_()
+                    dp["zeroed"].record(side)
+                return
             side.wait_event(dp["table_grad"])
             with torch.cuda.stream(side):
                 w_rs = dist.reduce_scatter_tensor(gsh, P.grad[:tbl], async_op=True)
@@ -542,6 +576,22 @@ class NRMSEngine:
             rec[name] = (a, b)
 
         main.wait_event(dp["table_grad"])
+        if self._dp_pull():
+            pt, fl = self._peer_tables(tbl), self._dp_flags()
+            timed("all_gather_row_flags", lambda: dist.all_gather_into_tensor(fl["all"].view(-1), fl["local"]))
+            timed("adam_pull_over_nvlink", lambda: _ebk.check(lib.ebk_adam_pull_step(
+                _ebk.ptr(P.theta), _ebk.ptr(P.m), _ebk.ptr(P.v), pt["grad_ptrs"], _ebk.ptr(fl["all"]), fl["v_pad"], self.world,
+                self.rank, self.E, lo, shard, alpha, None, self.beta1, self.beta2, self.eps, _ebk.stream())))
+            timed("all_reduce_dense_grad", lambda: dist.all_reduce(P.grad[tbl:]))
+            tt, tg, tm, tv = P.theta[tbl:], P.grad[tbl:], P.m[tbl:], P.v[tbl:]
+            _ebk.check(lib.ebk_adam_keras_step(_ebk.ptr(tt), _ebk.ptr(tg), _ebk.ptr(tm), _ebk.ptr(tv), P.n - tbl, alpha,
+                                               self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
+            self._table_stale = True
+            timed("fence_all_reduce", lambda: dist.all_reduce(self._buf("dp_fence", (1,))))
+            P.grad[:tbl].zero_()
+            dp["zeroed"].record(main)
+            self.dp_prof.append(rec)
+            return
         timed("reduce_scatter_table_grad", lambda: dist.reduce_scatter_tensor(gsh, P.grad[:tbl]))
         P.grad[:tbl].zero_()
         dp["zeroed"].record(main)
@@ -579,23 +629,28 @@ class NRMSEngine:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag) == 0:
             return None
+        self._peers = {"ptrs": self._ipc_map(self.params.theta), "grad_ptrs": self._ipc_map(self.params.grad),
+                       "shard": tbl // self.world}
+        return self._peers
+
+    def _ipc_map(self, tensor: torch.Tensor):
+        """This process's mappings of every rank's copy of `tensor` (CUDA IPC; own pointer for the own rank)."""
+        dist, lib = torch.distributed, _ebk.lib()
         handle = (C.c_char * 64)()
         off = C.c_size_t(0)
-        _ebk.check(lib.ebk_ipc_export(_ebk.ptr(self.params.theta), C.cast(handle, C.c_void_p), C.byref(off)))
-        mine = (bytes(handle.raw), int(off.value))
+        _ebk.check(lib.ebk_ipc_export(_ebk.ptr(tensor), C.cast(handle, C.c_void_p), C.byref(off)))
         allh = [None] * self.world
-        dist.all_gather_object(allh, mine)
+        dist.all_gather_object(allh, (bytes(handle.raw), int(off.value)))
         ptrs = []
         for r, (hb, o) in enumerate(allh):
             if r == self.rank:
-                ptrs.append(self.params.theta.data_ptr())
+                ptrs.append(tensor.data_ptr())
             else:
                 out = C.c_void_p()
                 buf = C.create_string_buffer(hb, 64)
                 _ebk.check(lib.ebk_ipc_open(C.cast(buf, C.c_void_p), o, C.byref(out)))
                 ptrs.append(out.value)
-        self._peers = {"ptrs": (C.c_void_p * self.world)(*ptrs), "shard": tbl // self.world}
-        return self._peers
+        return (C.c_void_p * self.world)(*ptrs)
 
     def _peer_opts(self):
         """Options of a TRAINING forward: gather table rows from the owners' shards while this rank's replica is
@@ -639,14 +694,34 @@ class NRMSEngine:
         for buf in (P.m, P.v):
             torch.distributed.all_gather_into_tensor(buf[:n], buf[lo: lo + shard].clone())
 
+    def _dp_pull(self) -> bool:
+        """Fused pull-reduce Adam for the table (data parallel on one NVSwitch box; EBK_DP_PULL=0 -> reduce-scatter)."""
+        ok = self.__dict__.get("_dp_pull_ok")
+        if ok is None:
+            tbl = self.params.offsets.get("news_Wqkv", 0)
+            ok = (os.environ.get("EBK_DP_PULL", "1") != "0" and self.world > 1 and tbl > 0
+                  and tbl % (4 * self.world) == 0 and self._peer_tables(tbl) is not None)
+            self._dp_pull_ok = ok
+        return ok
+
+    def _dp_flags(self) -> dict:
+        fl = self.__dict__.get("_dp_flag_bufs")
+        if fl is None:
+            v_pad = (self.V + 255) // 256 * 256
+            fl = {"v_pad": v_pad, "local": torch.zeros(v_pad, dtype=torch.uint8, device=self.device),
+                  "all": torch.zeros((self.world, v_pad), dtype=torch.uint8, device=self.device)}
+            self._dp_flag_bufs = fl
+        return fl
+
     def _dp_state(self) -> dict:
         """Side stream and events of the overlapped data-parallel optimizer step."""
         st = getattr(self, "_dp", None)
         if st is None:
             st = {"side": torch.cuda.Stream(device=self.device), "table_grad": torch.cuda.Event(),
-                  "zeroed": torch.cuda.Event(), "armed": False}
+                  "zeroed": torch.cuda.Event(), "pulled": torch.cuda.Event(), "armed": False}
             st["table_grad"].record()   # instantiate the CUDA events
             st["zeroed"].record()
+            st["pulled"].record()
             self._dp = st
         return st
 

@@ -323,6 +323,24 @@ int ebk_embed_adam_step(int32_t R, int32_t E, int32_t V, const int32_t* tok, con
                         double beta1, double beta2, float eps, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Data parallel, rank-sharded embedding table: gradient reduction FUSED into the Adam pass over NVLink peer memory
+ * (no reference counterpart -- the reference is single-device; replaces reduce-scatter + ebk_adam_keras_step on the
+ * shard).  Every rank scatter-adds its table gradient into its own dense [V, E] buffer (ebk_seqenc_bwd) and marks the
+ * rows it touched (ebk_dp_token_flags: flags[v] = 1 for every token id in tok, v_pad >= V bytes, zeroed first); the
+ * flags of all ranks are all-gathered into flags_all [world, v_pad].  ebk_adam_pull_step then updates floats
+ * [lo_float, lo_float + n_float) of theta / m / v (this rank's shard of the table): the gradient of every 16-byte chunk
+ * is the sum, in rank order, of the chunks of exactly those ranks whose flag for the row is set, read from
+ * grads[p] (this process's CUDA-IPC mapping of rank p's gradient buffer; grads[rank] is local and the consumed local
+ * chunks are cleared).  Same Keras-form arithmetic as ebk_adam_keras_step.  The caller orders it after every rank's
+ * scatter (the flags all-gather does) and keeps peers from clearing their buffers until every owner has pulled.
+ * ---------------------------------------------------------------------------------- */
+int ebk_dp_token_flags(int32_t R, int32_t V, const int32_t* tok, uint8_t* flags, size_t v_pad, void* stream);
+int ebk_adam_pull_step(float* theta, float* m, float* v, const void* const* grads, const uint8_t* flags_all,
+                       size_t v_pad, int32_t world, int32_t rank, int32_t E, size_t lo_float, size_t n_float,
+                       float alpha, const ebk_step_params* step_dev, double beta1, double beta2, float eps,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): number of kernels this library has launched so far, and an
  * optional per-kernel timer (CUDA events recorded on the launching stream around every
  * internal launch while enabled).  Slots [0, ebk_prof_num_tags()) are named by
