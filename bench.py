@@ -113,7 +113,7 @@ def kernel_models(w, B, nparam, world=1):
         # data parallel: dense Adam over THIS RANK's 1/world shard of the table (theta, g, m, v read; theta, m, v
         # written) + the dense pass over the remaining parameters on every rank
         adam = 7.0 * f * tbl / world + 8.0 * f * rest
-    return {
+    models = {
         "news.qkv_gemm_fwd": ("tensor", 2.0 * R * E * 3 * D),
         "news.qkv_dgrad_gemm": ("tensor", 2.0 * R * E * 3 * D),
         "news.qkv_wgrad_gemm": ("tensor", 2.0 * R * E * 3 * D),
@@ -126,9 +126,12 @@ def kernel_models(w, B, nparam, world=1):
         "news.att_wgrad_gemm": ("hbm", f * R * (D + att)),
         "news.attpool_fwd": ("hbm", f * R * (2 * att + D)),
         "news.attpool_bwd": ("hbm", f * R * (D + 2 * att)),
-        # dense [V, E] gradient scatter of the data-parallel path: dX rows read, gradient rows read-modify-written
-        "news.embed_scatter": ("hbm", 3.0 * f * R * E) if world > 1 else ("hbm", f * R * E),
     }
+    if world > 1:
+        # dense [V, E] gradient scatter of the data-parallel path: dX rows read, gradient rows read-modify-written
+        # (on one GPU this profiler slot only holds the token-CSR build of the fused Adam: no byte model)
+        models["news.embed_scatter"] = ("hbm", 3.0 * f * R * E)
+    return models
 
 
 def traffic_table():
@@ -431,7 +434,7 @@ def run_ours(args, w, wname):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    e2e_fit(min(3, args.warmup))
+    e2e_fit(max(5, args.warmup))      # (also fills the 4-slot pinned staging ring)
     e2e_all = [timed_fit(args.steps) for _ in range(REPEATS)]
     e2e_ms = statistics.median(e2e_all)
     # the synchronous variant (train_on_batch returns float(loss): the host waits for every step before preparing

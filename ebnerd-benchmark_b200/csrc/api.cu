@@ -242,6 +242,13 @@ extern "C" int ebk_ipc_open(const void* handle64, size_t offset, void** out) {
   *out = reinterpret_cast<char*>(base) + offset;
   return EBK_OK;
 }
+// plain asynchronous device-to-device copy (peer mappings included): lets a rank refresh its replica of the
+// rank-sharded table from its peers' memory WITHOUT a collective (inference on one rank after sharded training)
+extern "C" int ebk_memcpy_async(void* dst, const void* src, size_t bytes, void* stream) {
+  EBK_CHECK_ARG(bytes == 0 || (dst && src), "memcpy_async: null pointer");
+  if (bytes) EBK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return EBK_OK;
+}
 extern "C" long long ebk_launch_count(void) { return g_launches.load(); }
 extern "C" int ebk_prof_enable(int on) {
   g_prof = on != 0;

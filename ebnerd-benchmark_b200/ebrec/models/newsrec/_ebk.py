@@ -25,7 +25,7 @@ LOSS_BINARY_CE = 1        # hparams.loss "log_loss"
 SYMBOLS = [
     "ebk_last_error", "ebk_version", "ebk_device_ok",
     "ebk_seqenc_workspace_bytes", "ebk_seqenc_fwd", "ebk_seqenc_bwd", "ebk_seqenc_fwd_opts", "ebk_seqenc_bwd_opts",
-    "ebk_join_deferred", "ebk_seqenc_uses_tma", "ebk_ipc_export", "ebk_ipc_open",
+    "ebk_join_deferred", "ebk_seqenc_uses_tma", "ebk_ipc_export", "ebk_ipc_open", "ebk_memcpy_async",
     "ebk_score_softmax_ce", "ebk_score_loss", "ebk_score_sigmoid", "ebk_adam_keras_step", "ebk_adam_keras_step_p",
     "ebk_embed_adam_step_p", "ebk_dp_token_flags", "ebk_adam_pull_step",
     "ebk_embed_adam_workspace_bytes", "ebk_embed_adam_step",
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
     l.ebk_seqenc_uses_tma.argtypes = [dp]
     l.ebk_ipc_export.argtypes = [vp, vp, C.POINTER(sz)]
     l.ebk_ipc_open.argtypes = [vp, sz, C.POINTER(vp)]
+    l.ebk_memcpy_async.argtypes = [vp, vp, sz, vp]
     ddp = C.POINTER(DenseDesc)
     l.ebk_dense_workspace_bytes.restype = sz
     l.ebk_dense_workspace_bytes.argtypes = [ddp]

@@ -667,15 +667,24 @@ class NRMSEngine:
         return _ebk.SeqEncOpts(0, None, pt["ptrs"], self.world, pt["shard"], None)
 
     def _sync_table(self) -> None:
-        """Make this rank's replica of the table current (all-gather of the owners' shards); needed before any
-        inference / validation forward or weight export after sharded training steps.  Collective: every rank
-        reaches it (validation and checkpointing run in lockstep on all ranks)."""
+        """Make this rank's replica of the table current; needed before any inference / validation forward or weight
+        export after sharded training steps.  NOT a collective: the owners' shards are copied straight out of the
+        peers' memory through the CUDA-IPC mappings (every rank's Adam of the last step is ordered before this by the
+        step's fence), so `predict` / `get_weights` may be called on one rank alone."""
         if self.world > 1 and getattr(self, "_table_stale", False):
             P = self.params
             tbl = P.offsets["news_Wqkv"]
             shard = tbl // self.world
-            th = P.theta[self.rank * shard: (self.rank + 1) * shard]
-            torch.distributed.all_gather_into_tensor(P.theta[:tbl], th)
+            pt = self._peers if getattr(self, "_peers", None) else None
+            if pt is not None:
+                lib = _ebk.lib()
+                for r in range(self.world):
+                    if r != self.rank:
+                        _ebk.check(lib.ebk_memcpy_async(C.c_void_p(P.theta.data_ptr() + 4 * r * shard),
+                                                        C.c_void_p(pt["ptrs"][r] + 4 * r * shard), 4 * shard, _ebk.stream()))
+            else:
+                th = P.theta[self.rank * shard: (self.rank + 1) * shard]
+                torch.distributed.all_gather_into_tensor(P.theta[:tbl], th)
             self._table_stale = False
 
     def sync_optimizer_state(self) -> None:

@@ -156,6 +156,9 @@ int ebk_seqenc_uses_tma(const ebk_seqenc_desc* d);
  * byte transport. */
 int ebk_ipc_export(const void* ptr, void* handle64, size_t* offset);
 int ebk_ipc_open(const void* handle64, size_t offset, void** out);
+/* cudaMemcpyAsync(device to device) on `stream`; src may be a peer mapping from ebk_ipc_open: a rank can refresh its
+ * replica of the rank-sharded table from its peers' memory without entering a collective. */
+int ebk_memcpy_async(void* dst, const void* src, size_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Dense(+ReLU) -> [BatchNormalization] -> [Dropout] layer of the NRMSDocVec news encoder
