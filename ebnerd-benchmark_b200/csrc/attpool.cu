@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(PT) attpool_bwd_fused_kernel(int L, int D, int
 }
 
 // Two-stage deterministic column reduction: partial[blk, j] then out[j] += sum_blk.
-constexpr int CS_ROWS = 256;
+constexpr int CS_ROWS = 32;   // rows per partial block (32: enough blocks to hide the load latency even for the 256-row user encoder)
 __global__ void colsum_partial_kernel(int R, int Ncols, const float* __restrict__ X, int ldx,
                                       const float* __restrict__ coef, float* __restrict__ partial) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
