@@ -90,23 +90,32 @@ __global__ void __launch_bounds__(PT) attpool_fwd_fast_kernel(int L, int D, int 
                                                                float* __restrict__ hbuf, const float* __restrict__ attb,
                                                                const float* __restrict__ attq, float* __restrict__ w,
                                                                float* __restrict__ out, int out_ld) {
-  extern __shared__ __align__(16) float y_s[];   // [L, D]
+  extern __shared__ __align__(16) float sm_f[];   // h rows [L, att] | y rows [L, D]
   __shared__ float a_s[64];
   __shared__ float w_s[64];
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = PT / 32;
   const int D4 = D >> 2, A4 = att >> 2;
+  float* h_s = sm_f;
+  float* y_s = sm_f + (size_t)L * att;
+  // every HBM read of this sequence is issued NOW: first the h rows (needed first), then the y rows
+  const float4* hsrc = reinterpret_cast<const float4*>(hbuf + (long)n * L * att);
+  for (int i = threadIdx.x; i < L * A4; i += PT) cp_async16(reinterpret_cast<float4*>(h_s) + i, hsrc + i);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   const float4* ysrc = reinterpret_cast<const float4*>(y0 + (long)n * L * D);
   for (int i = threadIdx.x; i < L * D4; i += PT) cp_async16(reinterpret_cast<float4*>(y_s) + i, ysrc + i);
   asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 1;" ::: "memory");   // h rows have landed (this thread's copies) ...
+  __syncthreads();                                        // ... and everybody else's
   for (int t = warp; t < L; t += nwarp) {
-    float4* hrow = reinterpret_cast<float4*>(hbuf + ((long)n * L + t) * att);
+    float4* hrow_g = reinterpret_cast<float4*>(hbuf + ((long)n * L + t) * att);
+    const float4* hrow = reinterpret_cast<const float4*>(h_s + (size_t)t * att);
     float acc = 0.0f;
     for (int j = lane; j < A4; j += 32) {
       float4 h = hrow[j];
       const float4 bb = __ldg(reinterpret_cast<const float4*>(attb) + j), qq = __ldg(reinterpret_cast<const float4*>(attq) + j);
       h.x = tanhf(h.x + bb.x); h.y = tanhf(h.y + bb.y); h.z = tanhf(h.z + bb.z); h.w = tanhf(h.w + bb.w);
-      hrow[j] = h;
+      hrow_g[j] = h;     // tanh values: what the backward pass reads
       acc = fmaf(h.x, qq.x, fmaf(h.y, qq.y, fmaf(h.z, qq.z, fmaf(h.w, qq.w, acc))));
     }
     acc = warp_sum(acc);
@@ -201,23 +210,30 @@ __global__ void __launch_bounds__(PT) attpool_bwd_fused_kernel(int L, int D, int
                                                                 const float* __restrict__ d_out, int dout_ld,
                                                                 float* __restrict__ da, float* __restrict__ dpre,
                                                                 float* __restrict__ colpart, int h_in_smem) {
-  extern __shared__ __align__(16) float h_s[];   // [L, att] (when launched with shared memory: att % 4 == 0)
+  extern __shared__ __align__(16) float h_s[];   // [L, att] | [L, D] (when launched with shared memory)
   __shared__ float dw_s[64];
   __shared__ float da_s[64];
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = PT / 32;
   const float4* g4 = reinterpret_cast<const float4*>(d_out + (long)n * dout_ld);
   const int D4 = D >> 2;
-  if (h_in_smem) {   // issue the h rows now: they arrive while the X.g pass streams y0
+  float* y_s = h_s + (size_t)L * att;
+  if (h_in_smem) {   // every HBM read of this sequence is issued now: the y rows (needed first), then the h rows
+    const float4* ysrc = reinterpret_cast<const float4*>(y0 + (long)n * L * D);
+    for (int i = threadIdx.x; i < L * D4; i += PT) cp_async16(reinterpret_cast<float4*>(y_s) + i, ysrc + i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     const float4* hsrc = reinterpret_cast<const float4*>(hbuf + (long)n * L * att);
     for (int i = threadIdx.x; i < L * (att >> 2); i += PT) cp_async16(reinterpret_cast<float4*>(h_s) + i, hsrc + i);
     asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
   }
   for (int t = warp; t < L; t += nwarp) {
-    const float4* x4 = reinterpret_cast<const float4*>(y0 + ((long)n * L + t) * D);
+    const float4* x4 = h_in_smem ? reinterpret_cast<const float4*>(y_s + (size_t)t * D)
+                                 : reinterpret_cast<const float4*>(y0 + ((long)n * L + t) * D);
     float acc = 0.0f;
     for (int d = lane; d < D4; d += 32) {
-      const float4 x = __ldg(x4 + d), gd = __ldg(g4 + d);
+      const float4 x = x4[d], gd = __ldg(g4 + d);
       acc = fmaf(x.x, gd.x, fmaf(x.y, gd.y, fmaf(x.z, gd.z, fmaf(x.w, gd.w, acc))));
     }
     acc = warp_sum(acc);
@@ -368,7 +384,7 @@ int attpool_fwd(int n_seq, int L, int D, int att, const float* y0, Dropout drop,
   EBK_CHECK_ARG(L <= 64, "attpool: L=%d > 64", L);
   const int old = out_ld > 0 ? out_ld : D;
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  const size_t ysm = (size_t)L * D * sizeof(float);
+  const size_t ysm = (size_t)L * (D + att) * sizeof(float);   // h rows + y rows of one sequence
   static const bool fast_on = !(getenv("EBK_ATTPOOL_FAST") && atoi(getenv("EBK_ATTPOOL_FAST")) == 0);
   if (fast_on && !drop.on() && D % 4 == 0 && att % 4 == 0 && old % 4 == 0 && ysm <= 96 * 1024 && al(y0) && al(hbuf) &&
       al(attb) && al(attq) && al(out)) {
@@ -401,9 +417,12 @@ int attpool_bwd_fused(int n_seq, int L, int D, int att, const float* y0, const f
   if (dout_ld <= 0) dout_ld = D;
   EBK_CHECK_ARG(L <= 64 && D % 4 == 0 && dout_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0,
                 "attpool: L=%d > 64, or D=%d / dout_ld=%d not multiples of 4", L, D, dout_ld);
-  const size_t hsm = (size_t)L * att * sizeof(float);
+  const size_t hsm = (size_t)L * (att + D) * sizeof(float);   // h rows + y rows of one sequence
   static const bool fast_on = !(getenv("EBK_ATTPOOL_FAST") && atoi(getenv("EBK_ATTPOOL_FAST")) == 0);
-  const bool h_smem = fast_on && att % 4 == 0 && hsm <= 48 * 1024 && (reinterpret_cast<uintptr_t>(hbuf) & 15) == 0;
+  const bool h_smem = fast_on && att % 4 == 0 && hsm <= 96 * 1024 && (reinterpret_cast<uintptr_t>(hbuf) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(y0) & 15) == 0;
+  if (h_smem && hsm > 48 * 1024)
+    EBK_CUDA(cudaFuncSetAttribute(attpool_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   attpool_bwd_fused_kernel<<<n_seq, PT, h_smem ? hsm : 0, st>>>(L, D, att, y0, hbuf, attq, w, d_out, dout_ld, da, dpre, colpart,
                                                                 h_smem ? 1 : 0);
   EBK_LAUNCH_CHECK();

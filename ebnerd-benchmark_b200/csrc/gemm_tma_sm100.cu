@@ -169,8 +169,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  Only used to hand an accumulator buffer (TMEM) back to the MMA warp:
+// that hand-over is ordered by the tcgen05 fences on both sides, no generic-memory data travels with it, so the default
+// .release.cta form is enough (a .release.cluster arrive costs MEMBAR.ALL.GPU + ERRBAR per warp per tile).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -680,6 +683,10 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : MAX_THREADS, 1)
     // store staging of this warp: 2 x [32 rows][128 B], SWIZZLE_128B
     const uint32_t stg = smem_base + (uint32_t)S * stage_bytes + (uint32_t)(warp - 2) * 2u * 4096u;
     int nstore = 0;  // TMA stores issued by this warp (lane 0 tracks the bulk groups)
+    // the rowvec slab is filled with 16-byte cp.async when every address involved is 16-byte aligned (tile origins are
+    // multiples of 16 columns) and N is a multiple of 4, so that no float4 straddles the last column
+    const bool rv_vec = p.rv_smem && p.epi.rowvec != nullptr && (p.epi.rowvec_ld & 3) == 0 && (p.N & 3) == 0 && (BN & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(p.epi.rowvec) & 15) == 0;
     while (cu.valid(n_items)) {
       const int buf = NBUF == 2 ? (t & 1) : 0, use = NBUF == 2 ? (t >> 1) : t;
       const int n0 = cu.n0;
@@ -699,12 +706,25 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : MAX_THREADS, 1)
           const int art0 = row_lo / p.epi.L;
           if (p.rv_smem) {
             const int art_last = (min(row_lo + 31, p.M - 1)) / p.epi.L;
-            for (int a = 0; a < RV_ART; ++a) {
-              const int art = art0 + a;
-              for (int c = lane; c < BN; c += 32) {
-                float x = 0.0f;
-                if (art <= art_last && n0 + c < p.N) x = __ldg(p.epi.rowvec + (long)art * p.epi.rowvec_ld + n0 + c);
-                rv_s[(mt * RV_ART + a) * BN + c] = x;
+            if (rv_vec) {
+              // 16-byte asynchronous copies, none waited for here: the slab lands while this warp waits for the MMAs
+              const int BN4 = BN >> 2;
+              for (int i = lane; i < RV_ART * BN4; i += 32) {
+                const int a = i / BN4, c = (i - a * BN4) << 2, art = art0 + a;
+                const bool ok = art <= art_last && n0 + c < p.N;
+                const float* src = ok ? p.epi.rowvec + (long)art * p.epi.rowvec_ld + n0 + c : p.epi.rowvec;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(rv_s + (mt * RV_ART + a) * BN + c)),
+                             "l"(src), "r"(ok ? 16u : 0u)
+                             : "memory");
+              }
+            } else {
+              for (int a = 0; a < RV_ART; ++a) {
+                const int art = art0 + a;
+                for (int c = lane; c < BN; c += 32) {
+                  float x = 0.0f;
+                  if (art <= art_last && n0 + c < p.N) x = __ldg(p.epi.rowvec + (long)art * p.epi.rowvec_ld + n0 + c);
+                  rv_s[(mt * RV_ART + a) * BN + c] = x;
+                }
               }
             }
             er[mt].rv = rv_s + (mt * RV_ART + (min(row, p.M - 1) / p.epi.L - art0)) * BN;
@@ -712,10 +732,15 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : MAX_THREADS, 1)
             er[mt].rv = p.epi.rowvec + (long)(row / p.epi.L) * p.epi.rowvec_ld + n0;
           }
         }
+        if (rv_vec) asm volatile("cp.async.commit_group;" ::: "memory");
         __syncwarp();
       }
       mbar_wait_backoff(smem_u32(&tfull_bar[buf]), (uint32_t)(use & 1));
       tc_fence_after();
+      if (rv_vec) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+      }
       const bool vec_ok = vec_base && ((n0 & 3) == 0);
       const bool vec8_ok = vec8_base && ((n0 & 7) == 0);
 #pragma unroll
