@@ -107,15 +107,35 @@ __global__ void __launch_bounds__(PT) attpool_fwd_fast_kernel(int L, int D, int 
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 1;" ::: "memory");   // h rows have landed (this thread's copies) ...
   __syncthreads();                                        // ... and everybody else's
+  // this lane's slices of b and q stay in registers for every token (att <= 4 * 32 * PV floats, else re-read per token)
+  constexpr int PV = 2;
+  float4 bb_r[PV], qq_r[PV];
+#pragma unroll
+  for (int u = 0; u < PV; ++u) {
+    const int j = lane + 32 * u;
+    bb_r[u] = j < A4 ? __ldg(reinterpret_cast<const float4*>(attb) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    qq_r[u] = j < A4 ? __ldg(reinterpret_cast<const float4*>(attq) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int t = warp; t < L; t += nwarp) {
     float4* hrow_g = reinterpret_cast<float4*>(hbuf + ((long)n * L + t) * att);
     const float4* hrow = reinterpret_cast<const float4*>(h_s + (size_t)t * att);
     float acc = 0.0f;
-    for (int j = lane; j < A4; j += 32) {
+#pragma unroll
+    for (int u = 0; u < PV; ++u) {
+      const int j = lane + 32 * u;
+      if (j < A4) {
+        float4 h = hrow[j];
+        const float4 bb = bb_r[u], qq = qq_r[u];
+        h.x = tanhf(h.x + bb.x); h.y = tanhf(h.y + bb.y); h.z = tanhf(h.z + bb.z); h.w = tanhf(h.w + bb.w);
+        hrow_g[j] = h;     // tanh values: what the backward pass reads
+        acc = fmaf(h.x, qq.x, fmaf(h.y, qq.y, fmaf(h.z, qq.z, fmaf(h.w, qq.w, acc))));
+      }
+    }
+    for (int j = lane + 32 * PV; j < A4; j += 32) {
       float4 h = hrow[j];
       const float4 bb = __ldg(reinterpret_cast<const float4*>(attb) + j), qq = __ldg(reinterpret_cast<const float4*>(attq) + j);
       h.x = tanhf(h.x + bb.x); h.y = tanhf(h.y + bb.y); h.z = tanhf(h.z + bb.z); h.w = tanhf(h.w + bb.w);
-      hrow_g[j] = h;     // tanh values: what the backward pass reads
+      hrow_g[j] = h;
       acc = fmaf(h.x, qq.x, fmaf(h.y, qq.y, fmaf(h.z, qq.z, fmaf(h.w, qq.w, acc))));
     }
     acc = warp_sum(acc);
@@ -228,11 +248,24 @@ __global__ void __launch_bounds__(PT) attpool_bwd_fused_kernel(int L, int D, int
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
   }
+  // this lane's slice of d_out[n, :] stays in registers for every token (D <= 4 * 32 * GV floats, else re-read per token)
+  constexpr int GV = 4;
+  float4 g_r[GV];
+#pragma unroll
+  for (int u = 0; u < GV; ++u) g_r[u] = lane + 32 * u < D4 ? __ldg(g4 + lane + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int t = warp; t < L; t += nwarp) {
     const float4* x4 = h_in_smem ? reinterpret_cast<const float4*>(y_s + (size_t)t * D)
                                  : reinterpret_cast<const float4*>(y0 + ((long)n * L + t) * D);
     float acc = 0.0f;
-    for (int d = lane; d < D4; d += 32) {
+#pragma unroll
+    for (int u = 0; u < GV; ++u) {
+      const int d = lane + 32 * u;
+      if (d < D4) {
+        const float4 x = x4[d], gd = g_r[u];
+        acc = fmaf(x.x, gd.x, fmaf(x.y, gd.y, fmaf(x.z, gd.z, fmaf(x.w, gd.w, acc))));
+      }
+    }
+    for (int d = lane + 32 * GV; d < D4; d += 32) {
       const float4 x = x4[d], gd = __ldg(g4 + d);
       acc = fmaf(x.x, gd.x, fmaf(x.y, gd.y, fmaf(x.z, gd.z, fmaf(x.w, gd.w, acc))));
     }
@@ -354,6 +387,53 @@ __global__ void embed_rows_kernel(long n4, int E4, int V, const int32_t* __restr
   }
   v.x = round_tf32_bits(v.x); v.y = round_tf32_bits(v.y); v.z = round_tf32_bits(v.z); v.w = round_tf32_bits(v.w);
   xd[i] = v;
+}
+
+// The token gather proper: one warp per row, each lane keeps U independent 16-byte loads in flight (one token-id load
+// per warp instead of one per float4; ncu on the per-float4 kernel: 67 % of the stall samples on the two dependent loads).
+template <bool PEERS>
+__global__ void __launch_bounds__(256) embed_rows_warp_kernel(int R, int E4, int V, const int32_t* __restrict__ tok,
+                                                              const float4* __restrict__ src, Dropout drop,
+                                                              float4* __restrict__ xd, PeerTables peers, long group0) {
+  constexpr int U = 6;
+  const int lane = threadIdx.x & 31;
+  const long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int t = __ldg(tok + r);
+  const bool ok = t >= 0 && t < V;   // ids outside the table read a zero row
+  const long rowbase = (long)t * E4, obase = r * E4;
+  for (int c0 = 0; c0 < E4; c0 += 32 * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c4 = c0 + u * 32 + lane;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && c4 < E4) {
+        const long chunk = rowbase + c4;
+        const float4* p = src + chunk;
+        if (PEERS) {
+          const int owner = (int)(((unsigned long long)chunk * 4ull) / peers.shard_floats);
+          p = reinterpret_cast<const float4*>(peers.p[owner < peers.world ? owner : peers.world - 1]) + chunk;
+        }
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                     : "l"(p));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c4 = c0 + u * 32 + lane;
+      if (c4 < E4) {
+        float4 x = v[u];
+        if (drop.on()) {
+          const float4 f = drop.factor4_group((uint64_t)(group0 + obase + c4));
+          x.x *= f.x; x.y *= f.y; x.z *= f.z; x.w *= f.w;
+        }
+        x.x = round_tf32_bits(x.x); x.y = round_tf32_bits(x.y); x.z = round_tf32_bits(x.z); x.w = round_tf32_bits(x.w);
+        xd[obase + c4] = x;
+      }
+    }
+  }
 }
 
 __global__ void scatter_rows_add_kernel(int R, int E4, int V, const int32_t* __restrict__ tok,
@@ -479,17 +559,31 @@ int embed_rows(int R, int E, int V, const int32_t* tok, const float* table_or_x,
   if (R <= 0) return EBK_OK;
   EBK_CHECK_ARG(E % 4 == 0, "embed_rows: E=%d must be a multiple of 4", E);
   const long n4 = (long)R * (E / 4);
+  static const bool warp_rows = !(getenv("EBK_EMBED_WARP_ROWS") && atoi(getenv("EBK_EMBED_WARP_ROWS")) == 0);
+  const bool by_warp = warp_rows && tok != nullptr && E / 4 >= 32;
   if (peers != nullptr && peers->world > 1 && tok != nullptr) {
     EBK_CHECK_ARG(peers->world <= 8 && peers->shard_floats % 4 == 0 && peers->shard_floats > 0, "embed_rows: bad peer table");
-    embed_rows_kernel<true><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
-        n4, E / 4, V, tok, reinterpret_cast<const float4*>(table_or_x), drop, reinterpret_cast<float4*>(xd), *peers,
-        row_offset * (E / 4));
+    if (by_warp)
+      embed_rows_warp_kernel<true><<<(unsigned)((R + 7) / 8), 256, 0, st>>>(
+          R, E / 4, V, tok, reinterpret_cast<const float4*>(table_or_x), drop, reinterpret_cast<float4*>(xd), *peers,
+          row_offset * (E / 4));
+    else
+      embed_rows_kernel<true><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(
+          n4, E / 4, V, tok, reinterpret_cast<const float4*>(table_or_x), drop, reinterpret_cast<float4*>(xd), *peers,
+          row_offset * (E / 4));
     EBK_LAUNCH_CHECK();
     return EBK_OK;
   }
   PeerTables none;
   none.world = 1;
   none.shard_floats = 0;
+  if (by_warp) {
+    embed_rows_warp_kernel<false><<<(unsigned)((R + 7) / 8), 256, 0, st>>>(
+        R, E / 4, V, tok, reinterpret_cast<const float4*>(table_or_x), drop, reinterpret_cast<float4*>(xd), none,
+        row_offset * (E / 4));
+    EBK_LAUNCH_CHECK();
+    return EBK_OK;
+  }
   embed_rows_kernel<false><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, E / 4, V, tok,
                                                                  reinterpret_cast<const float4*>(table_or_x), drop,
                                                                  reinterpret_cast<float4*>(xd), none, row_offset * (E / 4));

@@ -56,7 +56,7 @@ constexpr int EPI_THREADS = 128;
 // GEMMs with a heavy fused epilogue (dropout hash + pooling term + rounding) run 8 epilogue warps, two per TMEM lane
 // quarter splitting the tile's 32-column chunks: one warp alone on its scheduler is latency-bound (ncu: 20k cycles per
 // 128x208 tile against a 5k-cycle main loop with 4 warps)
-constexpr int MAX_EPI_WARPS = 8;
+constexpr int MAX_EPI_WARPS = 16;
 constexpr int MAX_THREADS = 64 + 32 * MAX_EPI_WARPS;
 // fused-attention variant: 16 epilogue warps (four per TMEM lane quarter).  The per-(sequence, head) attention is a long
 // dependent chain of mma.sync / shuffles / exp (measured ~12k cycles per unit on one warp), so 8 units run per CTA at a
@@ -80,7 +80,8 @@ struct TParams {
   int rv_smem;         // 1: the rowvec rows of each epilogue warp are staged in shared memory (L >= 16)
   int c_tma;           // 1: C has a tensor map -> the epilogue stores through shared memory + TMA
   int tile_rows;       // matrix rows between consecutive m-tiles of one CTA (BM * MT; fused attention: spt * L <= 128)
-  int epi_warps;       // epilogue warps of the plain GEMM: 4, or 8 (two per TMEM lane quarter)
+  int epi_warps;       // epilogue warps of the plain GEMM: 4, 8 or 16 (1, 2 or 4 per TMEM lane quarter)
+  int stg_bufs;        // store staging tiles per epilogue warp: 2, or 1 when 16 warps share the shared memory
   // ---- fused QKV projection + attention epilogue (ADH > 0): the tile is spt whole sequences x HPT whole heads
   int att_L, att_spt, att_nh, att_nseq;
   float* att_qkv_t;    // [n_seq, nh, 3, 32, ST] tf32 Q|K|V tiles saved for the backward pass (NULL: inference)
@@ -100,7 +101,6 @@ template <int DH> struct AttGeo {
   static constexpr uint32_t SMEM = TILE_BYTES;             // (the 32x32 probability tile overlays the unit's own Q | K)
   static_assert(2 * MAT >= att::LP * att::PS, "the score tile overlays Q and K");
 };
-constexpr uint32_t STG_WARP_BYTES = 2u * 4096u;  // store staging per epilogue warp: 2 x [32][128 B]
 constexpr int RV_ART = 4;                   // articles a warp's 32 rows can span when L >= 16
 constexpr int RV_WARP_FLOATS = RV_ART * 256; // per warp, per m-subtile
 
@@ -305,6 +305,7 @@ struct Cursor {
 struct EpiRow {
   float rs;          // rowscale[row]
   const float* rv;   // rowvec row of this thread (shared-memory slab or global), indexed by tile column
+  uint32_t rv_sa;    // shared-state-space address of that row when it lives in the slab (p.rv_smem)
 };
 
 // fused epilogue on 16 consecutive columns [n0 + c0, n0 + c0 + 16) of one row (see GemmEpilogue)
@@ -314,10 +315,11 @@ __device__ __forceinline__ void epi_apply16(const TParams& p, const EpiRow& er, 
   if (p.epi.rowscale != nullptr && er.rv != nullptr) {
     // + rowscale[row] * rowvec[row / L, col]   (AttLayer2 backward: w_t * d_out[n, :])
     if (p.rv_smem) {
-      const float4* vec = reinterpret_cast<const float4*>(er.rv + c0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 x = vec[q];
+        float4 x;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                     : "r"(er.rv_sa + (uint32_t)(c0 + 4 * q) * 4u));
         v[q * 4] = fmaf(er.rs, x.x, v[q * 4]); v[q * 4 + 1] = fmaf(er.rs, x.y, v[q * 4 + 1]);
         v[q * 4 + 2] = fmaf(er.rs, x.z, v[q * 4 + 2]); v[q * 4 + 3] = fmaf(er.rs, x.w, v[q * 4 + 3]);
       }
@@ -677,11 +679,17 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : MAX_THREADS, 1)
     const bool vec_base = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
     const bool vec8_base = vec_base && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 31) == 0) && p.out_mode == 0;
     uint8_t* tail = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)S * stage_bytes;   // behind the stage ring
-    // rowvec slab of this warp: [MT][RV_ART][BN] floats
+    // rowvec slab of this TMEM lane quarter (the 32 rows its EG warps share): [MT][RV_ART][BN] floats
     const int EG = p.epi_warps >> 2, eg = (warp - 2) >> 2;   // warps per TMEM lane quarter, this warp's index among them
-    float* rv_s = reinterpret_cast<float*>(tail + (size_t)p.epi_warps * STG_WARP_BYTES) + (size_t)(warp - 2) * MT * RV_WARP_FLOATS;
-    // store staging of this warp: 2 x [32 rows][128 B], SWIZZLE_128B
-    const uint32_t stg = smem_base + (uint32_t)S * stage_bytes + (uint32_t)(warp - 2) * 2u * 4096u;
+    const uint32_t stg_warp = (uint32_t)p.stg_bufs * 4096u;
+    float* rv_s = reinterpret_cast<float*>(tail + (size_t)p.epi_warps * stg_warp) + (size_t)ew * MT * RV_WARP_FLOATS;
+    // the EG warps of a quarter meet on named barrier 1 + ew around their use of the slab
+    auto quarter_sync = [&]() {
+      if (EG > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + ew), "r"(32 * EG) : "memory");
+      else __syncwarp();
+    };
+    // store staging of this warp: stg_bufs x [32 rows][128 B], SWIZZLE_128B
+    const uint32_t stg = smem_base + (uint32_t)S * stage_bytes + (uint32_t)(warp - 2) * stg_warp;
     int nstore = 0;  // TMA stores issued by this warp (lane 0 tracks the bulk groups)
     // the rowvec slab is filled with 16-byte cp.async when every address involved is 16-byte aligned (tile origins are
     // multiples of 16 columns) and N is a multiple of 4, so that no float4 straddles the last column
@@ -695,6 +703,7 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : MAX_THREADS, 1)
       for (int mt = 0; mt < MT; ++mt) {
         er[mt].rs = 0.0f;
         er[mt].rv = nullptr;
+        er[mt].rv_sa = 0u;
       }
       if (p.epi.rowscale != nullptr) {
         // operands of the fused epilogue that do not depend on the accumulator: fetched BEFORE waiting
@@ -709,7 +718,7 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : MAX_THREADS, 1)
             if (rv_vec) {
               // 16-byte asynchronous copies, none waited for here: the slab lands while this warp waits for the MMAs
               const int BN4 = BN >> 2;
-              for (int i = lane; i < RV_ART * BN4; i += 32) {
+              for (int i = eg * 32 + lane; i < RV_ART * BN4; i += 32 * EG) {
                 const int a = i / BN4, c = (i - a * BN4) << 2, art = art0 + a;
                 const bool ok = art <= art_last && n0 + c < p.N;
                 const float* src = ok ? p.epi.rowvec + (long)art * p.epi.rowvec_ld + n0 + c : p.epi.rowvec;
@@ -720,7 +729,7 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : MAX_THREADS, 1)
             } else {
               for (int a = 0; a < RV_ART; ++a) {
                 const int art = art0 + a;
-                for (int c = lane; c < BN; c += 32) {
+                for (int c = eg * 32 + lane; c < BN; c += 32 * EG) {
                   float x = 0.0f;
                   if (art <= art_last && n0 + c < p.N) x = __ldg(p.epi.rowvec + (long)art * p.epi.rowvec_ld + n0 + c);
                   rv_s[(mt * RV_ART + a) * BN + c] = x;
@@ -728,18 +737,18 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : MAX_THREADS, 1)
               }
             }
             er[mt].rv = rv_s + (mt * RV_ART + (min(row, p.M - 1) / p.epi.L - art0)) * BN;
+            er[mt].rv_sa = smem_u32(er[mt].rv);
           } else if (row < p.M) {
             er[mt].rv = p.epi.rowvec + (long)(row / p.epi.L) * p.epi.rowvec_ld + n0;
           }
         }
         if (rv_vec) asm volatile("cp.async.commit_group;" ::: "memory");
-        __syncwarp();
       }
       mbar_wait_backoff(smem_u32(&tfull_bar[buf]), (uint32_t)(use & 1));
       tc_fence_after();
-      if (rv_vec) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
+      if (p.rv_smem) {
+        if (rv_vec) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        quarter_sync();   // every warp's share of the slab has landed
       }
       const bool vec_ok = vec_base && ((n0 & 3) == 0);
       const bool vec8_ok = vec8_base && ((n0 & 7) == 0);
@@ -750,15 +759,18 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : MAX_THREADS, 1)
         int c0 = 0;
         if (p.c_tma) {
           for (; c0 + 32 <= BN && n0 + c0 < p.N; c0 += 32) {
-            if (((c0 >> 5) % EG) != eg) continue;   // the warps of a lane quarter take the 32-column chunks in turn
+            if ((((c0 >> 5) + t) % EG) != eg) continue;   // the warps of a lane quarter take the 32-column chunks in turn, rotating per tile
             float v[32];
             tmem_ld16(tbase + (uint32_t)c0, v);
             tmem_ld16(tbase + (uint32_t)c0 + 16u, v + 16);
             epi_apply16(p, er[mt], v, row, n0, c0);
             epi_apply16(p, er[mt], v + 16, row, n0, c0 + 16);
-            const uint32_t sb = stg + (uint32_t)(nstore & 1) * 4096u;
-            if (nstore >= 2) {  // the store that used this staging tile two chunks ago must have read it
-              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            const uint32_t sb = stg + (p.stg_bufs == 2 ? (uint32_t)(nstore & 1) * 4096u : 0u);
+            if (nstore >= p.stg_bufs) {  // the store that used this staging tile before must have read it
+              if (lane == 0) {
+                if (p.stg_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              }
               __syncwarp();
             }
 #pragma unroll
@@ -788,7 +800,7 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : MAX_THREADS, 1)
         float* crow = p.C + (long)row * p.ldc + n0;
         for (; c0 < BN; c0 += 16) {
           if (n0 + c0 >= p.N) break;  // warp-uniform
-          if (((c0 >> 4) % EG) != eg) continue;
+          if ((((c0 >> 4) + t + 3) % EG) != eg) continue;
           float v[16];
           tmem_ld16(tbase + (uint32_t)c0, v);  // warp-collective
           if (row < p.M) {
@@ -801,7 +813,8 @@ __global__ void __launch_bounds__(ADH > 0 ? ATT_THREADS : MAX_THREADS, 1)
       // buffer may be overwritten by the MMA warp (PAIR: the leader's, which waits for both epilogues)
       if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
       else mbar_arrive(smem_u32(&tempty_bar[buf]));
-      __syncwarp();                             // all lanes are done with the rowvec slab
+      if (p.rv_smem) quarter_sync();            // every reader of the rowvec slab is done with it
+      else __syncwarp();
       cu.next_item(p, n_items, item_stride);
       ++t;
     }
@@ -954,10 +967,12 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   const size_t stage_bytes = (size_t)MT * BM * BK * 4 + (size_t)p.b_rows * BK * 4;
   p.rv_smem = (p.epi.rowscale != nullptr && p.epi.L >= 16) ? 1 : 0;
   static const int env_ew = getenv("EBK_GEMM_EPI_WARPS") ? atoi(getenv("EBK_GEMM_EPI_WARPS")) : 0;   // experiments
-  p.epi_warps = (env_ew == 4 || env_ew == 8) ? env_ew
-                : ((p.epi.rowscale != nullptr || p.epi.drop.on()) && MT == 1 && !pair) ? 8 : 4;
-  const size_t STG_BYTES = (size_t)p.epi_warps * STG_WARP_BYTES;
-  const size_t rv_bytes = p.rv_smem ? (size_t)p.epi_warps * MT * RV_WARP_FLOATS * sizeof(float) : 0;
+  // a fused epilogue is ~20 dependent ALU instructions per element: 4 warps per scheduler hide that latency, 1 or 2 do not
+  p.epi_warps = (env_ew == 4 || env_ew == 8 || env_ew == 16) ? env_ew
+                : ((p.epi.rowscale != nullptr || p.epi.drop.on()) && MT == 1 && !pair) ? 16 : 4;
+  p.stg_bufs = p.epi_warps == 16 ? 1 : 2;
+  const size_t STG_BYTES = (size_t)p.epi_warps * p.stg_bufs * 4096;
+  const size_t rv_bytes = p.rv_smem ? (size_t)4 * MT * RV_WARP_FLOATS * sizeof(float) : 0;   // one slab per TMEM lane quarter
   p.c_tma = (ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
   const size_t budget = 226 * 1024 - 1024 - STG_BYTES - rv_bytes;   // 227 KB per CTA minus barriers / alignment slack
   int stages = (int)(budget / stage_bytes);
@@ -1099,6 +1114,7 @@ int qkv_attn_fused(const float* xd, int Din, const float* wp, int n_seq, int L, 
   p.splitk = 1;
   p.out_mode = 0;
   p.rv_smem = 0;
+  p.stg_bufs = 2;
   p.c_tma = 0;
   p.att_L = L; p.att_spt = spt; p.att_nh = nh; p.att_nseq = n_seq;
   p.att_qkv_t = qkv_t; p.att_y = y; p.att_drop = drop;
