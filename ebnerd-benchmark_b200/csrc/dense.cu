@@ -216,9 +216,61 @@ extern "C" size_t ebk_dense_workspace_bytes(const ebk_dense_desc* d) {
   return dense_layout(*d, nullptr).bytes;
 }
 
+namespace {
+// dropout of a Dense+BN layer: host seed, or (CUDA-graph replay) seed1 / seed2 of a device-resident ebk_step_params + add
+int dense_dropout(const ebk_dense_desc* d, int training, const ebk_step_params* step_dev, int seed_sel, uint64_t seed_add,
+                  Dropout* out) {
+  EBK_TRY(check_dense(d));
+  EBK_CHECK_ARG(step_dev != nullptr && (seed_sel == 0 || seed_sel == 1), "dense: step_dev must be set and seed_sel 0 or 1");
+  *out = make_dropout(training != 0, d->dropout, 0, seed_sel ? &step_dev->seed2 : &step_dev->seed1);
+  out->seed_add = seed_add;
+  return EBK_OK;
+}
+int dense_fwd_impl(const ebk_dense_desc* d, const float* x, const float* W, const float* b, const float* gamma,
+                   const float* beta, float* mov_mean, float* mov_var, int training, Dropout drop, void* workspace,
+                   size_t workspace_bytes, float* y, void* stream);
+int dense_bwd_impl(const ebk_dense_desc* d, const float* x, const float* W, const float* gamma, const float* y, int training,
+                   Dropout drop, void* workspace, size_t workspace_bytes, const float* dy, float l2_grad_scale, float* dW,
+                   float* db, float* dgamma, float* dbeta, float* dx, void* stream);
+}  // namespace
+
 extern "C" int ebk_dense_fwd(const ebk_dense_desc* d, const float* x, const float* W, const float* b, const float* gamma,
                              const float* beta, float* mov_mean, float* mov_var, int training, uint64_t seed,
                              void* workspace, size_t workspace_bytes, float* y, void* stream) {
+  EBK_TRY(check_dense(d));
+  return dense_fwd_impl(d, x, W, b, gamma, beta, mov_mean, mov_var, training, make_dropout(training != 0, d->dropout, seed),
+                        workspace, workspace_bytes, y, stream);
+}
+extern "C" int ebk_dense_fwd_p(const ebk_dense_desc* d, const float* x, const float* W, const float* b, const float* gamma,
+                               const float* beta, float* mov_mean, float* mov_var, int training,
+                               const ebk_step_params* step_dev, int seed_sel, uint64_t seed_add, void* workspace,
+                               size_t workspace_bytes, float* y, void* stream) {
+  Dropout drop;
+  EBK_TRY(dense_dropout(d, training, step_dev, seed_sel, seed_add, &drop));
+  return dense_fwd_impl(d, x, W, b, gamma, beta, mov_mean, mov_var, training, drop, workspace, workspace_bytes, y, stream);
+}
+extern "C" int ebk_dense_bwd(const ebk_dense_desc* d, const float* x, const float* W, const float* gamma, const float* y,
+                             int training, uint64_t seed, void* workspace, size_t workspace_bytes, const float* dy,
+                             float l2_grad_scale, float* dW, float* db, float* dgamma, float* dbeta, float* dx,
+                             void* stream) {
+  EBK_TRY(check_dense(d));
+  return dense_bwd_impl(d, x, W, gamma, y, training, make_dropout(training != 0, d->dropout, seed), workspace,
+                        workspace_bytes, dy, l2_grad_scale, dW, db, dgamma, dbeta, dx, stream);
+}
+extern "C" int ebk_dense_bwd_p(const ebk_dense_desc* d, const float* x, const float* W, const float* gamma, const float* y,
+                               int training, const ebk_step_params* step_dev, int seed_sel, uint64_t seed_add,
+                               void* workspace, size_t workspace_bytes, const float* dy, float l2_grad_scale, float* dW,
+                               float* db, float* dgamma, float* dbeta, float* dx, void* stream) {
+  Dropout drop;
+  EBK_TRY(dense_dropout(d, training, step_dev, seed_sel, seed_add, &drop));
+  return dense_bwd_impl(d, x, W, gamma, y, training, drop, workspace, workspace_bytes, dy, l2_grad_scale, dW, db, dgamma,
+                        dbeta, dx, stream);
+}
+
+namespace {
+int dense_fwd_impl(const ebk_dense_desc* d, const float* x, const float* W, const float* b, const float* gamma,
+                   const float* beta, float* mov_mean, float* mov_var, int training, Dropout drop, void* workspace,
+                   size_t workspace_bytes, float* y, void* stream) {
   EBK_TRY(check_dense(d));
   if (d->N == 0) return EBK_OK;
   EBK_CHECK_ARG(x && W && b && y && workspace, "dense_fwd: null pointer");
@@ -232,7 +284,6 @@ extern "C" int ebk_dense_fwd(const ebk_dense_desc* d, const float* x, const floa
   const int N = d->N, K = d->K, U = d->U;
   const long n = (long)N * U;
   const Dropout none = make_dropout(false, 0.f, 0);
-  const Dropout drop = make_dropout(training != 0, d->dropout, seed);
   const bool tc = d->math != EBK_MATH_FP32;
   const bool x3 = d->math == EBK_MATH_TF32X3;
   GemmOperandA ax{x, K, false, nullptr, 0, none, 0};
@@ -266,10 +317,9 @@ extern "C" int ebk_dense_fwd(const ebk_dense_desc* d, const float* x, const floa
   return EBK_OK;
 }
 
-extern "C" int ebk_dense_bwd(const ebk_dense_desc* d, const float* x, const float* W, const float* gamma, const float* y,
-                             int training, uint64_t seed, void* workspace, size_t workspace_bytes, const float* dy,
-                             float l2_grad_scale, float* dW, float* db, float* dgamma, float* dbeta, float* dx,
-                             void* stream) {
+int dense_bwd_impl(const ebk_dense_desc* d, const float* x, const float* W, const float* gamma, const float* y, int training,
+                   Dropout drop, void* workspace, size_t workspace_bytes, const float* dy, float l2_grad_scale, float* dW,
+                   float* db, float* dgamma, float* dbeta, float* dx, void* stream) {
   EBK_TRY(check_dense(d));
   if (d->N == 0) return EBK_OK;
   EBK_CHECK_ARG(x && W && dy && dW && db && workspace, "dense_bwd: null pointer");
@@ -285,7 +335,6 @@ extern "C" int ebk_dense_bwd(const ebk_dense_desc* d, const float* x, const floa
   const int N = d->N, K = d->K, U = d->U;
   const long n = (long)N * U;
   const Dropout none = make_dropout(false, 0.f, 0);
-  const Dropout drop = make_dropout(training != 0, d->dropout, seed);
   const bool tc = d->math != EBK_MATH_FP32;
   const bool x3 = d->math == EBK_MATH_TF32X3;
   const bool rnd = tc && !x3;
@@ -319,6 +368,7 @@ extern "C" int ebk_dense_bwd(const ebk_dense_desc* d, const float* x, const floa
   }
   return EBK_OK;
 }
+}  // namespace
 
 extern "C" int ebk_sumsq_accum(const float* x, size_t n, float scale, float* out, void* stream) {
   if (n == 0) return EBK_OK;

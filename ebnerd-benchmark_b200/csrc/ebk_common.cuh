@@ -97,10 +97,11 @@ struct Dropout {
   // CUDA-graph replay: the seed of THIS step is read from device memory (ebk_step_params), so that a captured
   // launch does not bake a seed in; NULL => `seed`
   const uint64_t* seed_dev;
+  uint64_t seed_add;   // added to *seed_dev (one device-resident step seed serves a stack of layers: seed + layer index)
   __host__ __device__ bool on() const { return thr != 0; }
   __device__ __forceinline__ uint64_t cur_seed() const {
 #ifdef __CUDA_ARCH__
-    return seed_dev != nullptr ? __ldg(reinterpret_cast<const unsigned long long*>(seed_dev)) : seed;
+    return seed_dev != nullptr ? __ldg(reinterpret_cast<const unsigned long long*>(seed_dev)) + seed_add : seed;
 #else
     return seed;
 #endif
@@ -127,6 +128,7 @@ static inline Dropout make_dropout(bool training, float p, uint64_t seed, const 
   Dropout d;
   d.seed = seed;
   d.seed_dev = seed_dev;
+  d.seed_add = 0;
   if (training && p > 0.0f) {
     d.thr = dropout_threshold(p);
     d.scale = 1.0f / (1.0f - p);

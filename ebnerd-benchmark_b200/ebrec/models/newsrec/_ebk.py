@@ -29,7 +29,7 @@ SYMBOLS = [
     "ebk_score_softmax_ce", "ebk_score_loss", "ebk_score_sigmoid", "ebk_adam_keras_step", "ebk_adam_keras_step_p",
     "ebk_embed_adam_step_p", "ebk_dp_token_flags", "ebk_adam_pull_step",
     "ebk_embed_adam_workspace_bytes", "ebk_embed_adam_step",
-    "ebk_dense_workspace_bytes", "ebk_dense_fwd", "ebk_dense_bwd", "ebk_sumsq_accum",
+    "ebk_dense_workspace_bytes", "ebk_dense_fwd", "ebk_dense_bwd", "ebk_dense_fwd_p", "ebk_dense_bwd_p", "ebk_sumsq_accum",
     "ebk_attlayer_workspace_bytes", "ebk_attlayer_fwd", "ebk_attlayer_bwd",
     "ebk_conv1d_workspace_bytes", "ebk_conv1d_fwd", "ebk_conv1d_bwd",
     "ebk_catview_workspace_bytes", "ebk_catview_fwd", "ebk_catview_bwd",
@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
     l.ebk_dense_workspace_bytes.argtypes = [ddp]
     l.ebk_dense_fwd.argtypes = [ddp, vp, vp, vp, vp, vp, vp, vp, C.c_int, u64, vp, sz, vp, vp]
     l.ebk_dense_bwd.argtypes = [ddp, vp, vp, vp, vp, C.c_int, u64, vp, sz, vp, f32, vp, vp, vp, vp, vp, vp]
+    l.ebk_dense_fwd_p.argtypes = [ddp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, u64, vp, sz, vp, vp]
+    l.ebk_dense_bwd_p.argtypes = [ddp, vp, vp, vp, vp, C.c_int, vp, C.c_int, u64, vp, sz, vp, f32, vp, vp, vp, vp, vp, vp]
     l.ebk_sumsq_accum.argtypes = [vp, sz, f32, vp, vp]
     adp, cdp = C.POINTER(AttLayerDesc), C.POINTER(Conv1dDesc)
     l.ebk_attlayer_workspace_bytes.restype = sz

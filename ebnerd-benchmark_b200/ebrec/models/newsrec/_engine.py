@@ -168,14 +168,23 @@ class NRMSEngine:
             raise _ebk.EbkError(f"bad descriptor: {_ebk.lib().ebk_last_error().decode()}")
         cur = self._ws.get(kind)
         if cur is None or cur.numel() < need:
+            if cur is not None:
+                self._drop_graphs()
             cur = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
             self._ws[kind] = cur
         return cur
+
+    def _drop_graphs(self) -> None:
+        """A cached buffer is about to be replaced by a larger one (e.g. a validation batch bigger than the training
+        batch): captured CUDA graphs hold the OLD address, so they are dropped and re-captured on the next step."""
+        self.__dict__.pop("_graphs", None)
 
     def _buf(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
         n = int(np.prod(shape))
         cur = self._bufs.get(name)
         if cur is None or cur.numel() < n or cur.dtype != dtype:
+            if cur is not None:
+                self._drop_graphs()
             cur = torch.empty(max(n, 1), dtype=dtype, device=self.device)
             self._bufs[name] = cur
         return cur[:n].view(*shape)

@@ -10,6 +10,7 @@ loss and optimizer are those of NRMS and reuse the same C-ABI calls (`ebk_seqenc
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -101,12 +102,16 @@ class DocVecEngine(NRMSEngine):
         need = _ebk.lib().ebk_dense_workspace_bytes(C.byref(desc))
         cur = self._ws.get(key)
         if cur is None or cur.numel() < need:
+            if cur is not None:
+                self._drop_graphs()
             cur = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
             self._ws[key] = cur
         return cur
 
-    def _mlp_fwd(self, call, x, out, training, seed):
-        """x [n, Ddoc] -> out [n, D]; keeps per-layer inputs / descs / workspaces for backward."""
+    def _mlp_fwd(self, call, x, out, training, seed, step_dev=None):
+        """x [n, Ddoc] -> out [n, D]; keeps per-layer inputs / descs / workspaces for backward.  Layer i drops with seed
+        `seed + i`; with step_dev (CUDA-graph replay) the base seed is seed1 (call 0) / seed2 (call 1) of the
+        device-resident ebk_step_params."""
         lib, P = _ebk.lib(), self.params
         n = x.shape[0]
         ctx, cur = [], x
@@ -114,40 +119,44 @@ class DocVecEngine(NRMSEngine):
             desc = self._dense_desc(n, K, U, bn, training)
             ws = self._dense_ws((call, i), desc)
             y = out if not bn else self._buf(f"y{call}_{i}", (n, U))
-            _ebk.check(lib.ebk_dense_fwd(C.byref(desc), _ebk.ptr(cur), _ebk.ptr(P.p(f"{name}_W")), _ebk.ptr(P.p(f"{name}_b")),
-                                         _ebk.ptr(P.p(f"{name}_gamma")) if bn else None,
-                                         _ebk.ptr(P.p(f"{name}_beta")) if bn else None,
-                                         _ebk.ptr(self.bn_mean[i]) if bn else None, _ebk.ptr(self.bn_var[i]) if bn else None,
-                                         int(training), (seed + i) & ((1 << 64) - 1), _ebk.ptr(ws), ws.numel(), _ebk.ptr(y),
-                                         _ebk.stream()))
+            head = (C.byref(desc), _ebk.ptr(cur), _ebk.ptr(P.p(f"{name}_W")), _ebk.ptr(P.p(f"{name}_b")),
+                    _ebk.ptr(P.p(f"{name}_gamma")) if bn else None, _ebk.ptr(P.p(f"{name}_beta")) if bn else None,
+                    _ebk.ptr(self.bn_mean[i]) if bn else None, _ebk.ptr(self.bn_var[i]) if bn else None, int(training))
+            tail = (_ebk.ptr(ws), ws.numel(), _ebk.ptr(y), _ebk.stream())
+            if step_dev is not None:
+                _ebk.check(lib.ebk_dense_fwd_p(*head, C.c_void_p(step_dev.data_ptr()), call & 1, i, *tail))
+            else:
+                _ebk.check(lib.ebk_dense_fwd(*head, (seed + i) & ((1 << 64) - 1), *tail))
             ctx.append((desc, ws, cur, y, name, bn, i))
             cur = y
         return ctx
 
-    def _mlp_bwd(self, ctx, d_out, training, seed, l2_scale):
+    def _mlp_bwd(self, ctx, d_out, training, seed, l2_scale, step_dev=None, call=0):
         lib, P = _ebk.lib(), self.params
         dy = d_out
         for desc, ws, x_in, y, name, bn, i in reversed(ctx):
             first = i == 0
             dx = None if first else self._buf(f"dx_{i % 2}", (desc.N, desc.K))  # ping-pong: dy of layer i-1
-            _ebk.check(lib.ebk_dense_bwd(C.byref(desc), _ebk.ptr(x_in), _ebk.ptr(P.p(f"{name}_W")),
-                                         _ebk.ptr(P.p(f"{name}_gamma")) if bn else None, _ebk.ptr(y), int(training),
-                                         (seed + i) & ((1 << 64) - 1), _ebk.ptr(ws), ws.numel(), _ebk.ptr(dy), l2_scale,
-                                         _ebk.ptr(P.g(f"{name}_W")), _ebk.ptr(P.g(f"{name}_b")),
-                                         _ebk.ptr(P.g(f"{name}_gamma")) if bn else None,
-                                         _ebk.ptr(P.g(f"{name}_beta")) if bn else None, _ebk.ptr(dx) if dx is not None else None,
-                                         _ebk.stream()))
+            head = (C.byref(desc), _ebk.ptr(x_in), _ebk.ptr(P.p(f"{name}_W")), _ebk.ptr(P.p(f"{name}_gamma")) if bn else None,
+                    _ebk.ptr(y), int(training))
+            tail = (_ebk.ptr(ws), ws.numel(), _ebk.ptr(dy), l2_scale, _ebk.ptr(P.g(f"{name}_W")), _ebk.ptr(P.g(f"{name}_b")),
+                    _ebk.ptr(P.g(f"{name}_gamma")) if bn else None, _ebk.ptr(P.g(f"{name}_beta")) if bn else None,
+                    _ebk.ptr(dx) if dx is not None else None, _ebk.stream())
+            if step_dev is not None:
+                _ebk.check(lib.ebk_dense_bwd_p(*head, C.c_void_p(step_dev.data_ptr()), call & 1, i, *tail))
+            else:
+                _ebk.check(lib.ebk_dense_bwd(*head, (seed + i) & ((1 << 64) - 1), *tail))
             dy = dx
         return None
 
     # ------------------------------------------------------------------ forward / backward
-    def _encode_vec(self, x_all, B, training, seeds):
+    def _encode_vec(self, x_all, B, training, seeds, step_dev=None):
         """x_all [B*H + B*C, Ddoc] float -> n_all [N, D], u [B, D]."""
         lib, P = _ebk.lib(), self.params
         N, BH = x_all.shape[0], B * self.H
         n_all = self._buf("n_all", (N, self.D))
-        ctx_h = self._mlp_fwd(0, x_all[:BH], n_all[:BH], training, seeds[0])
-        ctx_c = self._mlp_fwd(1, x_all[BH:], n_all[BH:], training, seeds[1])
+        ctx_h = self._mlp_fwd(0, x_all[:BH], n_all[:BH], training, seeds[0], step_dev)
+        ctx_c = self._mlp_fwd(1, x_all[BH:], n_all[BH:], training, seeds[1], step_dev)
         du = self._desc("user", B, training)
         wu = self._workspace("user", du)
         u = self._buf("u", (B, self.D))
@@ -156,18 +165,18 @@ class DocVecEngine(NRMSEngine):
                                       0, 0, 0, _ebk.ptr(wu), wu.numel(), _ebk.ptr(u), _ebk.stream()))
         return n_all, u, (ctx_h, ctx_c, du, wu)
 
-    def forward_logits_parts(self, x_all, B, C_, training=False, seeds=(0, 0)):
-        n_all, u, ctx = self._encode_vec(x_all, B, training, seeds)
+    def forward_logits_parts(self, x_all, B, C_, training=False, seeds=(0, 0), step_dev=None):
+        n_all, u, ctx = self._encode_vec(x_all, B, training, seeds, step_dev)
         return n_all, n_all[B * self.H:].view(B, C_, self.D), u, ctx
 
     def step_seeds(self):
         base = _mix(self.seed, self.step_count * self.world + self.rank)
         return _mix(base, 1) & ((1 << 62) - 1), _mix(base, 2) & ((1 << 62) - 1)
 
-    def loss_and_grads_dev(self, x_all, labels, B, C_, training=True, seeds=None):
+    def loss_and_grads_dev(self, x_all, labels, B, C_, training=True, seeds=None, step_dev=None):
         lib, P = _ebk.lib(), self.params
         seeds = self.step_seeds() if seeds is None else seeds
-        n_all, news_c, u, (ctx_h, ctx_c, du, wu) = self.forward_logits_parts(x_all, B, C_, training, seeds)
+        n_all, news_c, u, (ctx_h, ctx_c, du, wu) = self.forward_logits_parts(x_all, B, C_, training, seeds, step_dev)
         N, BH = n_all.shape[0], B * self.H
         probs = self._buf("probs", (B, C_))
         loss = self._buf("loss", (1,))
@@ -186,9 +195,57 @@ class DocVecEngine(NRMSEngine):
                                       _ebk.ptr(P.g("user_attW")), _ebk.ptr(P.g("user_attb")), _ebk.ptr(P.g("user_attq")),
                                       None, _ebk.ptr(dn_all), _ebk.stream()))
         # the l2 gradient 2*l2*W is added once per step (by the history call), scaled like the loss
-        self._mlp_bwd(ctx_h, dn_all[:BH], training, seeds[0], 1.0 / self.world)
-        self._mlp_bwd(ctx_c, dn_all[BH:], training, seeds[1], 0.0)
+        self._mlp_bwd(ctx_h, dn_all[:BH], training, seeds[0], 1.0 / self.world, step_dev, 0)
+        self._mlp_bwd(ctx_c, dn_all[BH:], training, seeds[1], 0.0, step_dev, 1)
         return loss, probs
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the training step
+    def _graph_ok(self) -> bool:
+        """One GPU, unless EBK_NO_GRAPH=1 or the library profiler is recording (every launch of this graph takes its
+        per-step scalars -- two dropout seeds, the Adam alpha -- from a device-resident ebk_step_params)."""
+        if os.environ.get("EBK_NO_GRAPH", "0") == "1" or type(self) is not DocVecEngine or self.world != 1:
+            return False
+        return not _ebk.lib().ebk_prof_is_enabled()
+
+    def train_step_dev(self, x_all, labels, B, C_):
+        """One optimizer iteration on device-resident rows x_all [B*H + B*C, Ddoc].  The step is about 90 small
+        launches (5 120-12 800 rows through four Dense layers, twice): replayed from a CUDA graph per batch shape."""
+        if not self._graph_ok():
+            loss, probs = self.loss_and_grads_dev(x_all, labels, B, C_, training=True)
+            self.apply_adam()
+            return loss, probs
+        graphs = self.__dict__.setdefault("_graphs", {})
+        key = (int(B), int(C_), tuple(x_all.shape), self.eps, self.dropout, self.beta1, self.beta2, self.l2, int(self.loss_kind))
+        st = graphs.get(key)
+        if st is None:
+            st = {"step": torch.zeros(3, dtype=torch.int64, device=self.device), "x": torch.empty_like(x_all),
+                  "lab": torch.empty_like(labels), "graph": None, "warm": 0}
+            graphs[key] = st
+        if st["graph"] is None and st["warm"] < 1:     # eager warm-up with the same shapes: allocates every workspace
+            st["warm"] += 1
+            loss, probs = self.loss_and_grads_dev(x_all, labels, B, C_, training=True)
+            self.apply_adam()
+            return loss, probs
+        st["x"].copy_(x_all, non_blocking=True)
+        st["lab"].copy_(labels, non_blocking=True)
+        self._write_step_params(st)
+        if st["graph"] is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = _ebk.lib().ebk_launch_count()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                loss, probs = self.loss_and_grads_dev(st["x"], st["lab"], B, C_, training=True, seeds=(0, 0),
+                                                      step_dev=st["step"])
+                P, sp = self.params, C.c_void_p(st["step"].data_ptr())
+                _ebk.check(_ebk.lib().ebk_adam_keras_step_p(_ebk.ptr(P.theta), _ebk.ptr(P.grad), _ebk.ptr(P.m), _ebk.ptr(P.v),
+                                                            P.n, 0.0, sp, self.beta1, self.beta2, self.eps, 1, _ebk.stream()))
+            st["graph"], st["loss"], st["probs"] = g, loss, probs
+            st["launches"] = int(_ebk.lib().ebk_launch_count() - l0)
+        st["graph"].replay()
+        self.step_count += 1
+        self.graph_steps = getattr(self, "graph_steps", 0) + 1
+        self.graph_launches = getattr(self, "graph_launches", 0) + st["launches"]
+        return st["loss"], st["probs"]
 
     # ------------------------------------------------------------------ device-resident doc-vector matrix
     def set_article_matrix(self, matrix: np.ndarray) -> None:

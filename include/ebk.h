@@ -189,6 +189,16 @@ int ebk_dense_fwd(const ebk_dense_desc* d, const float* x, const float* W, const
 int ebk_dense_bwd(const ebk_dense_desc* d, const float* x, const float* W, const float* gamma, const float* y,
                   int training, uint64_t seed, void* workspace, size_t workspace_bytes, const float* dy,
                   float l2_grad_scale, float* dW, float* db, float* dgamma, float* dbeta, float* dx, void* stream);
+/* The same two calls for CUDA-graph replay: the dropout seed of the layer is
+ *   (seed_sel == 0 ? step_dev->seed1 : step_dev->seed2) + seed_add, read from device memory by the kernels, so a captured
+ *   launch bakes no seed in (NRMSDocVec: seed1 = history call, seed2 = candidate call, seed_add = layer index). */
+int ebk_dense_fwd_p(const ebk_dense_desc* d, const float* x, const float* W, const float* b, const float* gamma,
+                    const float* beta, float* mov_mean, float* mov_var, int training, const ebk_step_params* step_dev,
+                    int seed_sel, uint64_t seed_add, void* workspace, size_t workspace_bytes, float* y, void* stream);
+int ebk_dense_bwd_p(const ebk_dense_desc* d, const float* x, const float* W, const float* gamma, const float* y,
+                    int training, const ebk_step_params* step_dev, int seed_sel, uint64_t seed_add, void* workspace,
+                    size_t workspace_bytes, const float* dy, float l2_grad_scale, float* dW, float* db, float* dgamma,
+                    float* dbeta, float* dx, void* stream);
 /* out[0] += scale * sum_i x[i]^2   (the l2 kernel-regulariser term of the loss) */
 int ebk_sumsq_accum(const float* x, size_t n, float scale, float* out, void* stream);
 

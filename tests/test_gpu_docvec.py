@@ -118,3 +118,42 @@ def test_docvec_facade_fit_predict_shapes():
     assert m.model.predict((his, pred), batch_size=5).shape == (12, 4)
     assert m.scorer.predict((his, pred[:, :1]), batch_size=5).shape == (12, 1)
     assert len(m.model.get_weights()) == 6 * 2 + 8
+
+
+def test_docvec_graph_replay_matches_eager_steps(monkeypatch):
+    """The NRMSDocVec train step (about 90 launches) is replayed from a CUDA graph; the per-layer dropout seeds
+    (seed1 / seed2 of the device-resident ebk_step_params + layer index) and Adam's alpha are read from device memory.
+    5 steps -- eager warm-up, capture + replay, replays, with an lr change, and an evaluation on a LARGER batch in the
+    middle (cached buffers are re-allocated: the captured graph must be dropped, not replayed on stale addresses) --
+    must follow the eager engine (EBK_NO_GRAPH=1)."""
+    Dd, units, nh, dh, att, B, H, C = 64, [48, 32], 4, 8, 24, 8, 7, 3
+    rng = np.random.default_rng(11)
+    P, _, _, y = make(rng, Dd, units, nh, dh, att, B, H, C)
+    batches = [(rng.standard_normal((B, H, Dd)).astype(np.float32), rng.standard_normal((B, C, Dd)).astype(np.float32))
+               for _ in range(6)]
+    big = (rng.standard_normal((3 * B, H, Dd)).astype(np.float32), rng.standard_normal((3 * B, C, Dd)).astype(np.float32))
+    res = {}
+    for mode in ("graph", "eager"):
+        if mode == "eager":
+            monkeypatch.setenv("EBK_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("EBK_NO_GRAPH", raising=False)
+        e = engine(P, Dd, units, H, nh, dh, att, 0.2, 1)
+        e.loss_kind = 0
+        losses = []
+        for i, (his, pred) in enumerate(batches):
+            if i == 2:
+                e.lr = 5e-4
+            if i == 4:
+                xb, _ = e.to_device_batch(*big)
+                e.predict_dev(xb, 3 * B, C)
+            x, lab = e.to_device_batch(his, pred, y)
+            loss, _ = e.train_step_dev(x, lab, B, C)
+            losses.append(float(loss))
+        res[mode] = (losses, e.get_weights(), getattr(e, "graph_steps", 0), e.step_count)
+    (lg, wg, ng, tg), (le, we, ne, te) = res["graph"], res["eager"]
+    assert ne == 0 and tg == te == 6
+    assert ng == 3 + 1          # steps 1-3 replayed, the graph dropped by the big batch, step 4 eager again, step 5 replayed
+    assert np.allclose(lg, le, rtol=0, atol=2e-5 * max(1.0, max(abs(v) for v in le))), (lg, le)
+    for a, b in zip(wg, we):
+        assert np.abs(a - b).max() < 2e-6 + 1e-5 * np.abs(b).max()
