@@ -315,22 +315,35 @@ __global__ void colsum_partial_kernel(int R, int Ncols, const float* __restrict_
   }
   partial[(long)blockIdx.y * Ncols + j] = acc;
 }
-__global__ void colsum_final_kernel(int nblk, int Ncols, const float* __restrict__ partial,
-                                    float* __restrict__ out) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= Ncols) return;
+// final stage: block = 32 columns x 8 slices of the partial rows, slices combined in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) colsum_final_kernel(int nblk, int Ncols, const float* __restrict__ partial,
+                                                           float* __restrict__ out) {
+  __shared__ float sh[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
   float acc = 0.0f;
-  for (int b = 0; b < nblk; ++b) acc += partial[(long)b * Ncols + j];
+  if (j < Ncols)
+    for (int b = ty; b < nblk; b += 8) acc += partial[(long)b * Ncols + j];
+  sh[ty][tx] = acc;
+  __syncthreads();
+  if (ty != 0 || j >= Ncols) return;
+  for (int k = 1; k < 8; ++k) acc += sh[k][tx];
   out[j] += acc;
 }
 
 // the same with the columns split between two outputs (db | dq partials of AttLayer2): out0[j] for j < n0, out1[j - n0] after
 __global__ void colsum_final2_kernel(int nblk, int Ncols, int n0, const float* __restrict__ partial, float* __restrict__ out0,
                                      float* __restrict__ out1) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= Ncols) return;
+  __shared__ float sh[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
   float acc = 0.0f;
-  for (int b = 0; b < nblk; ++b) acc += partial[(long)b * Ncols + j];
+  if (j < Ncols)
+    for (int b = ty; b < nblk; b += 8) acc += partial[(long)b * Ncols + j];
+  sh[ty][tx] = acc;
+  __syncthreads();
+  if (ty != 0 || j >= Ncols) return;
+  for (int k = 1; k < 8; ++k) acc += sh[k][tx];
   if (j < n0) out0[j] += acc;
   else out1[j - n0] += acc;
 }
@@ -519,7 +532,7 @@ int colsum_accum_ws(int R, int Ncols, const float* X, int ldx, const float* coef
   dim3 grid(ceil_div(Ncols, 128), nblk);
   colsum_partial_kernel<<<grid, 128, 0, st>>>(R, Ncols, X, ldx, coef, partial);
   EBK_LAUNCH_CHECK();
-  colsum_final_kernel<<<ceil_div(Ncols, 128), 128, 0, st>>>(nblk, Ncols, partial, out);
+  colsum_final_kernel<<<ceil_div(Ncols, 32), 256, 0, st>>>(nblk, Ncols, partial, out);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }
@@ -531,7 +544,7 @@ int colsum_accum2_ws(int R, int Ncols, int n0, const float* X, int ldx, float* o
   dim3 grid(ceil_div(Ncols, 128), nblk);
   colsum_partial_kernel<<<grid, 128, 0, st>>>(R, Ncols, X, ldx, nullptr, partial);
   EBK_LAUNCH_CHECK();
-  colsum_final2_kernel<<<ceil_div(Ncols, 128), 128, 0, st>>>(nblk, Ncols, n0, partial, out0, out1);
+  colsum_final2_kernel<<<ceil_div(Ncols, 32), 256, 0, st>>>(nblk, Ncols, n0, partial, out0, out1);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

@@ -10,7 +10,8 @@
 namespace ebk {
 namespace {
 
-constexpr int ROWS_PER_BLK = 128;
+constexpr int ROWS_PER_BLK = 64;   // rows per partial block
+constexpr int RB_X = 32, RB_Y = 8;   // reduction blocks: 32 columns (or float4 column groups) x 8 row slices
 
 // a = act(z + b) in place, 128-bit
 __global__ void bias_act_kernel(float4* __restrict__ z, const float4* __restrict__ b, long n4, int U4, int relu) {
@@ -26,29 +27,56 @@ __global__ void bias_act_kernel(float4* __restrict__ z, const float4* __restrict
 }
 
 // partial[blk][0][j] = sum_r a[r,j], partial[blk][1][j] = sum_r a[r,j]^2 over the block's rows
-__global__ void col_stats_partial_kernel(const float* __restrict__ a, int N, int U, float* __restrict__ partial) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= U) return;
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+// Column reductions of this file: block (32 float4 column groups) x (8 row slices) over ROWS_PER_BLK rows, slices
+// combined through shared memory in a fixed order (deterministic), one partial row per block; the final kernels
+// reduce the partial rows the same way (32 columns x 8 slices).
+__global__ void __launch_bounds__(RB_X * RB_Y) col_stats_partial_kernel(const float* __restrict__ a, int N, int U,
+                                                                        float* __restrict__ partial) {
+  __shared__ float4 sh[2][RB_Y][RB_X];
+  const int U4 = U >> 2, c4 = blockIdx.x * RB_X + threadIdx.x;
   const int r0 = blockIdx.y * ROWS_PER_BLK, r1 = min(N, r0 + ROWS_PER_BLK);
-  float s = 0.f, q = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    const float v = a[(long)r * U + j];
-    s += v;
-    q = fmaf(v, v, q);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  if (c4 < U4) {
+#pragma unroll 4
+    for (int r = r0 + threadIdx.y; r < r1; r += RB_Y) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(a) + (long)r * U4 + c4);
+      s = f4add(s, v);
+      q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    }
   }
-  partial[((long)blockIdx.y * 2 + 0) * U + j] = s;
-  partial[((long)blockIdx.y * 2 + 1) * U + j] = q;
+  sh[0][threadIdx.y][threadIdx.x] = s;
+  sh[1][threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c4 < U4) {
+    for (int k = 1; k < RB_Y; ++k) {
+      s = f4add(s, sh[0][k][threadIdx.x]);
+      q = f4add(q, sh[1][k][threadIdx.x]);
+    }
+    reinterpret_cast<float4*>(partial + ((long)blockIdx.y * 2 + 0) * U)[c4] = s;
+    reinterpret_cast<float4*>(partial + ((long)blockIdx.y * 2 + 1) * U)[c4] = q;
+  }
 }
 // mean / invstd of this call and the Keras moving-average update
-__global__ void col_stats_final_kernel(const float* __restrict__ partial, int nblk, int N, int U, float eps, float momentum,
-                                       float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ mov_mean,
-                                       float* __restrict__ mov_var) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= U) return;
+__global__ void __launch_bounds__(RB_X * RB_Y) col_stats_final_kernel(const float* __restrict__ partial, int nblk, int N, int U,
+                                                                      float eps, float momentum, float* __restrict__ mean,
+                                                                      float* __restrict__ invstd, float* __restrict__ mov_mean,
+                                                                      float* __restrict__ mov_var) {
+  __shared__ double sh[2][RB_Y][RB_X];
+  const int j = blockIdx.x * RB_X + threadIdx.x;
   double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s += partial[((long)b * 2 + 0) * U + j];
-    q += partial[((long)b * 2 + 1) * U + j];
+  if (j < U)
+    for (int b = threadIdx.y; b < nblk; b += RB_Y) {
+      s += partial[((long)b * 2 + 0) * U + j];
+      q += partial[((long)b * 2 + 1) * U + j];
+    }
+  sh[0][threadIdx.y][threadIdx.x] = s;
+  sh[1][threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y != 0 || j >= U) return;
+  for (int k = 1; k < RB_Y; ++k) {
+    s += sh[0][k][threadIdx.x];
+    q += sh[1][k][threadIdx.x];
   }
   const double m = s / N;
   double var = q / N - m * m;
@@ -87,64 +115,114 @@ __global__ void bn_apply_kernel(const float4* __restrict__ a, long n4, int U4, c
 }
 
 // partial sums of dyd and dyd*xhat per column (dyd = dy * dropout factor)
-__global__ void bn_bwd_partial_kernel(const float* __restrict__ dy, const float* __restrict__ a, int N, int U,
-                                      const float* __restrict__ mean, const float* __restrict__ invstd, Dropout drop,
-                                      float* __restrict__ partial) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= U) return;
+__global__ void __launch_bounds__(RB_X * RB_Y) bn_bwd_partial_kernel(const float* __restrict__ dy, const float* __restrict__ a,
+                                                                     int N, int U, const float* __restrict__ mean,
+                                                                     const float* __restrict__ invstd, Dropout drop,
+                                                                     float* __restrict__ partial) {
+  __shared__ float4 sh[2][RB_Y][RB_X];
+  const int U4 = U >> 2, c4 = blockIdx.x * RB_X + threadIdx.x;
   const int r0 = blockIdx.y * ROWS_PER_BLK, r1 = min(N, r0 + ROWS_PER_BLK);
-  const float m = mean[j], is = invstd[j];
-  float s1 = 0.f, s2 = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    const long idx = (long)r * U + j;
-    float g = dy[idx];
-    if (drop.on()) g *= drop.factor((uint64_t)idx);
-    s1 += g;
-    s2 = fmaf(g, (a[idx] - m) * is, s2);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  if (c4 < U4) {
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + c4), is = __ldg(reinterpret_cast<const float4*>(invstd) + c4);
+#pragma unroll 4
+    for (int r = r0 + threadIdx.y; r < r1; r += RB_Y) {
+      const long i4 = (long)r * U4 + c4;
+      float4 g = __ldg(reinterpret_cast<const float4*>(dy) + i4);
+      const float4 av = __ldg(reinterpret_cast<const float4*>(a) + i4);
+      if (drop.on()) {
+        const float4 f = drop.factor4_group((uint64_t)i4);   // U % 4 == 0: group i4 = elements 4 i4 .. 4 i4 + 3
+        g.x *= f.x; g.y *= f.y; g.z *= f.z; g.w *= f.w;
+      }
+      s1 = f4add(s1, g);
+      s2.x = fmaf(g.x, (av.x - m.x) * is.x, s2.x); s2.y = fmaf(g.y, (av.y - m.y) * is.y, s2.y);
+      s2.z = fmaf(g.z, (av.z - m.z) * is.z, s2.z); s2.w = fmaf(g.w, (av.w - m.w) * is.w, s2.w);
+    }
   }
-  partial[((long)blockIdx.y * 2 + 0) * U + j] = s1;
-  partial[((long)blockIdx.y * 2 + 1) * U + j] = s2;
+  sh[0][threadIdx.y][threadIdx.x] = s1;
+  sh[1][threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c4 < U4) {
+    for (int k = 1; k < RB_Y; ++k) {
+      s1 = f4add(s1, sh[0][k][threadIdx.x]);
+      s2 = f4add(s2, sh[1][k][threadIdx.x]);
+    }
+    reinterpret_cast<float4*>(partial + ((long)blockIdx.y * 2 + 0) * U)[c4] = s1;
+    reinterpret_cast<float4*>(partial + ((long)blockIdx.y * 2 + 1) * U)[c4] = s2;
+  }
 }
-__global__ void bn_bwd_final_kernel(const float* __restrict__ partial, int nblk, int U, float* __restrict__ sums,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= U) return;
+__global__ void __launch_bounds__(RB_X * RB_Y) bn_bwd_final_kernel(const float* __restrict__ partial, int nblk, int U,
+                                                                   float* __restrict__ sums, float* __restrict__ dgamma,
+                                                                   float* __restrict__ dbeta) {
+  __shared__ float sh[2][RB_Y][RB_X];
+  const int j = blockIdx.x * RB_X + threadIdx.x;
   float s1 = 0.f, s2 = 0.f;
-  for (int b = 0; b < nblk; ++b) {
-    s1 += partial[((long)b * 2 + 0) * U + j];
-    s2 += partial[((long)b * 2 + 1) * U + j];
+  if (j < U)
+    for (int b = threadIdx.y; b < nblk; b += RB_Y) {
+      s1 += partial[((long)b * 2 + 0) * U + j];
+      s2 += partial[((long)b * 2 + 1) * U + j];
+    }
+  sh[0][threadIdx.y][threadIdx.x] = s1;
+  sh[1][threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y != 0 || j >= U) return;
+  for (int k = 1; k < RB_Y; ++k) {
+    s1 += sh[0][k][threadIdx.x];
+    s2 += sh[1][k][threadIdx.x];
   }
   sums[j] = s1;
   sums[U + j] = s2;
   dbeta[j] += s1;
   dgamma[j] += s2;
 }
-// dz = relu'(a) * invstd * gamma * (dyd - s1/N - xhat * s2/N)      (training-mode BN backward)
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ a, long n, int N, int U,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ gamma, const float* __restrict__ sums, Dropout drop,
-                                    int relu, int round_out, float* __restrict__ dz) {
+// dz = relu'(a) * invstd * gamma * (dyd - s1/N - xhat * s2/N)      (training-mode BN backward), 4 columns per thread
+__global__ void bn_bwd_apply_kernel(const float4* __restrict__ dy, const float4* __restrict__ a, long n4, int N, int U4,
+                                    const float4* __restrict__ mean, const float4* __restrict__ invstd,
+                                    const float4* __restrict__ gamma, const float4* __restrict__ sums, Dropout drop,
+                                    int relu, int round_out, float4* __restrict__ dz) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int j = (int)(i % U);
-  float g = dy[i];
-  if (drop.on()) g *= drop.factor((uint64_t)i);
-  const float av = a[i];
-  const float xhat = (av - mean[j]) * invstd[j];
+  if (i >= n4) return;
+  const int c = (int)(i % U4);
+  float4 g = __ldg(dy + i);
+  if (drop.on()) {
+    const float4 f = drop.factor4_group((uint64_t)i);
+    g.x *= f.x; g.y *= f.y; g.z *= f.z; g.w *= f.w;
+  }
+  const float4 av = __ldg(a + i), m = __ldg(mean + c), is = __ldg(invstd + c), ga = __ldg(gamma + c);
+  const float4 s1 = __ldg(sums + c), s2 = __ldg(sums + U4 + c);
   const float invN = 1.0f / (float)N;
-  float v = invstd[j] * gamma[j] * (g - sums[j] * invN - xhat * sums[U + j] * invN);
-  if (relu && !(av > 0.f)) v = 0.f;
-  dz[i] = round_out ? round_tf32_bits(v) : v;
+  auto one = [&](float gv, float avv, float mv, float isv, float gav, float s1v, float s2v) {
+    const float xhat = (avv - mv) * isv;
+    float v = isv * gav * (gv - s1v * invN - xhat * s2v * invN);
+    if (relu && !(avv > 0.f)) v = 0.f;
+    return round_out ? round_tf32_bits(v) : v;
+  };
+  float4 o;
+  o.x = one(g.x, av.x, m.x, is.x, ga.x, s1.x, s2.x);
+  o.y = one(g.y, av.y, m.y, is.y, ga.y, s1.y, s2.y);
+  o.z = one(g.z, av.z, m.z, is.z, ga.z, s1.z, s2.z);
+  o.w = one(g.w, av.w, m.w, is.w, ga.w, s1.w, s2.w);
+  dz[i] = o;
 }
-// no BN: dz = dy * dropout' * relu'(y)
-__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ yv, long n, Dropout drop, int relu,
-                               int round_out, float* __restrict__ dz) {
+// no BN: dz = dy * dropout' * relu'(y), 4 elements per thread
+__global__ void act_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ yv, long n4, Dropout drop, int relu,
+                               int round_out, float4* __restrict__ dz) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float g = dy[i];
-  if (drop.on()) g *= drop.factor((uint64_t)i);
-  if (relu && !(yv[i] > 0.f)) g = 0.f;
-  dz[i] = round_out ? round_tf32_bits(g) : g;
+  if (i >= n4) return;
+  float4 g = __ldg(dy + i);
+  if (drop.on()) {
+    const float4 f = drop.factor4_group((uint64_t)i);
+    g.x *= f.x; g.y *= f.y; g.z *= f.z; g.w *= f.w;
+  }
+  if (relu) {
+    const float4 y = __ldg(yv + i);
+    if (!(y.x > 0.f)) g.x = 0.f;
+    if (!(y.y > 0.f)) g.y = 0.f;
+    if (!(y.z > 0.f)) g.z = 0.f;
+    if (!(y.w > 0.f)) g.w = 0.f;
+  }
+  if (round_out) { g.x = round_tf32_bits(g.x); g.y = round_tf32_bits(g.y); g.z = round_tf32_bits(g.z); g.w = round_tf32_bits(g.w); }
+  dz[i] = g;
 }
 __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, long n, float a) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -203,7 +281,11 @@ int bias_act(float* z, const float* b, long n, int U, int relu, cudaStream_t st)
 }
 int act_bwd(const float* dy, const float* y, long n, Dropout drop, int relu, int round_out, float* dz, cudaStream_t st) {
   if (n == 0) return EBK_OK;
-  act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dy, y, n, drop, relu, round_out, dz);
+  EBK_CHECK_ARG(n % 4 == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0,
+                "act_bwd: n=%ld must be a multiple of 4 and the buffers 16-byte aligned", n);
+  act_bwd_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(dy),
+                                                                  reinterpret_cast<const float4*>(y), n / 4, drop, relu,
+                                                                  round_out, reinterpret_cast<float4*>(dz));
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }
@@ -300,10 +382,10 @@ int dense_fwd_impl(const ebk_dense_desc* d, const float* x, const float* W, cons
   if (!d->bn) return EBK_OK;
   if (training) {
     const int nblk = ceil_div(N, ROWS_PER_BLK);
-    col_stats_partial_kernel<<<dim3(ceil_div(U, 128), nblk), 128, 0, st>>>(a, N, U, ws.partial);
+    col_stats_partial_kernel<<<dim3(ceil_div(U / 4, RB_X), nblk), dim3(RB_X, RB_Y), 0, st>>>(a, N, U, ws.partial);
     EBK_LAUNCH_CHECK();
-    col_stats_final_kernel<<<ceil_div(U, 128), 128, 0, st>>>(ws.partial, nblk, N, U, d->bn_eps, d->bn_momentum, ws.mean,
-                                                             ws.invstd, mov_mean, mov_var);
+    col_stats_final_kernel<<<ceil_div(U, RB_X), dim3(RB_X, RB_Y), 0, st>>>(ws.partial, nblk, N, U, d->bn_eps, d->bn_momentum,
+                                                                           ws.mean, ws.invstd, mov_mean, mov_var);
     EBK_LAUNCH_CHECK();
   } else {
     inference_stats_kernel<<<ceil_div(U, 128), 128, 0, st>>>(U, d->bn_eps, mov_mean, mov_var, ws.mean, ws.invstd);
@@ -324,6 +406,8 @@ int dense_bwd_impl(const ebk_dense_desc* d, const float* x, const float* W, cons
   if (d->N == 0) return EBK_OK;
   EBK_CHECK_ARG(x && W && dy && dW && db && workspace, "dense_bwd: null pointer");
   EBK_CHECK_ARG(!d->bn || (gamma && dgamma && dbeta), "dense_bwd: BatchNorm needs gamma/dgamma/dbeta");
+  EBK_CHECK_ARG(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
+                "dense_bwd: dy, gamma and the workspace must be 16-byte aligned");
   EBK_CHECK_ARG(d->bn || y, "dense_bwd: the layer output y is needed when there is no BatchNorm");
   EBK_CHECK_ARG(!d->bn || training, "dense_bwd: BatchNorm backward is defined for training mode");
   DenseWs ws = dense_layout(*d, workspace);
@@ -340,16 +424,18 @@ int dense_bwd_impl(const ebk_dense_desc* d, const float* x, const float* W, cons
   const bool rnd = tc && !x3;
   if (d->bn) {
     const int nblk = ceil_div(N, ROWS_PER_BLK);
-    bn_bwd_partial_kernel<<<dim3(ceil_div(U, 128), nblk), 128, 0, st>>>(dy, ws.a, N, U, ws.mean, ws.invstd, drop, ws.partial);
+    bn_bwd_partial_kernel<<<dim3(ceil_div(U / 4, RB_X), nblk), dim3(RB_X, RB_Y), 0, st>>>(dy, ws.a, N, U, ws.mean, ws.invstd,
+                                                                                          drop, ws.partial);
     EBK_LAUNCH_CHECK();
-    bn_bwd_final_kernel<<<ceil_div(U, 128), 128, 0, st>>>(ws.partial, nblk, U, ws.sums, dgamma, dbeta);
+    bn_bwd_final_kernel<<<ceil_div(U, RB_X), dim3(RB_X, RB_Y), 0, st>>>(ws.partial, nblk, U, ws.sums, dgamma, dbeta);
     EBK_LAUNCH_CHECK();
-    bn_bwd_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dy, ws.a, n, N, U, ws.mean, ws.invstd, gamma, ws.sums,
-                                                                     drop, d->relu, rnd ? 1 : 0, ws.dz);
+    auto f4 = [](const float* p) { return reinterpret_cast<const float4*>(p); };
+    bn_bwd_apply_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(f4(dy), f4(ws.a), n / 4, N, U / 4, f4(ws.mean),
+                                                                         f4(ws.invstd), f4(gamma), f4(ws.sums), drop, d->relu,
+                                                                         rnd ? 1 : 0, reinterpret_cast<float4*>(ws.dz));
     EBK_LAUNCH_CHECK();
   } else {
-    act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dy, y, n, drop, d->relu, rnd ? 1 : 0, ws.dz);
-    EBK_LAUNCH_CHECK();
+    EBK_TRY(act_bwd(dy, y, n, drop, d->relu, rnd ? 1 : 0, ws.dz, st));
   }
   EBK_TRY(colsum_accum_ws(N, U, ws.dz, U, nullptr, db, ws.colsum, st));
   // dW += x^T dz  (+ 2 l2 W)
