@@ -237,6 +237,7 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long n, float scale, f
 
 struct DenseWs {
   float *a, *dz, *mean, *invstd, *sums, *partial, *w_f, *w_d, *colsum;
+  float *xr, *wr;   // all-TMA path (EBK_MATH_TF32): tf32-rounded copies of the layer input [N, K] and of W [K, U]
   size_t bytes;
 };
 DenseWs dense_layout(const ebk_dense_desc& d, void* base) {
@@ -258,8 +259,17 @@ DenseWs dense_layout(const ebk_dense_desc& d, void* base) {
   w.w_f = take(gemm_tf32_packed_floats(d.U, d.K, false));
   w.w_d = take(gemm_tf32_packed_floats(d.K, d.U, true));
   w.colsum = take(colsum_partial_floats((int)N, (int)U));
+  w.xr = take(N * (size_t)d.K);
+  w.wr = take((size_t)d.K * U);
   w.bytes = off;
   return w;
+}
+// EBK_MATH_TF32 layers run their three contractions on the all-TMA tcgen05 GEMM (gemm_tma_sm100.cu) from rounded copies of
+// x and W kept in the workspace (forward -> backward); EBK_DENSE_TMA=0 keeps the older register-staged GEMM (A/B runs).
+bool dense_uses_tma(const ebk_dense_desc& d, const DenseWs& ws, const float* x, const float* W) {
+  static const bool on = !(getenv("EBK_DENSE_TMA") && atoi(getenv("EBK_DENSE_TMA")) == 0);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return on && d.math == EBK_MATH_TF32 && al(x) && al(W) && gemm_tma_eligible(ws.xr, d.K, ws.wr, d.U, d.N, d.U, d.K);
 }
 int check_dense(const ebk_dense_desc* d) {
   EBK_CHECK_ARG(d != nullptr, "dense: null descriptor");
@@ -369,13 +379,19 @@ int dense_fwd_impl(const ebk_dense_desc* d, const float* x, const float* W, cons
   const bool tc = d->math != EBK_MATH_FP32;
   const bool x3 = d->math == EBK_MATH_TF32X3;
   GemmOperandA ax{x, K, false, nullptr, 0, none, 0};
-  const bool pk = tc && !x3 && gemm_tf32_eligible(ax, W, U, N, U, K);
   float* a = d->bn ? ws.a : y;  // without BN the activation IS the output
-  if (pk) {
-    EBK_TRY(gemm_tf32_pack_b(ws.w_f, nullptr, W, U, false, U, K, st));
-    EBK_TRY(gemm_tf32_pack_b(ws.w_d, nullptr, W, U, true, K, U, st));
+  if (dense_uses_tma(*d, ws, x, W)) {
+    EBK_TRY(round_tf32_copy(ws.xr, x, (size_t)N * K, st));
+    EBK_TRY(round_tf32_copy(ws.wr, W, (size_t)K * U, st));
+    EBK_TRY(gemm_tma(ws.xr, K, false, ws.wr, U, false, a, U, N, U, K, 0.0f, 1.0f, st, -1));
+  } else {
+    const bool pk = tc && !x3 && gemm_tf32_eligible(ax, W, U, N, U, K);
+    if (pk) {
+      EBK_TRY(gemm_tf32_pack_b(ws.w_f, nullptr, W, U, false, U, K, st));
+      EBK_TRY(gemm_tf32_pack_b(ws.w_d, nullptr, W, U, true, K, U, st));
+    }
+    EBK_TRY(gemm_dispatch(d->math, ax, pk ? ws.w_f : W, U, false, a, U, N, U, K, 0.0f, st, pk ? GEMM_B_PACKED : GEMM_B_RAW));
   }
-  EBK_TRY(gemm_dispatch(d->math, ax, pk ? ws.w_f : W, U, false, a, U, N, U, K, 0.0f, st, pk ? GEMM_B_PACKED : GEMM_B_RAW));
   bias_act_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(a),
                                                                    reinterpret_cast<const float4*>(b), n / 4, U / 4, d->relu);
   EBK_LAUNCH_CHECK();
@@ -439,14 +455,18 @@ int dense_bwd_impl(const ebk_dense_desc* d, const float* x, const float* W, cons
   }
   EBK_TRY(colsum_accum_ws(N, U, ws.dz, U, nullptr, db, ws.colsum, st));
   // dW += x^T dz  (+ 2 l2 W)
+  const bool tma = dense_uses_tma(*d, ws, x, W);   // same predicate as the forward call: ws.xr / ws.wr hold its copies
   GemmOperandA axT{x, K, true, nullptr, 0, none, 0};
-  EBK_TRY(gemm_dispatch(d->math, axT, ws.dz, U, false, dW, U, K, U, N, 1.0f, st, rnd ? GEMM_B_ROUNDED : GEMM_B_RAW));
+  if (tma) EBK_TRY(gemm_tma(ws.xr, K, true, ws.dz, U, false, dW, U, K, U, N, 1.0f, 1.0f, st, -1));
+  else EBK_TRY(gemm_dispatch(d->math, axT, ws.dz, U, false, dW, U, K, U, N, 1.0f, st, rnd ? GEMM_B_ROUNDED : GEMM_B_RAW));
   if (d->l2 > 0.f && l2_grad_scale != 0.f) {
     const long nw = (long)K * U;
     axpy_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(dW, W, nw, 2.0f * d->l2 * l2_grad_scale);
     EBK_LAUNCH_CHECK();
   }
-  if (dx) {
+  if (dx && tma) {
+    EBK_TRY(gemm_tma(ws.dz, U, false, ws.wr, U, true, dx, K, N, K, U, 0.0f, 1.0f, st, -1));
+  } else if (dx) {
     GemmOperandA adz{ws.dz, U, false, nullptr, 0, none, 0};
     GemmOperandA ax{x, K, false, nullptr, 0, none, 0};
     const bool pk = rnd && gemm_tf32_eligible(ax, W, U, N, U, K) && gemm_tf32_eligible(adz, W, U, N, K, U);

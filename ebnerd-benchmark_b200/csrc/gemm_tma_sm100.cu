@@ -932,12 +932,21 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   const bool a_mn = transA, b_mn = !transB;
   static const int env_cluster = getenv("EBK_GEMM_CLUSTER") ? atoi(getenv("EBK_GEMM_CLUSTER")) : -2;  // experiments
   if (env_cluster >= -1) cluster = env_cluster;
+  int bn_max = 256;
   if (tall < 0) {
-    // auto: 256-row tiles halve the L2 traffic of B; use them when they still fill the machine, or when
-    // split-K fills it anyway
+    // auto: 256-row tiles halve the L2 traffic of B; use them when they still fill the machine.  A problem with fewer
+    // 128 x 256 tiles than SMs is latency bound (pipeline fill + one epilogue per CTA: ~19 us for 256 x 256 tiles
+    // whatever the size): it gets 128 x <=128 tiles -- more CTAs, 5 stages instead of 2, a quarter of the epilogue each.
     const long tn = ceil_div(N, ceil_div(ceil_div(N, ceil_div(N, 256)), 16) * 16);
     const long t1 = (long)ceil_div(M, BM) * tn, t2 = (long)ceil_div(M, 2 * BM) * tn;
-    tall = (t2 >= 2L * g_sms || t1 < g_sms) ? 1 : 0;
+    static const bool small_on = !(getenv("EBK_GEMM_SMALL_TILES") && atoi(getenv("EBK_GEMM_SMALL_TILES")) == 0);
+    // (few tiles but a huge K -- the QKV weight gradient -- is not small: it keeps big tiles and splits K)
+    if (t1 < g_sms && t1 * (long)ceil_div(K, BK) < 128L * g_sms && small_on) {
+      tall = 0;
+      bn_max = 128;
+    } else {
+      tall = (t2 >= 2L * g_sms || t1 < g_sms) ? 1 : 0;
+    }
   }
   const int MT = tall ? 2 : 1;
   // cluster: 0 = one CTA per tile, 1 = CTA pairs (cta_group::2), -1 auto.  Measured on B200 (tools/bench_gemm_tma.py):
@@ -953,7 +962,7 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   const bool has_epi = p.epi.rowscale != nullptr || p.epi.drop.on() || p.epi.round_out;
   EBK_CHECK_ARG(!has_epi || beta == 0.0f, "gemm_tma: a fused epilogue needs beta == 0");
   EBK_CHECK_ARG(!p.epi.drop.on() || p.epi.drop_ld % 4 == 0, "gemm_tma: dropout epilogue needs drop_ld %% 4 == 0");
-  const int ntn = ceil_div(N, 256);
+  const int ntn = ceil_div(N, bn_max);
   p.BN = ceil_div(ceil_div(N, ntn), 16) * 16;
   p.tiles_n = ceil_div(N, p.BN);
   const int bn_cta = pair ? p.BN / 2 : p.BN;                       // B columns staged by one CTA
@@ -985,7 +994,7 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   int splitk = 1;
   if (tiles < max_clusters && p.ksteps_total >= 16 && !has_epi) {
     splitk = (int)(max_clusters / tiles);  // fill the machine in ONE wave of equal items
-    const int maxsplit = p.ksteps_total / 8;
+    const int maxsplit = p.ksteps_total / (bn_max < 256 ? 16 : 8);   // (small problems: a split must be worth its zero-fill)
     if (splitk > maxsplit) splitk = maxsplit;
     if (splitk < 1) splitk = 1;
   }
