@@ -372,8 +372,19 @@ extern "C" int ebk_seqenc_fwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
       // ---- north-star kernel: gather -> [QKV projection + per-head softmax(QK^T/sqrt(dh))^T V in ONE tcgen05 kernel]:
       // the accumulator tile is whole sequences x whole heads (weights permuted head-major), the attention runs in the
       // GEMM epilogue from TMEM through shared memory, Q|K|V reach HBM only as the tiles the backward needs
-      EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st,
-                                          remote ? &peers : nullptr));
+      if (tok != nullptr && opts != nullptr && opts->token_csr_ws != nullptr) {
+        // each distinct token's row once (ebk_seqenc_opts.token_csr_ws): what pays when the rows are remote
+        EBK_CHECK_ARG(opts->token_csr_ws_bytes >= token_csr_bytes(R, d->V), "seqenc_fwd: token_csr_ws %zu < %zu bytes",
+                      opts->token_csr_ws_bytes, token_csr_bytes(R, d->V));
+        TokenCsr csr;
+        if (prof_on()) prof_begin(T_EMBED_GATHER, st);
+        EBK_TRY(token_csr_build(R, d->V, tok, opts->token_csr_ws, &csr, st));
+        EBK_TRY(embed_rows_csr(R, d->Din, d->V, tok, table_or_x, drop1, ws.xd, st, remote ? &peers : nullptr, csr));
+        if (prof_on()) prof_end(T_EMBED_GATHER, st);
+      } else {
+        EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st,
+                                            remote ? &peers : nullptr));
+      }
       EBK_TRY(permute_round_wqkv(ws.wqkv_p, Wqkv, d->Din, d->nh, d->dh, st));
       float* y0f = pool ? ws.y0 : out;
       EBK_PROF(T_QKV_FWD, qkv_attn_fused(ws.xd, d->Din, ws.wqkv_p, d->n_seq, d->L, d->nh, d->dh, ws.qkv, y0f,

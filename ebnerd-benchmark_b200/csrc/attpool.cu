@@ -449,6 +449,98 @@ __global__ void __launch_bounds__(256) embed_rows_warp_kernel(int R, int E4, int
   }
 }
 
+// ---- gather through a token CSR: every DISTINCT token's row is read once and written to all of its positions (each
+// with its own dropout mask).  Under data parallel 7/8 of the rows are remote and the gather is NVLink-read bound, so
+// reading 134 k distinct rows instead of 192 k positions (uniform synthetic ids; far fewer distinct ids in real titles)
+// is what moves it.  One warp per token id; tokens with more than CSR_CAP positions and ids outside the table are left
+// to embed_rows_rest_kernel (one warp per position), so no warp walks a long list.
+constexpr int CSR_CAP = 32;
+template <bool PEERS>
+__global__ void __launch_bounds__(256) embed_rows_csr_kernel(int V, int E4, const int* __restrict__ count,
+                                                             const int* __restrict__ offset, const int* __restrict__ perm,
+                                                             const float4* __restrict__ src, Dropout drop,
+                                                             float4* __restrict__ xd, PeerTables peers, int rr_ways,
+                                                             int rr_rows) {
+  constexpr int U = 6;
+  const int lane = threadIdx.x & 31;
+  const long w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // warps walk the token ids round-robin over the owners' row ranges, so that local (HBM) and remote (NVLink) rows are
+  // in flight together for the whole kernel (in id order the kernel would run an HBM phase, then an NVLink phase)
+  const long t = (w % rr_ways) * rr_rows + w / rr_ways;
+  if (w >= (long)rr_ways * rr_rows || t >= V) return;
+  const int cnt = __ldg(count + t);
+  if (cnt == 0 || cnt > CSR_CAP) return;
+  const int off = __ldg(offset + t);
+  const int my_pos = lane < cnt ? __ldg(perm + off + lane) : 0;   // cnt <= 32: one position per lane, broadcast below
+  const long rowbase = t * E4;
+  for (int c0 = 0; c0 < E4; c0 += 32 * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c4 = c0 + u * 32 + lane;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < E4) {
+        const long chunk = rowbase + c4;
+        const float4* p = src + chunk;
+        if (PEERS) {
+          const int owner = (int)(((unsigned long long)chunk * 4ull) / peers.shard_floats);
+          p = reinterpret_cast<const float4*>(peers.p[owner < peers.world ? owner : peers.world - 1]) + chunk;
+        }
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                     : "l"(p));
+      }
+    }
+    for (int j = 0; j < cnt; ++j) {
+      const long obase = (long)__shfl_sync(0xffffffffu, my_pos, j) * E4;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c4 = c0 + u * 32 + lane;
+        if (c4 < E4) {
+          float4 x = v[u];
+          if (drop.on()) {
+            const float4 f = drop.factor4_group((uint64_t)(obase + c4));
+            x.x *= f.x; x.y *= f.y; x.z *= f.z; x.w *= f.w;
+          }
+          x.x = round_tf32_bits(x.x); x.y = round_tf32_bits(x.y); x.z = round_tf32_bits(x.z); x.w = round_tf32_bits(x.w);
+          xd[obase + c4] = x;
+        }
+      }
+    }
+  }
+}
+// the positions embed_rows_csr_kernel leaves: ids outside the table (zero row) and tokens with more than CSR_CAP positions
+template <bool PEERS>
+__global__ void __launch_bounds__(256) embed_rows_rest_kernel(int R, int E4, int V, const int32_t* __restrict__ tok,
+                                                              const int* __restrict__ count, const float4* __restrict__ src,
+                                                              Dropout drop, float4* __restrict__ xd, PeerTables peers) {
+  const int lane = threadIdx.x & 31;
+  const long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int t = __ldg(tok + r);
+  const bool ok = t >= 0 && t < V;
+  if (ok && __ldg(count + t) <= CSR_CAP) return;
+  const long rowbase = (long)t * E4, obase = r * E4;
+  for (int c4 = lane; c4 < E4; c4 += 32) {
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+      const long chunk = rowbase + c4;
+      const float4* p = src + chunk;
+      if (PEERS) {
+        const int owner = (int)(((unsigned long long)chunk * 4ull) / peers.shard_floats);
+        p = reinterpret_cast<const float4*>(peers.p[owner < peers.world ? owner : peers.world - 1]) + chunk;
+      }
+      x = __ldg(p);   // (allocating load: a frequent row is re-read by many warps)
+      if (drop.on()) {
+        const float4 f = drop.factor4_group((uint64_t)(obase + c4));
+        x.x *= f.x; x.y *= f.y; x.z *= f.z; x.w *= f.w;
+      }
+      x.x = round_tf32_bits(x.x); x.y = round_tf32_bits(x.y); x.z = round_tf32_bits(x.z); x.w = round_tf32_bits(x.w);
+    }
+    xd[obase + c4] = x;
+  }
+}
+
 __global__ void scatter_rows_add_kernel(int R, int E4, int V, const int32_t* __restrict__ tok,
                                         const float4* __restrict__ dX, Dropout drop,
                                         float* __restrict__ d_table) {
@@ -600,6 +692,35 @@ int embed_rows(int R, int E, int V, const int32_t* tok, const float* table_or_x,
   embed_rows_kernel<false><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, E / 4, V, tok,
                                                                  reinterpret_cast<const float4*>(table_or_x), drop,
                                                                  reinterpret_cast<float4*>(xd), none, row_offset * (E / 4));
+  EBK_LAUNCH_CHECK();
+  return EBK_OK;
+}
+
+int embed_rows_csr(int R, int E, int V, const int32_t* tok, const float* table, Dropout drop, float* xd, cudaStream_t st,
+                   const PeerTables* peers, const TokenCsr& csr) {
+  if (R <= 0) return EBK_OK;
+  EBK_CHECK_ARG(E % 4 == 0 && tok != nullptr && table != nullptr, "embed_rows_csr: E=%d must be a multiple of 4, tok / table set", E);
+  const int E4 = E / 4;
+  const float4* src = reinterpret_cast<const float4*>(table);
+  float4* dst = reinterpret_cast<float4*>(xd);
+  const unsigned gr = (unsigned)((R + 7) / 8);
+  if (peers != nullptr && peers->world > 1) {
+    EBK_CHECK_ARG(peers->world <= 8 && peers->shard_floats % 4 == 0 && peers->shard_floats > 0, "embed_rows_csr: bad peer table");
+    const int ways = peers->world, rows = ceil_div(V, ways);
+    const unsigned gt = (unsigned)(((long)ways * rows + 7) / 8);
+    embed_rows_csr_kernel<true><<<gt, 256, 0, st>>>(V, E4, csr.count, csr.offset, csr.perm, src, drop, dst, *peers, ways, rows);
+    EBK_LAUNCH_CHECK();
+    embed_rows_rest_kernel<true><<<gr, 256, 0, st>>>(R, E4, V, tok, csr.count, src, drop, dst, *peers);
+    EBK_LAUNCH_CHECK();
+    return EBK_OK;
+  }
+  PeerTables none;
+  none.world = 1;
+  none.shard_floats = 0;
+  embed_rows_csr_kernel<false><<<(unsigned)((V + 7) / 8), 256, 0, st>>>(V, E4, csr.count, csr.offset, csr.perm, src, drop, dst,
+                                                                        none, 1, V);
+  EBK_LAUNCH_CHECK();
+  embed_rows_rest_kernel<false><<<gr, 256, 0, st>>>(R, E4, V, tok, csr.count, src, drop, dst, none);
   EBK_LAUNCH_CHECK();
   return EBK_OK;
 }

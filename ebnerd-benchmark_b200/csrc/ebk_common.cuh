@@ -282,6 +282,17 @@ struct PeerTables {
   unsigned long long shard_floats;
   const float* p[8];
 };
+// Token CSR: the positions r of tok[0..R) grouped by token id (count[t], offset[t], perm[offset[t] .. +count[t])); ids
+// outside [0, V) are in no group.  Built by embed_adam.cu (the single-GPU optimizer groups the per-row gradients the
+// same way); `total` is the scan's running total, `cursor` the fill cursors.
+struct TokenCsr {
+  int *count, *cursor, *total, *offset, *perm;
+};
+size_t token_csr_bytes(int R, int V);
+int token_csr_build(int R, int V, const int32_t* tok, void* ws, TokenCsr* out, cudaStream_t st);
+// the gather of embed_rows with every DISTINCT token's row read once (tokens with more than 32 positions: per position)
+int embed_rows_csr(int R, int E, int V, const int32_t* tok, const float* table, Dropout drop, float* xd, cudaStream_t st,
+                   const PeerTables* peers, const TokenCsr& csr);
 int embed_rows(int R, int E, int V, const int32_t* tok, const float* table_or_x, Dropout drop, float* xd,
                cudaStream_t st, const PeerTables* peers = nullptr, long row_offset = 0 /* rows before this chunk: dropout index */);
 // d_table[tok[r], :] += dX[r, :] * dropout(r*E + e)

@@ -189,10 +189,40 @@ __global__ void __launch_bounds__(256) embed_adam_kernel(int V, int E4, const in
 
 using namespace ebk;
 
+namespace ebk {
+// count[V] | cursor[V] | total[64] (zeroed each build) | offset[V] | perm[R]
+size_t token_csr_bytes(int R, int V) { return ((size_t)3 * V + 64 + (size_t)R) * sizeof(int) + 256; }
+
+int token_csr_build(int R, int V, const int32_t* tok, void* ws, TokenCsr* out, cudaStream_t st) {
+  TokenCsr c;
+  c.count = reinterpret_cast<int*>(ws);
+  c.cursor = c.count + V;
+  c.total = c.cursor + V;
+  c.offset = c.total + 64;
+  c.perm = c.offset + V;
+  EBK_CUDA(cudaMemsetAsync(c.count, 0, ((size_t)2 * V + 64) * sizeof(int), st));
+  if (R > 0) {
+    tok_count_kernel<<<(R + 255) / 256, 256, 0, st>>>(R, V, tok, c.count);
+    EBK_LAUNCH_CHECK();
+  }
+  tok_offset_kernel<<<ceil_div(V, SCAN_T * SCAN_PER_T), SCAN_T, 0, st>>>(V, c.count, c.offset, c.total);
+  EBK_LAUNCH_CHECK();
+  if (R > 0) {
+    tok_fill_kernel<<<(R + 255) / 256, 256, 0, st>>>(R, V, tok, c.offset, c.cursor, c.perm);
+    EBK_LAUNCH_CHECK();
+  }
+  *out = c;
+  return EBK_OK;
+}
+}  // namespace ebk
+
+extern "C" size_t ebk_token_csr_bytes(int32_t R, int32_t V) {
+  if (R < 0 || V < 0) return 0;
+  return token_csr_bytes(R, V);
+}
 extern "C" size_t ebk_embed_adam_workspace_bytes(int32_t R, int32_t V) {
   if (R < 0 || V < 0) return 0;
-  // count[V] | cursor[V] | total[64] (zeroed each step) | offset[V] | perm[R]
-  return ((size_t)3 * V + 64 + (size_t)R) * sizeof(int) + 256;
+  return token_csr_bytes(R, V);
 }
 
 extern "C" int ebk_embed_adam_step(int32_t R, int32_t E, int32_t V, const int32_t* tok, const float* dX, float drop_p,
@@ -217,26 +247,15 @@ extern "C" int ebk_embed_adam_step_p(int32_t R, int32_t E, int32_t V, const int3
     return EBK_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  int* count = reinterpret_cast<int*>(workspace);
-  int* cursor = count + V;
-  int* total = cursor + V;
-  int* offset = total + 64;
-  int* perm = offset + V;
   const Dropout drop = make_dropout(drop_p > 0.0f, drop_p, drop_seed, step_dev ? &step_dev->seed1 : nullptr);
   const float* alpha_dev = step_dev ? &step_dev->alpha : nullptr;
   const int E4 = E / 4;
   prof_set_group(0);
   if (prof_on()) prof_begin(T_SCATTER, st);
-  EBK_CUDA(cudaMemsetAsync(count, 0, ((size_t)2 * V + 64) * sizeof(int), st));
+  TokenCsr csr;
+  EBK_TRY(token_csr_build(R, V, tok, workspace, &csr, st));
+  int *count = csr.count, *offset = csr.offset, *perm = csr.perm;
   if (R > 0) {
-    tok_count_kernel<<<(R + 255) / 256, 256, 0, st>>>(R, V, tok, count);
-    EBK_LAUNCH_CHECK();
-  }
-  tok_offset_kernel<<<ceil_div(V, SCAN_T * SCAN_PER_T), SCAN_T, 0, st>>>(V, count, offset, total);
-  EBK_LAUNCH_CHECK();
-  if (R > 0) {
-    tok_fill_kernel<<<(R + 255) / 256, 256, 0, st>>>(R, V, tok, offset, cursor, perm);
-    EBK_LAUNCH_CHECK();
     heavy_scatter_kernel<<<(unsigned)(((long)R * 32 + 255) / 256), 256, 0, st>>>(
         R, E4, V, tok, count, reinterpret_cast<const float4*>(dX), drop, d_table);
     EBK_LAUNCH_CHECK();

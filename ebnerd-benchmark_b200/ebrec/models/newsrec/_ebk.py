@@ -28,7 +28,7 @@ SYMBOLS = [
     "ebk_join_deferred", "ebk_seqenc_uses_tma", "ebk_ipc_export", "ebk_ipc_open", "ebk_memcpy_async",
     "ebk_score_softmax_ce", "ebk_score_loss", "ebk_score_sigmoid", "ebk_adam_keras_step", "ebk_adam_keras_step_p",
     "ebk_embed_adam_step_p", "ebk_dp_token_flags", "ebk_adam_pull_step",
-    "ebk_embed_adam_workspace_bytes", "ebk_embed_adam_step",
+    "ebk_embed_adam_workspace_bytes", "ebk_embed_adam_step", "ebk_token_csr_bytes",
     "ebk_dense_workspace_bytes", "ebk_dense_fwd", "ebk_dense_bwd", "ebk_dense_fwd_p", "ebk_dense_bwd_p", "ebk_sumsq_accum",
     "ebk_attlayer_workspace_bytes", "ebk_attlayer_fwd", "ebk_attlayer_bwd",
     "ebk_conv1d_workspace_bytes", "ebk_conv1d_fwd", "ebk_conv1d_bwd",
@@ -54,7 +54,8 @@ class SeqEncDesc(C.Structure):
 class SeqEncOpts(C.Structure):
     """Mirror of ebk_seqenc_opts (include/ebk.h): per-call options, nothing sticky."""
     _fields_ = [("defer_wgrad", C.c_int32), ("table_grad_event", C.c_void_p), ("peer_tables", C.POINTER(C.c_void_p)),
-                ("peer_world", C.c_int32), ("peer_shard_floats", C.c_size_t), ("step_dev", C.c_void_p)]
+                ("peer_world", C.c_int32), ("peer_shard_floats", C.c_size_t), ("step_dev", C.c_void_p),
+                ("token_csr_ws", C.c_void_p), ("token_csr_ws_bytes", C.c_size_t)]
 
 
 class DenseDesc(C.Structure):
@@ -142,6 +143,8 @@ def lib() -> C.CDLL:
     l.ebk_adam_pull_step.argtypes = [vp, vp, vp, C.POINTER(vp), vp, sz, i32, i32, i32, sz, sz, f32, vp, f64, f64, f32, vp]
     l.ebk_embed_adam_workspace_bytes.restype = sz
     l.ebk_embed_adam_workspace_bytes.argtypes = [i32, i32]
+    l.ebk_token_csr_bytes.restype = sz
+    l.ebk_token_csr_bytes.argtypes = [i32, i32]
     l.ebk_embed_adam_step.argtypes = [i32, i32, i32, vp, vp, f32, u64, vp, vp, vp, vp, f32, f64, f64, f32, vp, sz, vp]
     l.ebk_gemm.argtypes = [i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, f32, vp]
     l.ebk_gemm_tma.argtypes = [i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, f32, f32, vp]

@@ -200,6 +200,11 @@ class NRMSEngine:
         opts = None
         if training:
             opts = self._peer_opts()     # rank-sharded table: gather rows from their owners over NVLink
+            if opts is not None and os.environ.get("EBK_DP_CSR_GATHER", "1") != "0":
+                # remote rows: read each DISTINCT token's row once (token CSR built in this scratch by the forward)
+                need = lib.ebk_token_csr_bytes(N * self.T, self.V)
+                scratch = self._buf("tok_csr", (need,), dtype=torch.uint8)
+                opts.token_csr_ws, opts.token_csr_ws_bytes = C.c_void_p(scratch.data_ptr()), need
             if step_dev is not None:
                 opts = opts if opts is not None else _ebk.SeqEncOpts(0, None, None, 0, 0, None)
                 opts.step_dev = C.c_void_p(step_dev.data_ptr())

@@ -410,9 +410,9 @@ def test_device_feed_matches_host_feed():
 
 
 def test_peer_table_gather_paths_match_local_gather(monkeypatch):
-    """The rank-sharded-table gather (embed_rows_kernel<PEERS>, every 16-byte chunk read through its owner's
-    mapping) and its chunked, GEMM-pipelined variant, exercised on ONE GPU by mapping both 'ranks' to the local
-    table: loss and gradients must equal the plain local gather up to atomics order (same kernels downstream)."""
+    """The rank-sharded-table gather (every 16-byte chunk read through its owner's mapping), its token-CSR form (every
+    distinct id read once) and its chunked, GEMM-pipelined variant, exercised on ONE GPU by mapping both 'ranks' to the
+    local table: loss and gradients must equal the plain local gather up to atomics order (same kernels downstream)."""
     import ctypes as C
 
     from ebrec.models.newsrec import _ebk
@@ -420,11 +420,15 @@ def test_peer_table_gather_paths_match_local_gather(monkeypatch):
     V, E, nh, dh, att, B, H, C_, T = 3000, 32, 4, 8, 24, 32, 20, 5, 30     # R = 24 000 rows >= 4 * 4096
     rng = np.random.default_rng(8)
     P, his, pred, y = make_case(rng, V, E, nh, dh, att, B, H, C_, T)
+    his[:, :, -6:] = 0                       # a padding-like id with thousands of positions (> 32: per-position path)
+    pred[0, 0, :3], his[1, 2, 0] = V + 7, -1  # ids outside the table read a zero row
     lib = _ebk.lib()
     outs = []
-    for mode in ("local", "peers", "peers_chunked"):
+    # "peers": one read per position; "peers_csr" (the default under data parallel): token CSR, one read per distinct id
+    for mode in ("local", "peers", "peers_csr", "peers_chunked"):
         eng = make_engine(P, V, E, T, H, nh, dh, att, 0.2, 1e-3, 1, seed=2)
         tok, lab = eng.to_device_batch(his, pred, y)
+        monkeypatch.setenv("EBK_DP_CSR_GATHER", "1" if mode == "peers_csr" else "0")
         if mode == "peers_chunked":
             monkeypatch.setenv("EBK_DP_CHUNKED_GATHER", "1")
         else:
