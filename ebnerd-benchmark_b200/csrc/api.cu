@@ -341,6 +341,23 @@ extern "C" int ebk_seqenc_fwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
     const GemmEpilogue round_epi{nullptr, nullptr, 0, 1, none, 0, true};
     // opt-in (EBK_DP_CHUNKED_GATHER=1): measured on 2 GPUs it does not pay (5.81 vs 5.73 ms/step: the remote share
     // of the gather is small there and four partial GEMM waves cost more); not yet measured on 8
+    // the whole gather: plain (one read per position), or through a token CSR built in ebk_seqenc_opts.token_csr_ws (each
+    // distinct token's row read once: what pays when the rows are remote)
+    auto gather_rows = [&]() -> int {
+      if (tok != nullptr && opts != nullptr && opts->token_csr_ws != nullptr) {
+        EBK_CHECK_ARG(opts->token_csr_ws_bytes >= token_csr_bytes(R, d->V), "seqenc_fwd: token_csr_ws %zu < %zu bytes",
+                      opts->token_csr_ws_bytes, token_csr_bytes(R, d->V));
+        TokenCsr csr;
+        if (prof_on()) prof_begin(T_EMBED_GATHER, st);
+        EBK_TRY(token_csr_build(R, d->V, tok, opts->token_csr_ws, &csr, st));
+        EBK_TRY(embed_rows_csr(R, d->Din, d->V, tok, table_or_x, drop1, ws.xd, st, remote ? &peers : nullptr, csr));
+        if (prof_on()) prof_end(T_EMBED_GATHER, st);
+        return EBK_OK;
+      }
+      EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st,
+                                          remote ? &peers : nullptr));
+      return EBK_OK;
+    };
     const char* env_ch = getenv("EBK_DP_CHUNKED_GATHER");
     const bool env_chunked = env_ch != nullptr && atoi(env_ch) != 0;
     if (remote && env_chunked && R >= GATHER_CHUNKS * 4096) {
@@ -372,19 +389,7 @@ extern "C" int ebk_seqenc_fwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
       // ---- north-star kernel: gather -> [QKV projection + per-head softmax(QK^T/sqrt(dh))^T V in ONE tcgen05 kernel]:
       // the accumulator tile is whole sequences x whole heads (weights permuted head-major), the attention runs in the
       // GEMM epilogue from TMEM through shared memory, Q|K|V reach HBM only as the tiles the backward needs
-      if (tok != nullptr && opts != nullptr && opts->token_csr_ws != nullptr) {
-        // each distinct token's row once (ebk_seqenc_opts.token_csr_ws): what pays when the rows are remote
-        EBK_CHECK_ARG(opts->token_csr_ws_bytes >= token_csr_bytes(R, d->V), "seqenc_fwd: token_csr_ws %zu < %zu bytes",
-                      opts->token_csr_ws_bytes, token_csr_bytes(R, d->V));
-        TokenCsr csr;
-        if (prof_on()) prof_begin(T_EMBED_GATHER, st);
-        EBK_TRY(token_csr_build(R, d->V, tok, opts->token_csr_ws, &csr, st));
-        EBK_TRY(embed_rows_csr(R, d->Din, d->V, tok, table_or_x, drop1, ws.xd, st, remote ? &peers : nullptr, csr));
-        if (prof_on()) prof_end(T_EMBED_GATHER, st);
-      } else {
-        EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st,
-                                            remote ? &peers : nullptr));
-      }
+      EBK_TRY(gather_rows());
       EBK_TRY(permute_round_wqkv(ws.wqkv_p, Wqkv, d->Din, d->nh, d->dh, st));
       float* y0f = pool ? ws.y0 : out;
       EBK_PROF(T_QKV_FWD, qkv_attn_fused(ws.xd, d->Din, ws.wqkv_p, d->n_seq, d->L, d->nh, d->dh, ws.qkv, y0f,
@@ -392,8 +397,7 @@ extern "C" int ebk_seqenc_fwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
       if (!pool) return EBK_OK;
       goto attlayer;
     } else {
-      EBK_PROF(T_EMBED_GATHER, embed_rows(R, d->Din, d->V, tok, table_or_x, tok ? drop1 : none, ws.xd, st,
-                                          remote ? &peers : nullptr));
+      EBK_TRY(gather_rows());
       // (1) Q|K|V = dropout1(gather(table, tok)) . Wqkv        nrms.py:134-139, layers.py:214-230
       EBK_PROF(T_QKV_FWD, gemm_tma(ws.xd, d->Din, false, ws.wqkv_r, 3 * D, false, ws.qkv, 3 * D, R, 3 * D, d->Din, 0.0f,
                                    1.0f, st, -1, &round_epi));

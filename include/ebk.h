@@ -135,8 +135,8 @@ typedef struct {
   int32_t peer_world;
   size_t peer_shard_floats;
   const ebk_step_params* step_dev; /* DEVICE pointer or NULL: when set, seed1 / seed2 come from it, not from the arguments */
-  void* token_csr_ws;              /* DEVICE scratch of ebk_token_csr_bytes(n_seq * L, V) bytes or NULL: when set (forward,
-                                      fused projection + attention path), the token positions are grouped by id first and
+  void* token_csr_ws;              /* DEVICE scratch of ebk_token_csr_bytes(n_seq * L, V) bytes or NULL: when set (forward on the
+                                      all-TMA path, see ebk_seqenc_uses_tma), the token positions are grouped by id first and
                                       every DISTINCT table row is read once -- what pays when rows come from peer tables */
   size_t token_csr_ws_bytes;
 } ebk_seqenc_opts;
