@@ -419,8 +419,9 @@ extern "C" int ebk_seqenc_fwd_opts(const ebk_seqenc_desc* d, const ebk_seqenc_op
     if (!pool) return EBK_OK;
   attlayer:
     // (3) pre-activation of AttLayer2                                nrms.py:153-156, layers.py:65
+    static const int att_fwd_tall = getenv("EBK_ATT_FWD_TALL") ? atoi(getenv("EBK_ATT_FWD_TALL")) : -1;   // experiments
     EBK_PROF(T_ATT_GEMM_FWD, gemm_tma(ws.y0, D, false, ws.attw_r, d->att, false, ws.hbuf, d->att, R, d->att, D, 0.0f,
-                                      1.0f, st, -1));
+                                      1.0f, st, att_fwd_tall));
     // (4) tanh, .q, exp, normalise (+1e-7), pool                     layers.py:65-81
     EBK_PROF(T_POOL_FWD, attpool_fwd(d->n_seq, d->L, D, d->att, ws.y0, none, ws.hbuf, attb, attq, ws.w, out, st));
     return EBK_OK;

@@ -962,7 +962,29 @@ int gemm_tma(const float* A, int lda, bool transA, const float* B, int ldb, bool
   const bool has_epi = p.epi.rowscale != nullptr || p.epi.drop.on() || p.epi.round_out;
   EBK_CHECK_ARG(!has_epi || beta == 0.0f, "gemm_tma: a fused epilogue needs beta == 0");
   EBK_CHECK_ARG(!p.epi.drop.on() || p.epi.drop_ld % 4 == 0, "gemm_tma: dropout epilogue needs drop_ld %% 4 == 0");
-  const int ntn = ceil_div(N, bn_max);
+  int ntn = ceil_div(N, bn_max);
+  {
+    // Split-K problems (few tiles, long K: the QKV weight gradient is 3 x 5 tiles of 256 x 240 over K = 192 000): the
+    // split count is floor(SMs / tiles), so 15 tiles leave 13 of 148 SMs without a CTA.  One more tile column (3 x 6 tiles
+    // of 256 x 208, 8 splits = 144 CTAs) is 10 % slower as a kernel on its own (0.70 -> 0.78 ms) but the train step, where
+    // this GEMM runs on the side stream against the HBM-bound optimizer pass, is 0.07-0.1 ms FASTER (measured three times,
+    // profiles/r02_bench_ab.md calls 21 / 22; narrower tiles -- 176, 160, 128 -- lose again).  Taken when it lifts the
+    // CTA count above 95 % of the SMs.
+    static const int env_bn_bigk = getenv("EBK_GEMM_BN_BIGK") ? atoi(getenv("EBK_GEMM_BN_BIGK")) : -1;   // experiments: 0 = off
+    const long tm = ceil_div(M, BM * MT * (pair ? 2 : 1)), sms = g_sms / (pair ? 2 : 1);
+    auto ctas = [&](int ntn_) {
+      const int bn = ceil_div(ceil_div(N, ntn_), 16) * 16;
+      const long t = tm * ceil_div(N, bn);
+      long sk = t < sms ? sms / t : 1;
+      const long maxsplit = ceil_div(K, BK) / 8;
+      if (sk > maxsplit) sk = maxsplit;
+      return t * (sk < 1 ? 1 : sk);
+    };
+    if (env_bn_bigk > 0 && K >= 100000) ntn = ceil_div(N, env_bn_bigk);
+    else if (env_bn_bigk != 0 && bn_max == 256 && !has_epi && K >= 32768 && tm * ntn < sms && ctas(ntn) * 100 < sms * 95 &&
+             ctas(ntn + 1) * 100 >= sms * 95)
+      ntn += 1;
+  }
   p.BN = ceil_div(ceil_div(N, ntn), 16) * 16;
   p.tiles_n = ceil_div(N, p.BN);
   const int bn_cta = pair ? p.BN / 2 : p.BN;                       // B columns staged by one CTA
