@@ -159,8 +159,9 @@ def kernel_roofline(dom, prof, models, pk, step_prof_ms, world=1):
     if bound == "tensor":
         ach = amount / (ms * 1e-3) / 1e12
         return {**common, "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
-                "algorithmic_flops": amount,
-                "peak_source": f"{pk['src']} bf16 sustained (the kernel computes in tf32, nominally half the bf16 rate)"}
+                "algorithmic_flops": amount, "frac_of_tf32_rate": ach / (pk["tensor"] / 2),
+                "peak_source": f"{pk['src']} bf16 sustained (the kernel computes in tf32, nominally half the bf16 rate: "
+                               f"frac_of_tf32_rate = achieved / (peak / 2))"}
     ach = amount / (ms * 1e-3) / 1e9
     return {**common, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
             "algorithmic_bytes": amount, "peak_source": pk["src"]}
