@@ -175,6 +175,47 @@ def test_c_abi_header_is_plain_c():
     assert r.returncode == 0, r.stderr
 
 
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """The ctypes.Structure mirrors in _ebk.py against the C structs of include/ebk.h: same size, same field offsets
+    (a C program prints sizeof / offsetof; a field added on one side only shows up here, on CPU)."""
+    import ctypes as C
+    import shutil
+
+    from ebrec.models.newsrec import _ebk
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    pairs = {"ebk_seqenc_desc": _ebk.SeqEncDesc, "ebk_seqenc_opts": _ebk.SeqEncOpts, "ebk_dense_desc": _ebk.DenseDesc,
+             "ebk_attlayer_desc": _ebk.AttLayerDesc, "ebk_conv1d_desc": _ebk.Conv1dDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "ebk.h"}"', "int main(void) {"]
+    for cname, mirror in pairs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in mirror._fields_:
+            lines.append(f'  printf(" {fname}=%zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines.append('  printf("ebk_step_params %zu seed1=%zu seed2=%zu alpha=%zu\\n", sizeof(ebk_step_params), '
+                 'offsetof(ebk_step_params, seed1), offsetof(ebk_step_params, seed2), offsetof(ebk_step_params, alpha));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    r = subprocess.run([gcc, "-std=c99", "-o", str(exe), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    seen = {}
+    for line in out:
+        name, size, *fields = line.split()
+        seen[name] = (int(size), {f.split("=")[0]: int(f.split("=")[1]) for f in fields})
+    for cname, mirror in pairs.items():
+        size, offs = seen[cname]
+        assert C.sizeof(mirror) == size, (cname, C.sizeof(mirror), size)
+        for fname, _ in mirror._fields_:
+            assert getattr(mirror, fname).offset == offs[fname], (cname, fname)
+    # the engine writes ebk_step_params as three 8-byte words: seed1 | seed2 | alpha (float) + padding
+    assert seen["ebk_step_params"] == (24, {"seed1": 0, "seed2": 8, "alpha": 16})
+
+
 def test_product_path_fails_loudly_without_cuda():
     import torch
 
