@@ -2,7 +2,7 @@
 
 Run in the BUILD container only (needs /root/reference):
 
-    python tests/golden/make_reference_fixtures.py
+    python tests/golden/make_reference_fixtures.py          # EBK_FIXTURE_OUT=<dir>: write there instead of tests/golden
 
 TensorFlow is not installable here, so the reference files
     /root/reference/src/ebrec/models/newsrec/{layers,nrms,nrms_docvec,naml,base_model,model_config}.py
@@ -20,8 +20,11 @@ from pathlib import Path
 
 import numpy as np
 
+import os
+
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parents[1]
+OUT = Path(os.environ.get("EBK_FIXTURE_OUT", HERE))   # tests/test_cpu_reference_golden.py regenerates into a temp dir
 sys.path.insert(0, str(HERE))
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, "/root/reference/src")
@@ -109,7 +112,7 @@ def nrms_fixture(name, with_grads_full):
             out[f"w2_{k}"] = w
     SH._Phase.dropout_masks = None
     spread = float(np.ptp(out["logits"], axis=1).min())
-    np.savez_compressed(HERE / f"ref_nrms_{name}.npz", **out)
+    np.savez_compressed(OUT / f"ref_nrms_{name}.npz", **out)
     assert spread >= 1.0, f"{name}: logit spread {spread:.2f} < 1 would make the score gate vacuous"
     print(f"ref_nrms_{name}: loss {out['loss_nodrop']:.6f} / {out['loss_drop']:.6f}, min per-row logit spread {spread:.2f}")
 
@@ -128,7 +131,7 @@ def nrms_dense_fixture():
         out[f"g_{i}"] = g
     for i, w in enumerate(m.model.get_weights()):                               # moving statistics after the step
         out[f"w_after_{i}"] = w
-    np.savez_compressed(HERE / "ref_nrms_dense.npz", **out)
+    np.savez_compressed(OUT / "ref_nrms_dense.npz", **out)
     print(f"ref_nrms_dense: loss {loss:.6f}, {len(grads)} arrays")
 
 
@@ -146,7 +149,7 @@ def docvec_fixture():
         out[f"g_{i}"] = g
     for i, w in enumerate(m.model.get_weights()):
         out[f"w_after_{i}"] = w
-    np.savez_compressed(HERE / "ref_docvec.npz", **out)
+    np.savez_compressed(OUT / "ref_docvec.npz", **out)
     print(f"ref_docvec: loss {loss:.6f}, {len(grads)} arrays, shapes {[g.shape for g in grads]}")
 
 
@@ -176,7 +179,7 @@ def naml_fixture():
     for i, g in enumerate(grads):
         out[f"g_drop_{i}"] = g
     SH._Phase.dropout_masks = None
-    np.savez_compressed(HERE / "ref_naml.npz", **out)
+    np.savez_compressed(OUT / "ref_naml.npz", **out)
     print(f"ref_naml: loss {out['loss_nodrop']:.6f} / {out['loss_drop']:.6f}")
 
 
